@@ -1,0 +1,108 @@
+"""The oracle (oracle/pygp_oracle.py) against the committed reference outputs
+(tests/golden, written by oracle/make_golden.py from the unmodified reference),
+the known answers of SURVEY.md 8c, and the reference's own self-consistency
+checks (tests/test_kernels.py:53-85, tests/test_inference.py:105-112)."""
+
+import numpy as np
+import numpy.testing as nt
+import pytest
+import scipy.optimize as spop
+
+from oracle import ref_loader
+from oracle.cases import (KERNEL_CASES, GP_CASES, SURVEY_KAT, GP_SN, GP_MEAN,
+                          kernel_inputs, gp_inputs)
+from oracle.pygp_oracle import make_kernel, OExactGP, OFITC
+
+
+@pytest.mark.parametrize('name', sorted(KERNEL_CASES))
+def test_kernel_vs_golden(name, golden):
+    g = golden['kernels']
+    k = make_kernel(KERNEL_CASES[name])
+    x1, x2 = kernel_inputs(k.ndim)
+    nt.assert_array_equal(k.get_hyper(), g[name + '/hyper'])
+    nt.assert_allclose(k.get(x1, x2), g[name + '/get12'], rtol=1e-13, atol=1e-15)
+    nt.assert_allclose(k.get(x1), g[name + '/get11'], rtol=1e-13, atol=1e-15)
+    nt.assert_allclose(np.array(k.grad(x1, x2)), g[name + '/grad12'], rtol=1e-12, atol=1e-14)
+    nt.assert_allclose(np.array(k.grad(x1)), g[name + '/grad11'], rtol=1e-12, atol=1e-14)
+    nt.assert_allclose(k.dget(x1), g[name + '/dget'], rtol=1e-15)
+    nt.assert_allclose(np.array(k.dgrad(x1)), g[name + '/dgrad'], rtol=1e-15)
+    k2 = k.copy_with(g[name + '/hyper2'])
+    nt.assert_allclose(k2.get(x1, x2), g[name + '/get12_h2'], rtol=1e-13, atol=1e-15)
+    nt.assert_allclose(np.array(k2.grad(x1, x2)), g[name + '/grad12_h2'], rtol=1e-12, atol=1e-14)
+
+
+@pytest.mark.parametrize('name', sorted(KERNEL_CASES))
+def test_kernel_self_consistency(name):
+    # tests/test_kernels.py:53-85
+    k = make_kernel(KERNEL_CASES[name])
+    x1, x2 = kernel_inputs(k.ndim)
+    nt.assert_allclose(k.get(x1, x2), k.get(x2, x1).T)
+    nt.assert_allclose(np.array(k.grad(x1, x2)), np.array(k.grad(x2, x1)).swapaxes(1, 2))
+    nt.assert_allclose(k.get(x1), k.get(x1, x1))
+    nt.assert_allclose(np.array(k.dgrad(x1)), [np.diag(_) for _ in k.grad(x1)])
+    h = k.get_hyper()
+    f = lambda h_, a, b: k.copy_with(h_).get(a[None], b[None])[0, 0]
+    G2 = np.array([spop.approx_fprime(h, f, 1e-8, a, b) for a in x1 for b in x2])
+    G2 = G2.swapaxes(0, 1).reshape(-1, x1.shape[0], x2.shape[0])
+    nt.assert_allclose(np.array(k.grad(x1, x2)), G2, rtol=1e-6, atol=1e-6)
+
+
+def _build(name):
+    spec, N, d, fitc = GP_CASES[name]
+    X, y, Xs, U = gp_inputs(N, d, fitc)
+    k = make_kernel(spec)
+    gp = OFITC(GP_SN, k, GP_MEAN, U) if fitc else OExactGP(GP_SN, k, GP_MEAN)
+    gp.add_data(X, y)
+    return gp, Xs
+
+
+@pytest.mark.parametrize('name', sorted(GP_CASES))
+def test_gp_vs_golden(name, golden):
+    g = golden['gp']
+    gp, Xs = _build(name)
+    lZ, dlZ = gp.loglikelihood(True)
+    mu, s2 = gp.posterior(Xs)
+    nt.assert_allclose(lZ, g[name + '/lZ'], rtol=1e-12)
+    nt.assert_allclose(dlZ, g[name + '/dlZ'], rtol=1e-10, atol=1e-10)
+    nt.assert_allclose(mu, g[name + '/mu'], rtol=1e-12)
+    nt.assert_allclose(s2, g[name + '/s2'], rtol=1e-10, atol=1e-14)
+    gp.set_hyper(g[name + '/hyper2'])
+    lZ, dlZ = gp.loglikelihood(True)
+    nt.assert_allclose(lZ, g[name + '/lZ_h2'], rtol=1e-12)
+    nt.assert_allclose(dlZ, g[name + '/dlZ_h2'], rtol=1e-10, atol=1e-10)
+
+
+@pytest.mark.parametrize('name', sorted(SURVEY_KAT))
+def test_gp_vs_survey_kat(name):
+    lZ0, dlZ0, mu0, s20 = SURVEY_KAT[name]
+    gp, Xs = _build(name)
+    lZ, dlZ = gp.loglikelihood(True)
+    mu, s2 = gp.posterior(Xs)
+    nt.assert_allclose(lZ, lZ0, rtol=1e-10)
+    nt.assert_allclose(dlZ, dlZ0, rtol=1e-8, atol=1e-9)
+    nt.assert_allclose(mu, mu0, rtol=1e-10)
+    nt.assert_allclose(s2, s20, rtol=1e-9)
+
+
+@pytest.mark.parametrize('name', ['se_ard_3d', 'fitc_se_2d'])
+def test_gp_grad_fd(name):
+    # tests/test_inference.py:105-112
+    gp, _ = _build(name)
+    import copy
+    h = gp.get_hyper()
+
+    def f(h_):
+        g2 = copy.deepcopy(gp)
+        g2.set_hyper(h_)
+        return g2.loglikelihood()
+    _, g1 = gp.loglikelihood(True)
+    nt.assert_allclose(g1, spop.approx_fprime(h, f, 1e-8), rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason='reference tree absent (GPU box)')
+def test_live_reference():
+    """In the build container: the restatement equals the live reference."""
+    from oracle import make_golden
+    pygp = ref_loader.load()
+    make_golden.kernel_golden(pygp)
+    make_golden.gp_golden(pygp)
