@@ -1,0 +1,185 @@
+/*
+ * pygp_b200.h -- C ABI of libpygp_b200.so: the exact-GP hot path of
+ * mwhoffman/pygp on NVIDIA B200 (sm_100a).
+ *
+ * The reference has no FFI of its own; the seam this library sits behind is
+ * the pair of Python ABCs `Kernel` (pygp/kernels/_base.py:22-64) and `GP`
+ * (pygp/inference/_base.py:27-242).  Each entry point below names the
+ * reference method whose arithmetic it replaces.  INTEGRATION.md shows the
+ * ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - all arrays are C-order float64, all pointers are HOST pointers unless
+ *     the parameter is prefixed d_ (device pointer on the context's device);
+ *   - hyper-parameters are the reference's log-space vectors in get_hyper()
+ *     order; a GP vector is [log sn | kernel hypers | mean]
+ *     (pygp/inference/_base.py:91-105);
+ *   - return value: 0 = ok; > 0 = LAPACK-style info, the order of the leading
+ *     minor that is not positive definite (the reference raises
+ *     numpy.linalg.LinAlgError from scipy.linalg.cholesky, exact.py:54);
+ *     < 0 = PGP_E_* (bad argument / CUDA failure); pgp_last_error() explains;
+ *   - calls on one context are serialised by the caller (the reference is not
+ *     thread-safe either); every call is synchronous w.r.t. its outputs.
+ *   - there is NO CPU fallback: without a CUDA device pgp_ctx_create fails.
+ */
+#ifndef PYGP_B200_H
+#define PYGP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PGP_ABI_VERSION 1
+
+#define PGP_MAX_PARTS 8     /* leaf kernels in one composite            */
+#define PGP_MAX_OPS   16    /* postfix program length                   */
+#define PGP_MAX_DIM   64    /* input dimensions                         */
+#define PGP_MAX_HYPER 96    /* kernel hyper-parameters                  */
+
+#define PGP_E_ARG    (-1)   /* bad argument            -> ValueError    */
+#define PGP_E_CUDA   (-2)   /* CUDA runtime failure    -> RuntimeError  */
+#define PGP_E_NOMEM  (-3)   /* device allocation failed-> MemoryError   */
+#define PGP_E_STATE  (-4)   /* call out of order       -> RuntimeError  */
+
+/* leaf kernel types: pygp/kernels/{se,matern,periodic,rq}.py */
+enum { PGP_SE = 0, PGP_MATERN1 = 1, PGP_MATERN3 = 2, PGP_MATERN5 = 3,
+       PGP_PERIODIC = 4, PGP_RQ = 5 };
+/* postfix ops: PUSH leaf `arg`; SUM / PROD of the top `arg` stack entries
+ * (pygp/kernels/_combo.py:103-146) */
+enum { PGP_OP_PUSH = 0, PGP_OP_SUM = 1, PGP_OP_PROD = 2 };
+
+typedef struct {
+    int32_t type;          /* PGP_SE ...                                     */
+    int32_t iso;           /* 1: one length-scale for all ndim inputs        */
+    int32_t hyper_offset;  /* first hyper of this leaf in the kernel vector  */
+    int32_t nhyper;        /* SE/Matern: 1+nell; RQ: 2+nell; Periodic: 3     */
+} pgp_part;
+
+typedef struct { int32_t op; int32_t arg; } pgp_op;
+
+/* A kernel as data (no callbacks): leaves + postfix program.  Hyper values
+ * travel separately, so one spec serves every set_hyper() call. */
+typedef struct {
+    int32_t ndim;
+    int32_t nhyper;
+    int32_t n_parts;
+    int32_t n_ops;
+    pgp_part parts[PGP_MAX_PARTS];
+    pgp_op   ops[PGP_MAX_OPS];
+} pgp_kernel_spec;
+
+typedef struct pgp_ctx   pgp_ctx;     /* one per device: stream + workspaces  */
+typedef struct pgp_model pgp_model;   /* ExactGP state resident in HBM        */
+typedef struct pgp_fitc  pgp_fitc;    /* FITC state resident in HBM           */
+
+/* ---- context ------------------------------------------------------------ */
+int  pgp_abi_version(void);
+int  pgp_ctx_create(int device, pgp_ctx** out);
+void pgp_ctx_destroy(pgp_ctx* ctx);
+const char* pgp_last_error(pgp_ctx* ctx);          /* ctx may be NULL */
+void* pgp_ctx_stream(pgp_ctx* ctx);                /* cudaStream_t all work runs on */
+int  pgp_ctx_sync(pgp_ctx* ctx);
+/* kernels launched by this context since creation (bench.py gpu_launches) */
+int64_t pgp_ctx_launch_count(pgp_ctx* ctx);
+/* per-class device timing with CUDA events on the context stream.
+ * classes: 0 gemm(DMMA) 1 gram 2 trace 3 potrf_base 4 trsm_base 5 other */
+#define PGP_PROF_CLASSES 6
+int  pgp_ctx_profile(pgp_ctx* ctx, int enable);    /* enable also resets */
+int  pgp_ctx_profile_read(pgp_ctx* ctx, int cls, int64_t* launches,
+                          double* ms, double* work /* flops or bytes */);
+
+/* ---- Kernel interface: pygp/kernels/_base.py:31-58 ------------------------ */
+/* Kernel.get(X1, X2=None)  (se.py:53, matern.py:69, periodic.py:53, rq.py:56,
+ * _combo.py:106,126).  X2 == NULL means X2 = X1.  out: (n1, n2). */
+int pgp_gram(pgp_ctx* ctx, const pgp_kernel_spec* spec, const double* hyp,
+             const double* X1, int64_t n1, const double* X2, int64_t n2,
+             double* out);
+/* Kernel.grad(X1, X2=None) (se.py:57, matern.py:76, periodic.py:61, rq.py:65,
+ * _combo.py:114,130).  k_index >= 0: that hyper's matrix, out (n1, n2);
+ * k_index == -1: all of them, out (nhyper, n1, n2) in get_hyper() order. */
+int pgp_gram_grad(pgp_ctx* ctx, const pgp_kernel_spec* spec, const double* hyp,
+                  const double* X1, int64_t n1, const double* X2, int64_t n2,
+                  int32_t k_index, double* out);
+/* Kernel.dget(X) (se.py:68 ...): out (n). */
+int pgp_dget(pgp_ctx* ctx, const pgp_kernel_spec* spec, const double* hyp,
+             const double* X, int64_t n, double* out);
+/* Kernel.dgrad(X) (se.py:71 ...): out (nhyper, n). */
+int pgp_dgrad(pgp_ctx* ctx, const pgp_kernel_spec* spec, const double* hyp,
+              const double* X, int64_t n, double* out);
+/* same as pgp_gram with operands and result resident in HBM (bench.py `value`) */
+int pgp_gram_dev(pgp_ctx* ctx, const pgp_kernel_spec* spec, const double* hyp,
+                 const double* d_X1, int64_t n1, const double* d_X2, int64_t n2,
+                 double* d_out);
+
+/* ---- ExactGP: pygp/inference/exact.py ------------------------------------- */
+/* GP.add_data first call (_base.py:120-131): upload X (n, ndim), y (n). */
+int pgp_exact_create(pgp_ctx* ctx, const pgp_kernel_spec* spec,
+                     const double* X, const double* y, int64_t n,
+                     pgp_model** out);
+/* GP.add_data later calls (_base.py:132-141, full-update branch): append rows;
+ * the caller follows with pgp_exact_update. */
+int pgp_exact_append(pgp_model* m, const double* X, const double* y, int64_t n_new);
+/* Parameterized.copy (utils/models.py:47-55): deep copy of the device state. */
+int pgp_model_clone(const pgp_model* m, pgp_model** out);
+void pgp_model_destroy(pgp_model* m);
+int64_t pgp_model_ndata(const pgp_model* m);
+/* ExactGP._update (exact.py:50-55): K = k(X,X) + sn2 I; R = chol(K);
+ * a = R^-T (y - mean).  hyp = [log sn | kernel | mean].  No jitter, no retry
+ * (as the reference): returns info > 0 when K is not positive definite. */
+int pgp_exact_update(pgp_model* m, const double* hyp);
+/* ExactGP.loglikelihood(grad) (exact.py:118-143).  dlZ: (1 + nhyper_k + 1) or NULL. */
+int pgp_exact_loglike(pgp_model* m, int want_grad, double* lZ, double* dlZ);
+/* ExactGP._marg_posterior(X, grad=False) (exact.py:81-97): mu (ms), s2 (ms). */
+int pgp_exact_predict(pgp_model* m, const double* Xs, int64_t ms,
+                      double* mu, double* s2);
+/* device-resident test points / outputs (bench.py `value`, sharded predict) */
+int pgp_exact_predict_dev(pgp_model* m, const double* d_Xs, int64_t ms,
+                          double* d_mu, double* d_s2);
+/* the factor as the reference holds it: upper R (n, n) C-order, a (n) */
+int pgp_exact_get_factor(pgp_model* m, double* R_out, double* a_out);
+
+/* ---- batched small-N path: learning/sampling.py:146, meta/mcmc.py:75-93 ---- */
+/* B independent ExactGP._update + loglikelihood() sharing X, y.
+ * hyps (B, nhyper_gp); lZ (B); info (B) per-problem potrf info (0 = ok). */
+int pgp_batched_loglike(pgp_ctx* ctx, const pgp_kernel_spec* spec,
+                        const double* X, const double* y, int64_t n,
+                        const double* hyps, int64_t B,
+                        double* lZ, int32_t* info);
+/* B independent posteriors at the same test points: mu, s2 are (B, ms). */
+int pgp_batched_predict(pgp_ctx* ctx, const pgp_kernel_spec* spec,
+                        const double* X, const double* y, int64_t n,
+                        const double* hyps, int64_t B,
+                        const double* Xs, int64_t ms,
+                        double* mu, double* s2, int32_t* info);
+
+/* ---- FITC: pygp/inference/fitc.py ----------------------------------------- */
+int pgp_fitc_create(pgp_ctx* ctx, const pgp_kernel_spec* spec,
+                    const double* U, int64_t nu,
+                    const double* X, const double* y, int64_t n,
+                    pgp_fitc** out);
+void pgp_fitc_destroy(pgp_fitc* f);
+/* FITC._update (fitc.py:66-100) */
+int pgp_fitc_update(pgp_fitc* f, const double* hyp);
+/* FITC.loglikelihood(grad) (fitc.py:167-232) */
+int pgp_fitc_loglike(pgp_fitc* f, int want_grad, double* lZ, double* dlZ);
+/* FITC._marg_posterior(X, grad=False) (fitc.py:122-142) */
+int pgp_fitc_predict(pgp_fitc* f, const double* Xs, int64_t ms,
+                     double* mu, double* s2);
+
+/* ---- building blocks exported for tests and profiling ---------------------- */
+/* C (m, n) = beta C + alpha A (m, k) B (n, k)^T on device buffers, row-major,
+ * through the DMMA kernel; tri != 0 skips tiles strictly above the diagonal. */
+int pgp_dev_gemm_nt(pgp_ctx* ctx, int64_t m, int64_t n, int64_t k,
+                    double alpha, const double* d_A, int64_t lda,
+                    const double* d_B, int64_t ldb,
+                    double beta, double* d_C, int64_t ldc, int tri);
+/* in-place lower Cholesky of a device matrix (n, n) row-major with `extra`
+ * further rows below it that receive the same right-solves (row n = r -> a). */
+int pgp_dev_potrf(pgp_ctx* ctx, double* d_F, int64_t n, int64_t ld, int64_t extra);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYGP_B200_H */

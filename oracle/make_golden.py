@@ -114,6 +114,11 @@ def main():
     np.savez_compressed(os.path.join(GOLDEN, 'kernels.npz'), **kg)
     gg = gp_golden(pygp)
     np.savez_compressed(os.path.join(GOLDEN, 'gp.npz'), **gg)
+    # the reference's own demo data set (pygp/demos/xy.npz, X:(20,1) y:(20,)), used by
+    # its tests/test_learning.py:26-30 -- a data fixture, copied verbatim
+    import shutil
+    shutil.copyfile(os.path.join(ref_loader.REFERENCE_ROOT, 'pygp', 'demos', 'xy.npz'),
+                    os.path.join(GOLDEN, 'xy.npz'))
     print('wrote %d kernel arrays, %d gp arrays to %s' % (len(kg), len(gg), GOLDEN))
 
 

@@ -1,0 +1,801 @@
+// capi.cu -- extern "C" entry points of libpygp_b200.so (include/pygp_b200.h):
+// context, Kernel.get/grad/dget/dgrad, the ExactGP model and the batched path.
+
+#include <algorithm>
+#include <cmath>
+#include <new>
+
+#include "chol.cuh"
+#include "gram.cuh"
+#include "spec.cuh"
+
+using namespace pgp;
+
+static thread_local std::string g_last_error;
+
+// ---------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------
+extern "C" int pgp_abi_version(void) { return PGP_ABI_VERSION; }
+
+extern "C" int pgp_ctx_create(int device, pgp_ctx** out) {
+    if (!out) return PGP_E_ARG;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        g_last_error = std::string("no CUDA device available: ") + cudaGetErrorString(e) +
+                       " (libpygp_b200 has no CPU fallback)";
+        cudaGetLastError();
+        return PGP_E_CUDA;
+    }
+    if (device < 0 || device >= count) {
+        g_last_error = "device index out of range";
+        return PGP_E_ARG;
+    }
+    pgp_ctx* ctx = new (std::nothrow) pgp_ctx();
+    if (!ctx) return PGP_E_NOMEM;
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        g_last_error = std::string("CUDA context setup failed: ") + cudaGetErrorString(e);
+        delete ctx;
+        return PGP_E_CUDA;
+    }
+    if (prop.major < 10) {
+        g_last_error = "libpygp_b200 is built for sm_100a (B200) only; found " + std::string(prop.name);
+        cudaStreamDestroy(ctx->stream);
+        delete ctx;
+        return PGP_E_CUDA;
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    ctx->h_pin_doubles = 4096;
+    if ((e = cudaMallocHost((void**)&ctx->h_pin, ctx->h_pin_doubles * sizeof(double))) != cudaSuccess) {
+        g_last_error = std::string("cudaMallocHost failed: ") + cudaGetErrorString(e);
+        cudaStreamDestroy(ctx->stream);
+        delete ctx;
+        return PGP_E_CUDA;
+    }
+    *out = ctx;
+    return 0;
+}
+
+static void prof_clear(pgp_ctx* ctx) {
+    for (auto& r : ctx->prof) {
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+    }
+    ctx->prof.clear();
+}
+
+extern "C" void pgp_ctx_destroy(pgp_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    prof_clear(ctx);
+    if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" const char* pgp_last_error(pgp_ctx* ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
+extern "C" void* pgp_ctx_stream(pgp_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+extern "C" int pgp_ctx_sync(pgp_ctx* ctx) {
+    if (!ctx) return PGP_E_ARG;
+    PGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+extern "C" int64_t pgp_ctx_launch_count(pgp_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int pgp_ctx_profile(pgp_ctx* ctx, int enable) {
+    if (!ctx) return PGP_E_ARG;
+    PGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    prof_clear(ctx);
+    ctx->profile = enable != 0;
+    return 0;
+}
+
+extern "C" int pgp_ctx_profile_read(pgp_ctx* ctx, int cls, int64_t* launches, double* ms, double* work) {
+    if (!ctx || cls < 0 || cls >= PGP_PROF_CLASSES) return PGP_E_ARG;
+    PGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    int64_t nl = 0;
+    double t = 0.0, w = 0.0;
+    for (auto& r : ctx->prof) {
+        if (r.cls != cls) continue;
+        float f = 0.f;
+        PGP_CUDA(ctx, cudaEventElapsedTime(&f, r.e0, r.e1));
+        t += f;
+        w += r.work;
+        ++nl;
+    }
+    if (launches) *launches = nl;
+    if (ms) *ms = t;
+    if (work) *work = w;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// helpers
+// ---------------------------------------------------------------------------
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    template <class T> T* as() { return reinterpret_cast<T*>(p); }
+};
+
+template <class T>
+int alloc(pgp_ctx* ctx, DevBuf& b, size_t count) {
+    T* p = nullptr;
+    PGP_TRY(dev_alloc(ctx, &p, std::max<size_t>(count, 1)));
+    b.p = p;
+    return 0;
+}
+
+int single_type(const pgp_kernel_spec* s) { return s->n_parts == 1 ? s->parts[0].type : -1; }
+
+int upload_spec(pgp_ctx* ctx, const DevSpec& h, DevSpec* d) {
+    // DevSpec is ~5 KB: stage through pageable memory (synchronous w.r.t. host)
+    PGP_CUDA(ctx, cudaMemcpyAsync(d, &h, sizeof(DevSpec), cudaMemcpyHostToDevice, ctx->stream));
+    PGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int set_device(pgp_ctx* ctx) {
+    PGP_CUDA(ctx, cudaSetDevice(ctx->device));
+    return 0;
+}
+
+// shared implementation of Kernel.get / Kernel.grad on device operands
+int gram_device(pgp_ctx* ctx, const pgp_kernel_spec* spec, const double* hyp, const double* d_X1, int64_t n1,
+                const double* d_X2, int64_t n2, int hidx, double* d_out, int64_t ldo) {
+    DevSpec hs;
+    PGP_TRY(compile_spec(spec, hyp, 0.0, 0.0, &hs, &ctx->err));
+    DevBuf dspec, z1, z2;
+    PGP_TRY(alloc<DevSpec>(ctx, dspec, 1));
+    PGP_TRY(upload_spec(ctx, hs, dspec.as<DevSpec>()));
+    const int d = spec->ndim, np = spec->n_parts;
+    PGP_TRY(alloc<double>(ctx, z1, (size_t)np * n1 * d));
+    PGP_TRY(launch_scale(ctx, dspec.as<DevSpec>(), d_X1, n1, d, np, z1.as<double>(), 1));
+    const double* Z2 = z1.as<double>();
+    if (d_X2) {
+        PGP_TRY(alloc<double>(ctx, z2, (size_t)np * n2 * d));
+        PGP_TRY(launch_scale(ctx, dspec.as<DevSpec>(), d_X2, n2, d, np, z2.as<double>(), 1));
+        Z2 = z2.as<double>();
+    }
+    GramArgs g;
+    g.spec = dspec.as<DevSpec>();
+    g.Z1 = z1.as<double>();
+    g.Z2 = Z2;
+    g.n1 = n1;
+    g.n2 = n2;
+    g.ndim = d;
+    g.n_parts = np;
+    g.out = d_out;
+    g.ldo = ldo;
+    g.hidx = hidx;
+    g.single_type = single_type(spec);
+    PGP_TRY(launch_gram(ctx, g));
+    PGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// Kernel interface
+// ---------------------------------------------------------------------------
+static int gram_host(pgp_ctx* ctx, const pgp_kernel_spec* spec, const double* hyp, const double* X1, int64_t n1,
+                     const double* X2, int64_t n2, int hidx_first, int hidx_count, double* out) {
+    if (!ctx) return PGP_E_ARG;
+    if (!spec || !hyp || !X1 || !out || n1 < 0 || n2 < 0) return ctx->fail(PGP_E_ARG, "null or negative argument");
+    PGP_TRY(set_device(ctx));
+    if (!X2) n2 = n1;
+    if (n1 == 0 || n2 == 0) return 0;
+    const int d = spec->ndim;
+    DevBuf x1, x2, o;
+    PGP_TRY(alloc<double>(ctx, x1, (size_t)n1 * d));
+    PGP_CUDA(ctx, cudaMemcpyAsync(x1.p, X1, sizeof(double) * n1 * d, cudaMemcpyHostToDevice, ctx->stream));
+    if (X2) {
+        PGP_TRY(alloc<double>(ctx, x2, (size_t)n2 * d));
+        PGP_CUDA(ctx, cudaMemcpyAsync(x2.p, X2, sizeof(double) * n2 * d, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    const int64_t ldo = round_up(n2, 2);
+    PGP_TRY(alloc<double>(ctx, o, (size_t)n1 * ldo));
+    for (int h = 0; h < hidx_count; ++h) {
+        int hidx = hidx_first < 0 ? -1 : hidx_first + h;
+        PGP_TRY(gram_device(ctx, spec, hyp, x1.as<double>(), n1, X2 ? x2.as<double>() : nullptr, n2, hidx,
+                            o.as<double>(), ldo));
+        PGP_CUDA(ctx, cudaMemcpy2DAsync(out + (size_t)h * n1 * n2, sizeof(double) * n2, o.p, sizeof(double) * ldo,
+                                        sizeof(double) * n2, n1, cudaMemcpyDeviceToHost, ctx->stream));
+        PGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return 0;
+}
+
+extern "C" int pgp_gram(pgp_ctx* ctx, const pgp_kernel_spec* spec, const double* hyp, const double* X1, int64_t n1,
+                        const double* X2, int64_t n2, double* out) {
+    return gram_host(ctx, spec, hyp, X1, n1, X2, n2, -1, 1, out);
+}
+
+extern "C" int pgp_gram_grad(pgp_ctx* ctx, const pgp_kernel_spec* spec, const double* hyp, const double* X1,
+                             int64_t n1, const double* X2, int64_t n2, int32_t k_index, double* out) {
+    if (!ctx) return PGP_E_ARG;
+    if (!spec) return ctx->fail(PGP_E_ARG, "null spec");
+    if (k_index >= spec->nhyper || k_index < -1) return ctx->fail(PGP_E_ARG, "k_index out of range");
+    if (k_index >= 0) return gram_host(ctx, spec, hyp, X1, n1, X2, n2, k_index, 1, out);
+    return gram_host(ctx, spec, hyp, X1, n1, X2, n2, 0, spec->nhyper, out);
+}
+
+extern "C" int pgp_gram_dev(pgp_ctx* ctx, const pgp_kernel_spec* spec, const double* hyp, const double* d_X1,
+                            int64_t n1, const double* d_X2, int64_t n2, double* d_out) {
+    if (!ctx) return PGP_E_ARG;
+    if (!spec || !hyp || !d_X1 || !d_out) return ctx->fail(PGP_E_ARG, "null argument");
+    PGP_TRY(set_device(ctx));
+    if (!d_X2) n2 = n1;
+    return gram_device(ctx, spec, hyp, d_X1, n1, d_X2, n2, -1, d_out, n2);
+}
+
+static int diag_host(pgp_ctx* ctx, const pgp_kernel_spec* spec, const double* hyp, int64_t n, int hmode,
+                     double* out) {
+    if (!ctx) return PGP_E_ARG;
+    if (!spec || !hyp || !out || n < 0) return ctx->fail(PGP_E_ARG, "null or negative argument");
+    PGP_TRY(set_device(ctx));
+    if (n == 0) return 0;
+    DevSpec hs;
+    PGP_TRY(compile_spec(spec, hyp, 0.0, 0.0, &hs, &ctx->err));
+    DevBuf dspec, o;
+    PGP_TRY(alloc<DevSpec>(ctx, dspec, 1));
+    PGP_TRY(upload_spec(ctx, hs, dspec.as<DevSpec>()));
+    size_t rows = hmode ? spec->nhyper : 1;
+    PGP_TRY(alloc<double>(ctx, o, rows * n));
+    PGP_TRY(launch_diag(ctx, dspec.as<DevSpec>(), n, hmode, spec->nhyper, o.as<double>()));
+    PGP_CUDA(ctx, cudaMemcpyAsync(out, o.p, sizeof(double) * rows * n, cudaMemcpyDeviceToHost, ctx->stream));
+    PGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int pgp_dget(pgp_ctx* ctx, const pgp_kernel_spec* spec, const double* hyp, const double* X, int64_t n,
+                        double* out) {
+    (void)X;  // stationary kernels: k(x, x) does not depend on x (se.py:68-69)
+    return diag_host(ctx, spec, hyp, n, 0, out);
+}
+
+extern "C" int pgp_dgrad(pgp_ctx* ctx, const pgp_kernel_spec* spec, const double* hyp, const double* X, int64_t n,
+                         double* out) {
+    (void)X;
+    return diag_host(ctx, spec, hyp, n, 1, out);
+}
+
+// ---------------------------------------------------------------------------
+// ExactGP model
+// ---------------------------------------------------------------------------
+struct pgp_model {
+    pgp_ctx* ctx = nullptr;
+    pgp_kernel_spec spec;
+    int64_t n = 0;
+    int ndim = 0;
+    int64_t ld = 0;
+    double* d_X = nullptr;
+    double* d_y = nullptr;
+    double* d_Z = nullptr;       // [parts][n][ndim]
+    DevSpec* d_spec = nullptr;
+    double* d_F = nullptr;       // (n + 1, ld): L below/on the diagonal, a in row n
+    double* d_G = nullptr;       // (n, ld): V = L^-T (upper); allocated on first gradient
+    double* d_H = nullptr;       // (n, ld): K~^-1 (lower)
+    double* d_alpha = nullptr;   // (n)
+    double* d_partials = nullptr;
+    double* d_res = nullptr;     // [0] lZ, [1..] dlZ
+    int* d_info = nullptr;
+    double* d_Bc = nullptr;      // predict chunk (bc_rows, ld)
+    int64_t bc_rows = 0;
+    DevSpec hspec;
+    bool factored = false;
+    double lZ = 0.0;
+    int info = 0;
+};
+
+namespace {
+
+void model_free_work(pgp_model* m) {
+    cudaFree(m->d_Z); m->d_Z = nullptr;
+    cudaFree(m->d_F); m->d_F = nullptr;
+    cudaFree(m->d_G); m->d_G = nullptr;
+    cudaFree(m->d_H); m->d_H = nullptr;
+    cudaFree(m->d_alpha); m->d_alpha = nullptr;
+    cudaFree(m->d_partials); m->d_partials = nullptr;
+    cudaFree(m->d_Bc); m->d_Bc = nullptr;
+    m->bc_rows = 0;
+    m->factored = false;
+}
+
+int model_alloc_work(pgp_model* m) {
+    pgp_ctx* ctx = m->ctx;
+    m->ld = lead_dim(m->n);
+    PGP_TRY(dev_alloc(ctx, &m->d_Z, (size_t)m->spec.n_parts * m->n * m->ndim));
+    PGP_TRY(dev_alloc(ctx, &m->d_F, (size_t)(m->n + 1) * m->ld));
+    PGP_TRY(dev_alloc(ctx, &m->d_alpha, (size_t)m->n));
+    return 0;
+}
+
+int model_upload(pgp_model* m, const double* X, const double* y, int64_t n_old, int64_t n_new) {
+    pgp_ctx* ctx = m->ctx;
+    const int d = m->ndim;
+    int64_t n = n_old + n_new;
+    double *nx = nullptr, *ny = nullptr;
+    PGP_TRY(dev_alloc(ctx, &nx, (size_t)n * d));
+    PGP_TRY(dev_alloc(ctx, &ny, (size_t)n));
+    if (n_old) {
+        PGP_CUDA(ctx, cudaMemcpyAsync(nx, m->d_X, sizeof(double) * n_old * d, cudaMemcpyDeviceToDevice, ctx->stream));
+        PGP_CUDA(ctx, cudaMemcpyAsync(ny, m->d_y, sizeof(double) * n_old, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    PGP_CUDA(ctx, cudaMemcpyAsync(nx + n_old * d, X, sizeof(double) * n_new * d, cudaMemcpyHostToDevice, ctx->stream));
+    PGP_CUDA(ctx, cudaMemcpyAsync(ny + n_old, y, sizeof(double) * n_new, cudaMemcpyHostToDevice, ctx->stream));
+    PGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(m->d_X);
+    cudaFree(m->d_y);
+    m->d_X = nx;
+    m->d_y = ny;
+    m->n = n;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int pgp_exact_create(pgp_ctx* ctx, const pgp_kernel_spec* spec, const double* X, const double* y,
+                                int64_t n, pgp_model** out) {
+    if (!ctx) return PGP_E_ARG;
+    if (!spec || !X || !y || !out || n <= 0) return ctx->fail(PGP_E_ARG, "null argument or n <= 0");
+    PGP_TRY(set_device(ctx));
+    *out = nullptr;
+    // validate the spec once with neutral hypers
+    {
+        std::vector<double> h0(std::max(spec->nhyper, 1), 0.0);
+        DevSpec tmp;
+        if (spec->nhyper < 1 || spec->nhyper > kMaxHyper) return ctx->fail(PGP_E_ARG, "nhyper out of range");
+        PGP_TRY(compile_spec(spec, h0.data(), 1.0, 0.0, &tmp, &ctx->err));
+    }
+    if (spec->n_parts * spec->ndim > 192) return ctx->fail(PGP_E_ARG, "n_parts * ndim > 192 not supported");
+    pgp_model* m = new (std::nothrow) pgp_model();
+    if (!m) return PGP_E_NOMEM;
+    m->ctx = ctx;
+    m->spec = *spec;
+    m->ndim = spec->ndim;
+    int rc = model_upload(m, X, y, 0, n);
+    if (!rc) rc = model_alloc_work(m);
+    if (!rc) rc = dev_alloc(ctx, &m->d_spec, 1);
+    if (!rc) rc = dev_alloc(ctx, &m->d_res, (size_t)kMaxHyper + 4);
+    if (!rc) rc = dev_alloc(ctx, &m->d_info, 1);
+    if (rc) {
+        pgp_model_destroy(m);
+        return rc;
+    }
+    *out = m;
+    return 0;
+}
+
+extern "C" int pgp_exact_append(pgp_model* m, const double* X, const double* y, int64_t n_new) {
+    if (!m) return PGP_E_ARG;
+    pgp_ctx* ctx = m->ctx;
+    if (!X || !y || n_new <= 0) return ctx->fail(PGP_E_ARG, "null argument or n_new <= 0");
+    PGP_TRY(set_device(ctx));
+    int64_t n_old = m->n;
+    model_free_work(m);
+    PGP_TRY(model_upload(m, X, y, n_old, n_new));
+    return model_alloc_work(m);
+}
+
+extern "C" void pgp_model_destroy(pgp_model* m) {
+    if (!m) return;
+    cudaSetDevice(m->ctx->device);
+    cudaStreamSynchronize(m->ctx->stream);
+    model_free_work(m);
+    cudaFree(m->d_X);
+    cudaFree(m->d_y);
+    cudaFree(m->d_spec);
+    cudaFree(m->d_res);
+    cudaFree(m->d_info);
+    delete m;
+}
+
+extern "C" int64_t pgp_model_ndata(const pgp_model* m) { return m ? m->n : 0; }
+
+extern "C" int pgp_model_clone(const pgp_model* src, pgp_model** out) {
+    if (!src || !out) return PGP_E_ARG;
+    pgp_ctx* ctx = src->ctx;
+    PGP_TRY(set_device(ctx));
+    *out = nullptr;
+    pgp_model* m = new (std::nothrow) pgp_model();
+    if (!m) return PGP_E_NOMEM;
+    m->ctx = ctx;
+    m->spec = src->spec;
+    m->ndim = src->ndim;
+    m->n = src->n;
+    m->hspec = src->hspec;
+    m->factored = src->factored;
+    m->lZ = src->lZ;
+    m->info = src->info;
+    const int64_t n = src->n;
+    const int d = src->ndim;
+    int rc = dev_alloc(ctx, &m->d_X, (size_t)n * d);
+    if (!rc) rc = dev_alloc(ctx, &m->d_y, (size_t)n);
+    if (!rc) rc = model_alloc_work(m);
+    if (!rc) rc = dev_alloc(ctx, &m->d_spec, 1);
+    if (!rc) rc = dev_alloc(ctx, &m->d_res, (size_t)kMaxHyper + 4);
+    if (!rc) rc = dev_alloc(ctx, &m->d_info, 1);
+    if (rc) {
+        pgp_model_destroy(m);
+        return rc;
+    }
+    cudaStream_t s = ctx->stream;
+    cudaError_t e = cudaMemcpyAsync(m->d_X, src->d_X, sizeof(double) * n * d, cudaMemcpyDeviceToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(m->d_y, src->d_y, sizeof(double) * n, cudaMemcpyDeviceToDevice, s);
+    if (e == cudaSuccess && src->factored) {
+        e = cudaMemcpyAsync(m->d_Z, src->d_Z, sizeof(double) * src->spec.n_parts * n * d, cudaMemcpyDeviceToDevice, s);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(m->d_F, src->d_F, sizeof(double) * (n + 1) * src->ld, cudaMemcpyDeviceToDevice, s);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(m->d_spec, src->d_spec, sizeof(DevSpec), cudaMemcpyDeviceToDevice, s);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) {
+        pgp_model_destroy(m);
+        return ctx->cuda_fail(e, "model clone copies", __FILE__, __LINE__);
+    }
+    *out = m;
+    return 0;
+}
+
+extern "C" int pgp_exact_update(pgp_model* m, const double* hyp) {
+    if (!m) return PGP_E_ARG;
+    pgp_ctx* ctx = m->ctx;
+    if (!hyp) return ctx->fail(PGP_E_ARG, "null hyper vector");
+    PGP_TRY(set_device(ctx));
+    const int nk = m->spec.nhyper;
+    const double sn2 = std::exp(hyp[0] * 2);  // likelihoods/gaussian.py:36-39
+    const double mean = hyp[1 + nk];
+    PGP_TRY(compile_spec(&m->spec, hyp + 1, sn2, mean, &m->hspec, &ctx->err));
+    m->factored = false;
+    PGP_CUDA(ctx, cudaMemcpyAsync(m->d_spec, &m->hspec, sizeof(DevSpec), cudaMemcpyHostToDevice, ctx->stream));
+    PGP_CUDA(ctx, cudaMemsetAsync(m->d_info, 0, sizeof(int), ctx->stream));
+    const int64_t n = m->n;
+    PGP_TRY(launch_scale(ctx, m->d_spec, m->d_X, n, m->ndim, m->spec.n_parts, m->d_Z, 1));
+    GramArgs g;
+    g.spec = m->d_spec;
+    g.Z1 = g.Z2 = m->d_Z;
+    g.n1 = g.n2 = n;
+    g.ndim = m->ndim;
+    g.n_parts = m->spec.n_parts;
+    g.out = m->d_F;
+    g.ldo = m->ld;
+    g.lower_only = 1;
+    g.add_noise = 1;
+    g.single_type = single_type(&m->spec);
+    PGP_TRY(launch_gram(ctx, g));
+    Mat F;
+    F.p = m->d_F;
+    F.ld = m->ld;
+    PGP_TRY(launch_set_residual(ctx, F, n, m->d_y, m->d_spec));
+    PGP_TRY(potrf_lower(ctx, F, n, 1, m->d_info));
+    PGP_TRY(launch_loglik(ctx, F, n, m->d_res));
+    double* hp = ctx->h_pin;
+    PGP_CUDA(ctx, cudaMemcpyAsync(hp, m->d_res, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    PGP_CUDA(ctx, cudaMemcpyAsync(hp + 1, m->d_info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    PGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    m->lZ = hp[0];
+    m->info = *reinterpret_cast<int*>(hp + 1);
+    if (m->info != 0) {
+        char buf[160];
+        snprintf(buf, sizeof buf, "%d-th leading minor of the array is not positive definite", m->info);
+        ctx->err = buf;
+        return m->info;
+    }
+    m->factored = true;
+    return 0;
+}
+
+extern "C" int pgp_exact_loglike(pgp_model* m, int want_grad, double* lZ, double* dlZ) {
+    if (!m) return PGP_E_ARG;
+    pgp_ctx* ctx = m->ctx;
+    if (!lZ || (want_grad && !dlZ)) return ctx->fail(PGP_E_ARG, "null output");
+    if (!m->factored) return ctx->fail(PGP_E_STATE, "loglike before a successful update");
+    *lZ = m->lZ;
+    if (!want_grad) return 0;
+    PGP_TRY(set_device(ctx));
+    const int64_t n = m->n, ld = m->ld;
+    const int nk = m->spec.nhyper;
+    if (!m->d_G) {
+        PGP_TRY(dev_alloc(ctx, &m->d_G, (size_t)n * ld));
+        // blocks of G below the diagonal are never written: zero them once
+        PGP_CUDA(ctx, cudaMemsetAsync(m->d_G, 0, sizeof(double) * n * ld, ctx->stream));
+    }
+    if (!m->d_H) PGP_TRY(dev_alloc(ctx, &m->d_H, (size_t)n * ld));
+    if (!m->d_partials) PGP_TRY(dev_alloc(ctx, &m->d_partials, (size_t)trace_cta_count(n) * (kMaxHyper + 1)));
+    Mat F, G, H;
+    F.p = m->d_F; F.ld = ld;
+    G.p = m->d_G; G.ld = ld;
+    H.p = m->d_H; H.ld = ld;
+    PGP_TRY(inv_upper(ctx, G, F, n));                                       // V = L^-T
+    PGP_TRY(launch_gemv_upper(ctx, m->d_G, ld, m->d_F + n * ld, n, m->d_alpha));  // alpha = V a
+    PGP_TRY(syrk_upper_lower(ctx, H, G, n));                                // K~^-1 = V V^T
+    TraceArgs t;
+    t.spec = m->d_spec;
+    t.Z = m->d_Z;
+    t.n = n;
+    t.ndim = m->ndim;
+    t.n_parts = m->spec.n_parts;
+    t.nhyper = nk;
+    t.P = m->d_H;
+    t.ldp = ld;
+    t.alpha = m->d_alpha;
+    t.partials = m->d_partials;
+    t.dlZ = m->d_res + 1;
+    t.single_type = single_type(&m->spec);
+    PGP_TRY(launch_trace(ctx, t));
+    double* hp = ctx->h_pin;
+    PGP_CUDA(ctx, cudaMemcpyAsync(hp, m->d_res + 1, sizeof(double) * (nk + 2), cudaMemcpyDeviceToHost, ctx->stream));
+    PGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < nk + 2; ++i) dlZ[i] = hp[i];
+    return 0;
+}
+
+namespace {
+
+int predict_chunked(pgp_model* m, const double* Xs, bool xs_on_device, int64_t ms, double* mu, double* s2,
+                    bool out_on_device) {
+    pgp_ctx* ctx = m->ctx;
+    if (!m->factored) return ctx->fail(PGP_E_STATE, "predict before a successful update");
+    if (ms == 0) return 0;
+    const int64_t n = m->n, ld = m->ld;
+    const int d = m->ndim, np = m->spec.n_parts;
+    // chunk of test points: B (chunk, ld) capped at 4 GiB
+    int64_t chunk = std::max<int64_t>(256, (int64_t)(4ll << 30) / (ld * 8));
+    chunk = std::min(chunk, ms);
+    if (m->bc_rows < chunk) {
+        cudaFree(m->d_Bc);
+        m->d_Bc = nullptr;
+        m->bc_rows = 0;
+        PGP_TRY(dev_alloc(ctx, &m->d_Bc, (size_t)chunk * ld));
+        m->bc_rows = chunk;
+    }
+    DevBuf xs, zs, o;
+    if (!xs_on_device) PGP_TRY(alloc<double>(ctx, xs, (size_t)chunk * d));
+    PGP_TRY(alloc<double>(ctx, zs, (size_t)np * chunk * d));
+    if (!out_on_device) PGP_TRY(alloc<double>(ctx, o, (size_t)2 * chunk));
+    Mat B, F;
+    B.p = m->d_Bc; B.ld = ld;
+    F.p = m->d_F; F.ld = ld;
+    for (int64_t s0 = 0; s0 < ms; s0 += chunk) {
+        int64_t mc = std::min(chunk, ms - s0);
+        const double* dx;
+        if (xs_on_device) {
+            dx = Xs + s0 * d;
+        } else {
+            PGP_CUDA(ctx, cudaMemcpyAsync(xs.p, Xs + s0 * d, sizeof(double) * mc * d, cudaMemcpyHostToDevice, ctx->stream));
+            dx = xs.as<double>();
+        }
+        PGP_TRY(launch_scale(ctx, m->d_spec, dx, mc, d, np, zs.as<double>(), 1));
+        GramArgs g;                       // B = k(Xs, X): rows = test points
+        g.spec = m->d_spec;
+        g.Z1 = zs.as<double>();
+        g.Z2 = m->d_Z;
+        g.n1 = mc;
+        g.n2 = n;
+        g.ndim = d;
+        g.n_parts = np;
+        g.out = m->d_Bc;
+        g.ldo = ld;
+        g.single_type = single_type(&m->spec);
+        PGP_TRY(launch_gram(ctx, g));
+        PGP_TRY(trsm_right_lt(ctx, B, mc, F, n));  // rows become (R^-T k*)^T
+        double* dmu = out_on_device ? mu + s0 : o.as<double>();
+        double* ds2 = out_on_device ? s2 + s0 : o.as<double>() + chunk;
+        PGP_TRY(launch_predict_reduce(ctx, m->d_Bc, ld, mc, n, m->d_F + n * ld, m->d_spec, dmu, ds2, 1, 0, 0, 0));
+        if (!out_on_device) {
+            PGP_CUDA(ctx, cudaMemcpyAsync(mu + s0, dmu, sizeof(double) * mc, cudaMemcpyDeviceToHost, ctx->stream));
+            PGP_CUDA(ctx, cudaMemcpyAsync(s2 + s0, ds2, sizeof(double) * mc, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        PGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int pgp_exact_predict(pgp_model* m, const double* Xs, int64_t ms, double* mu, double* s2) {
+    if (!m) return PGP_E_ARG;
+    if (!Xs || !mu || !s2 || ms < 0) return m->ctx->fail(PGP_E_ARG, "null or negative argument");
+    PGP_TRY(set_device(m->ctx));
+    return predict_chunked(m, Xs, false, ms, mu, s2, false);
+}
+
+extern "C" int pgp_exact_predict_dev(pgp_model* m, const double* d_Xs, int64_t ms, double* d_mu, double* d_s2) {
+    if (!m) return PGP_E_ARG;
+    if (!d_Xs || !d_mu || !d_s2 || ms < 0) return m->ctx->fail(PGP_E_ARG, "null or negative argument");
+    PGP_TRY(set_device(m->ctx));
+    return predict_chunked(m, d_Xs, true, ms, d_mu, d_s2, true);
+}
+
+extern "C" int pgp_exact_get_factor(pgp_model* m, double* R_out, double* a_out) {
+    if (!m) return PGP_E_ARG;
+    pgp_ctx* ctx = m->ctx;
+    if (!m->factored) return ctx->fail(PGP_E_STATE, "get_factor before a successful update");
+    PGP_TRY(set_device(ctx));
+    const int64_t n = m->n;
+    if (R_out) {
+        DevBuf r;
+        PGP_TRY(alloc<double>(ctx, r, (size_t)n * n));
+        PGP_TRY(launch_extract_upper(ctx, m->d_F, m->ld, n, r.as<double>()));
+        PGP_CUDA(ctx, cudaMemcpyAsync(R_out, r.p, sizeof(double) * n * n, cudaMemcpyDeviceToHost, ctx->stream));
+        PGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    if (a_out) {
+        PGP_CUDA(ctx, cudaMemcpyAsync(a_out, m->d_F + n * m->ld, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+        PGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// batched small-N path
+// ---------------------------------------------------------------------------
+static int batched_impl(pgp_ctx* ctx, const pgp_kernel_spec* spec, const double* X, const double* y, int64_t n,
+                        const double* hyps, int64_t B, const double* Xs, int64_t ms, double* lZ, double* mu,
+                        double* s2, int32_t* info) {
+    if (!ctx) return PGP_E_ARG;
+    if (!spec || !X || !y || !hyps || n <= 0 || B < 0) return ctx->fail(PGP_E_ARG, "null argument or bad size");
+    if (spec->n_parts * spec->ndim > 192) return ctx->fail(PGP_E_ARG, "n_parts * ndim > 192 not supported");
+    PGP_TRY(set_device(ctx));
+    if (B == 0) return 0;
+    const int d = spec->ndim, np = spec->n_parts, nk = spec->nhyper, nh = nk + 2;
+    const int64_t ld = lead_dim(n);
+    const bool pred = Xs != nullptr && ms > 0;
+    // per-problem device footprint -> chunk of the batch that fits a 24 GiB budget
+    size_t per = sizeof(double) * ((size_t)(n + 1) * ld + (size_t)np * n * d) + sizeof(DevSpec);
+    if (pred) per += sizeof(double) * ((size_t)ms * ld + (size_t)np * ms * d + 2 * ms);
+    size_t free_b = 0, total_b = 0;
+    PGP_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+    size_t budget = std::min<size_t>((size_t)24 << 30, free_b / 2);
+    int64_t chunk = std::max<int64_t>(1, std::min<int64_t>({(int64_t)(budget / per), B, (int64_t)32768}));
+
+    DevBuf dX, dy, dXs, dspec, dZ, dF, dres, dinfo, dZs, dB, dout;
+    PGP_TRY(alloc<double>(ctx, dX, (size_t)n * d));
+    PGP_TRY(alloc<double>(ctx, dy, (size_t)n));
+    PGP_CUDA(ctx, cudaMemcpyAsync(dX.p, X, sizeof(double) * n * d, cudaMemcpyHostToDevice, ctx->stream));
+    PGP_CUDA(ctx, cudaMemcpyAsync(dy.p, y, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+    PGP_TRY(alloc<DevSpec>(ctx, dspec, chunk));
+    PGP_TRY(alloc<double>(ctx, dZ, (size_t)chunk * np * n * d));
+    PGP_TRY(alloc<double>(ctx, dF, (size_t)chunk * (n + 1) * ld));
+    PGP_TRY(alloc<double>(ctx, dres, (size_t)chunk));
+    PGP_TRY(alloc<int>(ctx, dinfo, (size_t)chunk));
+    if (pred) {
+        PGP_TRY(alloc<double>(ctx, dXs, (size_t)ms * d));
+        PGP_CUDA(ctx, cudaMemcpyAsync(dXs.p, Xs, sizeof(double) * ms * d, cudaMemcpyHostToDevice, ctx->stream));
+        PGP_TRY(alloc<double>(ctx, dZs, (size_t)chunk * np * ms * d));
+        PGP_TRY(alloc<double>(ctx, dB, (size_t)chunk * ms * ld));
+        PGP_TRY(alloc<double>(ctx, dout, (size_t)chunk * 2 * ms));
+    }
+    std::vector<DevSpec> hspecs((size_t)chunk);
+    std::vector<int> hinfo((size_t)chunk);
+    std::vector<double> hres((size_t)chunk);
+
+    for (int64_t b0 = 0; b0 < B; b0 += chunk) {
+        const int bc = (int)std::min<int64_t>(chunk, B - b0);
+        for (int b = 0; b < bc; ++b) {
+            const double* h = hyps + (b0 + b) * nh;
+            PGP_TRY(compile_spec(spec, h + 1, std::exp(h[0] * 2), h[1 + nk], &hspecs[b], &ctx->err));
+        }
+        PGP_CUDA(ctx, cudaMemcpyAsync(dspec.p, hspecs.data(), sizeof(DevSpec) * bc, cudaMemcpyHostToDevice, ctx->stream));
+        PGP_CUDA(ctx, cudaMemsetAsync(dinfo.p, 0, sizeof(int) * bc, ctx->stream));
+        PGP_TRY(launch_scale(ctx, dspec.as<DevSpec>(), dX.as<double>(), n, d, np, dZ.as<double>(), bc));
+        Mat F;
+        F.p = dF.as<double>();
+        F.ld = ld;
+        F.bstride = (n + 1) * ld;
+        F.batch = bc;
+        GramArgs g;
+        g.spec = dspec.as<DevSpec>();
+        g.Z1 = g.Z2 = dZ.as<double>();
+        g.n1 = g.n2 = n;
+        g.ndim = d;
+        g.n_parts = np;
+        g.out = F.p;
+        g.ldo = ld;
+        g.out_bstride = F.bstride;
+        g.lower_only = 1;
+        g.add_noise = 1;
+        g.batch = bc;
+        g.single_type = single_type(spec);
+        PGP_TRY(launch_gram(ctx, g));
+        PGP_TRY(launch_set_residual(ctx, F, n, dy.as<double>(), dspec.as<DevSpec>()));
+        PGP_TRY(potrf_lower(ctx, F, n, 1, dinfo.as<int>()));
+        PGP_TRY(launch_loglik(ctx, F, n, dres.as<double>()));
+        PGP_CUDA(ctx, cudaMemcpyAsync(hres.data(), dres.p, sizeof(double) * bc, cudaMemcpyDeviceToHost, ctx->stream));
+        PGP_CUDA(ctx, cudaMemcpyAsync(hinfo.data(), dinfo.p, sizeof(int) * bc, cudaMemcpyDeviceToHost, ctx->stream));
+        if (pred) {
+            PGP_TRY(launch_scale(ctx, dspec.as<DevSpec>(), dXs.as<double>(), ms, d, np, dZs.as<double>(), bc));
+            GramArgs c;
+            c.spec = dspec.as<DevSpec>();
+            c.Z1 = dZs.as<double>();
+            c.Z2 = dZ.as<double>();
+            c.n1 = ms;
+            c.n2 = n;
+            c.ndim = d;
+            c.n_parts = np;
+            c.out = dB.as<double>();
+            c.ldo = ld;
+            c.out_bstride = ms * ld;
+            c.batch = bc;
+            c.single_type = single_type(spec);
+            PGP_TRY(launch_gram(ctx, c));
+            Mat Bm;
+            Bm.p = dB.as<double>();
+            Bm.ld = ld;
+            Bm.bstride = ms * ld;
+            Bm.batch = bc;
+            PGP_TRY(trsm_right_lt(ctx, Bm, ms, F, n));
+            double* dmu = dout.as<double>();
+            double* ds2 = dmu + (size_t)chunk * ms;
+            PGP_TRY(launch_predict_reduce(ctx, Bm.p, ld, ms, n, F.p + n * ld, dspec.as<DevSpec>(), dmu, ds2, bc,
+                                          Bm.bstride, F.bstride, ms));
+            PGP_CUDA(ctx, cudaMemcpyAsync(mu + b0 * ms, dmu, sizeof(double) * bc * ms, cudaMemcpyDeviceToHost, ctx->stream));
+            PGP_CUDA(ctx, cudaMemcpyAsync(s2 + b0 * ms, ds2, sizeof(double) * bc * ms, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        PGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        for (int b = 0; b < bc; ++b) {
+            if (lZ) lZ[b0 + b] = hres[b];
+            if (info) info[b0 + b] = hinfo[b];
+        }
+    }
+    return 0;
+}
+
+extern "C" int pgp_batched_loglike(pgp_ctx* ctx, const pgp_kernel_spec* spec, const double* X, const double* y,
+                                   int64_t n, const double* hyps, int64_t B, double* lZ, int32_t* info) {
+    if (ctx && !lZ) return ctx->fail(PGP_E_ARG, "null output");
+    return batched_impl(ctx, spec, X, y, n, hyps, B, nullptr, 0, lZ, nullptr, nullptr, info);
+}
+
+extern "C" int pgp_batched_predict(pgp_ctx* ctx, const pgp_kernel_spec* spec, const double* X, const double* y,
+                                   int64_t n, const double* hyps, int64_t B, const double* Xs, int64_t ms,
+                                   double* mu, double* s2, int32_t* info) {
+    if (ctx && (!Xs || !mu || !s2 || ms < 0)) return ctx->fail(PGP_E_ARG, "null or negative argument");
+    return batched_impl(ctx, spec, X, y, n, hyps, B, Xs, ms, nullptr, mu, s2, info);
+}
+
+// ---------------------------------------------------------------------------
+// building blocks (tests / profiling)
+// ---------------------------------------------------------------------------
+extern "C" int pgp_dev_gemm_nt(pgp_ctx* ctx, int64_t m, int64_t n, int64_t k, double alpha, const double* d_A,
+                               int64_t lda, const double* d_B, int64_t ldb, double beta, double* d_C, int64_t ldc,
+                               int tri) {
+    if (!ctx) return PGP_E_ARG;
+    PGP_TRY(set_device(ctx));
+    GemmArgs g;
+    g.A = d_A; g.lda = lda;
+    g.B = d_B; g.ldb = ldb;
+    g.C = d_C; g.ldc = ldc;
+    g.M = m; g.N = n; g.K = k;
+    g.alpha = alpha; g.beta = beta;
+    g.tri = tri;
+    return launch_gemm_nt(ctx, g);
+}
+
+extern "C" int pgp_dev_potrf(pgp_ctx* ctx, double* d_F, int64_t n, int64_t ld, int64_t extra) {
+    if (!ctx) return PGP_E_ARG;
+    PGP_TRY(set_device(ctx));
+    DevBuf info;
+    PGP_TRY(alloc<int>(ctx, info, 1));
+    PGP_CUDA(ctx, cudaMemsetAsync(info.p, 0, sizeof(int), ctx->stream));
+    Mat F;
+    F.p = d_F;
+    F.ld = ld;
+    PGP_TRY(potrf_lower(ctx, F, n, extra, info.as<int>()));
+    int h = 0;
+    PGP_CUDA(ctx, cudaMemcpyAsync(&h, info.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    PGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return h;
+}

@@ -1,0 +1,54 @@
+// chol.cuh -- in-place FP64 factorisation and triangular algebra on row-major
+// device buffers; every O(N^3) flop goes through launch_gemm_nt (DMMA).
+#pragma once
+
+#include "gemm.cuh"
+
+namespace pgp {
+
+constexpr int kNB = 64;  // base block of the recursions
+
+// A factor buffer F: row-major, `ld` doubles per row, rows 0..n-1 hold a
+// symmetric positive-definite matrix in their LOWER triangle (the strict upper
+// triangle is scratch), followed by `extra` further rows (right-hand sides).
+struct Mat {
+    double* p = nullptr;
+    int64_t ld = 0;
+    int64_t bstride = 0;  // doubles between consecutive batch members
+    int batch = 1;
+};
+
+// In-place lower Cholesky F = L L^T of columns [0, n) applied to all
+// n + extra rows: afterwards the extra rows hold B L^-T (row n = r becomes
+// a = L^-1 r, ExactGP._update exact.py:54-55).  info[b] receives the LAPACK
+// style index of the first non-positive pivot (0 = ok).
+int potrf_lower(pgp_ctx* ctx, const Mat& F, int64_t n, int64_t extra, int* d_info);
+
+// B[:, 0:n) <- B L^-T for `rows` rows of B (same column space as L).
+int trsm_right_lt(pgp_ctx* ctx, const Mat& B, int64_t rows, const Mat& L, int64_t n);
+
+// G (pre-zeroed outside its upper triangle) <- L^-T, upper triangular.
+int inv_upper(pgp_ctx* ctx, const Mat& G, const Mat& L, int64_t n);
+
+// H lower triangle <- G G^T with G upper triangular (= K~^-1 when G = L^-T).
+int syrk_upper_lower(pgp_ctx* ctx, const Mat& H, const Mat& G, int64_t n);
+
+// out[b] = -1/2 |a|^2 - n/2 log 2 pi - sum log L_ii, a = row n of F (exact.py:119-121)
+int launch_loglik(pgp_ctx* ctx, const Mat& F, int64_t n, double* d_out);
+
+// alpha = G a  (alpha = R^-1 a of exact.py:128), G upper triangular (n, ld)
+int launch_gemv_upper(pgp_ctx* ctx, const double* G, int64_t ld, const double* a, int64_t n, double* alpha);
+
+// F[n][j] = y[j] - mean(spec[b])   (exact.py:53)
+struct DevSpec;
+int launch_set_residual(pgp_ctx* ctx, const Mat& F, int64_t n, const double* d_y, const DevSpec* d_spec);
+
+// mu[i] = mean + <B[i], a>, s2[i] = kdiag - |B[i]|^2 (exact.py:93-94); B (rows, ld)
+int launch_predict_reduce(pgp_ctx* ctx, const double* B, int64_t ld, int64_t rows, int64_t n,
+                          const double* a, const DevSpec* d_spec, double* mu, double* s2,
+                          int batch, int64_t bstrideB, int64_t bstrideA, int64_t bstrideOut);
+
+// R_out (n, n) dense upper = L^T  (the reference's self._R)
+int launch_extract_upper(pgp_ctx* ctx, const double* F, int64_t ld, int64_t n, double* R);
+
+}  // namespace pgp

@@ -1,0 +1,122 @@
+// common.cuh -- context, error plumbing, launch accounting shared by all
+// translation units of libpygp_b200.so.  sm_100a only.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/pygp_b200.h"
+
+namespace pgp {
+
+enum ProfClass { PC_GEMM = 0, PC_GRAM = 1, PC_TRACE = 2, PC_POTRF = 3, PC_TRSM = 4, PC_OTHER = 5 };
+
+struct ProfRec {
+    cudaEvent_t e0, e1;
+    int cls;
+    double work;
+};
+
+struct Status {
+    int code = 0;
+    bool ok() const { return code == 0; }
+};
+
+}  // namespace pgp
+
+struct pgp_ctx {
+    int device = 0;
+    int sm_count = 148;
+    size_t smem_optin = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int64_t launches = 0;
+    bool profile = false;
+    std::vector<pgp::ProfRec> prof;
+    std::vector<cudaEvent_t> event_pool;
+    // small pinned staging area for hypers / results
+    double* h_pin = nullptr;
+    size_t h_pin_doubles = 0;
+
+    int fail(int code, const std::string& msg) {
+        err = msg;
+        return code;
+    }
+    int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+        char buf[512];
+        snprintf(buf, sizeof buf, "CUDA error %s (%s) at %s:%d in %s", cudaGetErrorName(e),
+                 cudaGetErrorString(e), file, line, what);
+        err = buf;
+        return e == cudaErrorMemoryAllocation ? PGP_E_NOMEM : PGP_E_CUDA;
+    }
+};
+
+#define PGP_CUDA(ctx, call)                                                      \
+    do {                                                                         \
+        cudaError_t e__ = (call);                                                \
+        if (e__ != cudaSuccess) return (ctx)->cuda_fail(e__, #call, __FILE__, __LINE__); \
+    } while (0)
+
+#define PGP_TRY(expr)                   \
+    do {                                \
+        int rc__ = (expr);              \
+        if (rc__ != 0) return rc__;     \
+    } while (0)
+
+namespace pgp {
+
+// RAII bracket around one kernel launch: counts it and, when profiling is on,
+// records an event pair on the context stream.
+struct Launch {
+    pgp_ctx* ctx;
+    int idx = -1;
+    Launch(pgp_ctx* c, int cls, double work) : ctx(c) {
+        ctx->launches++;
+        if (ctx->profile) {
+            ProfRec r;
+            r.cls = cls;
+            r.work = work;
+            cudaEventCreate(&r.e0);
+            cudaEventCreate(&r.e1);
+            cudaEventRecord(r.e0, ctx->stream);
+            ctx->prof.push_back(r);
+            idx = (int)ctx->prof.size() - 1;
+        }
+    }
+    ~Launch() {
+        if (idx >= 0) cudaEventRecord(ctx->prof[idx].e1, ctx->stream);
+    }
+};
+
+inline int check_launch(pgp_ctx* ctx, const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return ctx->cuda_fail(e, what, __FILE__, __LINE__);
+    return 0;
+}
+
+template <class T>
+inline int dev_alloc(pgp_ctx* ctx, T** p, size_t count) {
+    *p = nullptr;
+    if (count == 0) return 0;
+    cudaError_t e = cudaMalloc((void**)p, count * sizeof(T));
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        char buf[256];
+        snprintf(buf, sizeof buf, "cudaMalloc of %zu bytes failed: %s", count * sizeof(T),
+                 cudaGetErrorString(e));
+        return ctx->fail(PGP_E_NOMEM, buf);
+    }
+    return 0;
+}
+
+inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+inline int64_t ceil_div(int64_t x, int64_t m) { return (x + m - 1) / m; }
+
+// leading dimension of every square work buffer: rows start 128-byte aligned
+inline int64_t lead_dim(int64_t n) { return round_up(n, 16); }
+
+}  // namespace pgp

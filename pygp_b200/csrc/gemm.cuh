@@ -1,0 +1,33 @@
+// gemm.cuh -- the FP64 tensor-core (DMMA) GEMM every O(N^3) step is built from.
+#pragma once
+
+#include "common.cuh"
+
+namespace pgp {
+
+// C (M x N, row-major, ldc) = beta * C + alpha * A (M x K) * B (N x K)^T
+// A and B are row-major with the contraction index contiguous ("NT").
+struct GemmArgs {
+    const double* A = nullptr;
+    const double* B = nullptr;
+    double* C = nullptr;
+    int64_t lda = 0, ldb = 0, ldc = 0;
+    int64_t M = 0, N = 0, K = 0;
+    double alpha = 1.0, beta = 0.0;
+    // tri: skip C tiles lying strictly above the diagonal row - col = tri_off
+    // (entry (i, j) is "on or below" when j <= i + tri_off).
+    int tri = 0;
+    int64_t tri_off = 0;
+    // krow: A is upper-triangular in (row, k): A[i][k] == 0 for k < i + krow_off,
+    // so the contraction of tile row i0 may start at k = i0 + krow_off
+    // (rounded down to the k-tile).  Used by the triangular inverse and by
+    // V V^T (k >= max(i, j) = i on the lower tiles).
+    int krow = 0;
+    int64_t krow_off = 0;
+    int batch = 1;
+    int64_t strideA = 0, strideB = 0, strideC = 0;
+};
+
+int launch_gemm_nt(pgp_ctx* ctx, const GemmArgs& a);
+
+}  // namespace pgp

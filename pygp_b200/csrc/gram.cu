@@ -1,0 +1,572 @@
+// gram.cu -- covariance tile kernels: Gram build (Kernel.get), one hyper-gradient
+// matrix (Kernel.grad), the fused gradient trace sum(Q o dK_h) of
+// ExactGP.loglikelihood (pygp/inference/exact.py:131-141) and the diagonal
+// forms (Kernel.dget / dgrad).
+//
+// Bound: these kernels write (or read) 8 B per entry and spend
+// ~(3 ndim + 40) FP64 instructions per entry, so on B200 (64 FP64 lanes/SM)
+// they are HBM-bound only for ndim <= 2 and FP64-pipe-bound above that;
+// DESIGN.md section 4 has the arithmetic.
+//
+// Layout: inputs are pre-divided by the length-scales (launch_scale, the
+// reference's `rescale`), one scaled copy Z[p] per leaf kernel.  A CTA stages
+// the 64 rows and 64 columns of its tile in shared memory TRANSPOSED
+// ([leaf][dim][64]) so that threads of a warp read consecutive columns without
+// bank conflicts; each thread owns a 4 x 4 micro-tile (rows ty+16a, column
+// pairs 2tx+32h) so the output is written with coalesced 128-bit stores.
+
+#include "gram.cuh"
+
+namespace pgp {
+
+namespace {
+
+constexpr int kThreads = 256;
+
+struct Tile {
+    int tx, ty;
+    __device__ Tile() : tx(threadIdx.x & 15), ty(threadIdx.x >> 4) {}
+    __device__ int row(int a) const { return ty + 16 * a; }
+    __device__ int col(int b) const { return 2 * tx + 32 * (b >> 1) + (b & 1); }
+};
+
+// stage `rows` x ndim doubles of every leaf's scaled inputs, transposed
+__device__ __forceinline__ void stage_tile(double* dst, const double* Z, int64_t zstride, int64_t n,
+                                           int64_t r0, int ndim, int n_parts) {
+    const int per_part = kTile * ndim;
+    for (int idx = threadIdx.x; idx < n_parts * per_part; idx += kThreads) {
+        int p = idx / per_part;
+        int rem = idx - p * per_part;
+        int r = rem / ndim;
+        int k = rem - r * ndim;
+        int64_t gr = r0 + r;
+        double v = 0.0;
+        if (gr < n) v = Z[p * zstride + gr * ndim + k];
+        dst[(p * ndim + k) * kTile + r] = v;
+    }
+}
+
+__device__ __forceinline__ void load_hdr(DevSpecHdr* dst, const DevSpec* src) {
+    const int nwords = sizeof(DevSpecHdr) / 4;
+    const int* s = reinterpret_cast<const int*>(&src->h);
+    int* d = reinterpret_cast<int*>(dst);
+    for (int i = threadIdx.x; i < nwords; i += kThreads) d[i] = s[i];
+}
+
+// triangular tile index -> (ti, tj) with tj <= ti
+__device__ __forceinline__ void tri_decode(int64_t idx, int* ti, int* tj) {
+    int64_t t = (int64_t)((sqrt(8.0 * (double)idx + 1.0) - 1.0) * 0.5);
+    while (t * (t + 1) / 2 > idx) --t;
+    while ((t + 1) * (t + 2) / 2 <= idx) ++t;
+    *ti = (int)t;
+    *tj = (int)(idx - t * (t + 1) / 2);
+}
+
+// all leaves at one entry: squared distances by direct differences
+template <bool GRAD>
+__device__ __forceinline__ void eval_parts(const DevSpecHdr& S, const double* z1, const double* z2,
+                                           PartVal* pv) {
+    const int d = S.ndim;
+    for (int p = 0; p < S.n_parts; ++p) {
+        double D = 0.0;
+        for (int k = 0; k < d; ++k) {
+            double df = z1[(p * d + k) * kTile] - z2[(p * d + k) * kTile];
+            D += df * df;
+        }
+        part_eval<GRAD>(S.parts[p], D, pv[p]);
+    }
+}
+
+// value of d k / d hyper[slot] for a composite at one entry
+__device__ __forceinline__ double composite_grad1(const DevSpecHdr& S, const double* z1, const double* z2,
+                                                  int part, int kind, int dim) {
+    PartVal pv[kMaxParts];
+    double val[kMaxNodes], adj[kMaxNodes];
+    eval_parts<true>(S, z1, z2, pv);
+    tree_forward(S, pv, val);
+    tree_backward(S, val, adj);
+    double C = adj[S.leaf_node[part]];
+    const PartVal& v = pv[part];
+    double g;
+    if (kind == SLOT_SF) g = v.g_sf;
+    else if (kind == SLOT_ISO) g = v.g_iso;
+    else if (kind == SLOT_E0) g = v.e0;
+    else {
+        double df = z1[(part * S.ndim + dim) * kTile] - z2[(part * S.ndim + dim) * kTile];
+        g = v.ardw * (df * df);
+    }
+    return C * g;
+}
+
+__device__ __forceinline__ double slot_value(const PartVal& v, int kind, double dk2) {
+    return kind == SLOT_SF ? v.g_sf : kind == SLOT_ISO ? v.g_iso : kind == SLOT_E0 ? v.e0 : v.ardw * dk2;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// scale: Z[b][p][i][k] = X[i][k] / ell[b][p][k]
+// ---------------------------------------------------------------------------
+__global__ void scale_kernel(const DevSpec* __restrict__ spec, const double* __restrict__ X, int64_t n,
+                             int ndim, int n_parts, double* __restrict__ Z) {
+    const int b = blockIdx.y;
+    const DevSpec* sp = spec + b;
+    const int64_t per_part = n * ndim;
+    const int64_t total = per_part * n_parts;
+    double* Zb = Z + (int64_t)b * total;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        int p = (int)(idx / per_part);
+        int64_t rem = idx - p * per_part;
+        int k = (int)(rem % ndim);
+        Zb[idx] = X[rem] / sp->ell[p][k];
+    }
+}
+
+int launch_scale(pgp_ctx* ctx, const DevSpec* d_spec, const double* d_X, int64_t n, int ndim,
+                 int n_parts, double* d_Z, int batch) {
+    if (n == 0) return 0;
+    int64_t total = n * ndim * n_parts;
+    int blocks = (int)std::min<int64_t>(ceil_div(total, 256), 148 * 8);
+    Launch L(ctx, PC_OTHER, 16.0 * total * batch);
+    scale_kernel<<<dim3(blocks, batch), 256, 0, ctx->stream>>>(d_spec, d_X, n, ndim, n_parts, d_Z);
+    return check_launch(ctx, "scale_kernel");
+}
+
+// ---------------------------------------------------------------------------
+// Gram / single hyper-gradient tile kernel
+//   PTYPE >= 0: single leaf of that type (register micro-tile fast path)
+//   PTYPE <  0: composite, one entry at a time through the tree
+// ---------------------------------------------------------------------------
+template <int PTYPE, bool GRAD1>
+__global__ void __launch_bounds__(kThreads) gram_kernel(GramArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    DevSpecHdr* S = reinterpret_cast<DevSpecHdr*>(smem_raw);
+    double* Zs1 = reinterpret_cast<double*>(smem_raw + ((sizeof(DevSpecHdr) + 15) / 16) * 16);
+    double* Zs2 = Zs1 + a.n_parts * a.ndim * kTile;
+
+    const int b = a.lower_only ? blockIdx.y : blockIdx.z;
+    int ti, tj;
+    if (a.lower_only) tri_decode(blockIdx.x, &ti, &tj);
+    else { ti = blockIdx.y; tj = blockIdx.x; }
+    const int64_t i0 = (int64_t)ti * kTile, j0 = (int64_t)tj * kTile;
+    const int ndim = a.ndim, n_parts = a.n_parts;
+
+    load_hdr(S, a.spec + b);
+    stage_tile(Zs1, a.Z1 + (int64_t)b * n_parts * a.n1 * ndim, a.n1 * ndim, a.n1, i0, ndim, n_parts);
+    stage_tile(Zs2, a.Z2 + (int64_t)b * n_parts * a.n2 * ndim, a.n2 * ndim, a.n2, j0, ndim, n_parts);
+    __syncthreads();
+
+    Tile t;
+    double* out = a.out + (int64_t)b * a.out_bstride;
+    int gpart = 0, gkind = 0, gdim = 0;
+    if (GRAD1) classify_hyper(*S, a.hidx, &gpart, &gkind, &gdim);
+    const double noise = a.add_noise ? S->sn2 : 0.0;
+
+    double res[4][4];
+    if (PTYPE >= 0) {
+        double D[4][4];
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+            for (int y = 0; y < 4; ++y) D[x][y] = 0.0;
+        for (int k = 0; k < ndim; ++k) {
+            double zi[4], zj[4];
+#pragma unroll
+            for (int x = 0; x < 4; ++x) zi[x] = Zs1[k * kTile + t.row(x)];
+            double2 q0 = *reinterpret_cast<const double2*>(&Zs2[k * kTile + 2 * t.tx]);
+            double2 q1 = *reinterpret_cast<const double2*>(&Zs2[k * kTile + 2 * t.tx + 32]);
+            zj[0] = q0.x; zj[1] = q0.y; zj[2] = q1.x; zj[3] = q1.y;
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+#pragma unroll
+                for (int y = 0; y < 4; ++y) {
+                    double df = zi[x] - zj[y];
+                    D[x][y] += df * df;
+                }
+        }
+        DevPart part = S->parts[0];
+        part.type = PTYPE;  // compile-time type: the switch in part_eval folds
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+            for (int y = 0; y < 4; ++y) {
+                PartVal v;
+                part_eval<GRAD1>(part, D[x][y], v);
+                if (GRAD1) {
+                    double dk2 = 0.0;
+                    if (gkind == SLOT_ARD) {
+                        double df = Zs1[gdim * kTile + t.row(x)] - Zs2[gdim * kTile + t.col(y)];
+                        dk2 = df * df;
+                    }
+                    res[x][y] = slot_value(v, gkind, dk2);
+                } else {
+                    res[x][y] = v.K;
+                }
+            }
+    } else {
+#pragma unroll 1
+        for (int x = 0; x < 4; ++x)
+#pragma unroll 1
+            for (int y = 0; y < 4; ++y) {
+                const double* z1 = Zs1 + t.row(x);
+                const double* z2 = Zs2 + t.col(y);
+                if (GRAD1) {
+                    res[x][y] = composite_grad1(*S, z1, z2, gpart, gkind, gdim);
+                } else {
+                    PartVal pv[kMaxParts];
+                    double val[kMaxNodes];
+                    eval_parts<false>(*S, z1, z2, pv);
+                    res[x][y] = tree_forward(*S, pv, val);
+                }
+            }
+    }
+
+    const bool vec_ok = ((a.ldo & 1) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+#pragma unroll
+    for (int x = 0; x < 4; ++x) {
+        int64_t gi = i0 + t.row(x);
+        if (gi >= a.n1) continue;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            int64_t gj = j0 + t.col(2 * h);
+            double v0 = res[x][2 * h], v1 = res[x][2 * h + 1];
+            if (gi == gj) v0 += noise;
+            if (gi == gj + 1) v1 += noise;
+            double* dst = out + gi * a.ldo + gj;
+            if (vec_ok && gj + 1 < a.n2) {
+                *reinterpret_cast<double2*>(dst) = make_double2(v0, v1);
+            } else {
+                if (gj < a.n2) dst[0] = v0;
+                if (gj + 1 < a.n2) dst[1] = v1;
+            }
+        }
+    }
+}
+
+template <int PTYPE, bool GRAD1>
+static int launch_gram_t(pgp_ctx* ctx, const GramArgs& a, size_t smem) {
+    auto kern = gram_kernel<PTYPE, GRAD1>;
+    PGP_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t t1 = ceil_div(a.n1, kTile), t2 = ceil_div(a.n2, kTile);
+    dim3 grid;
+    double entries;
+    if (a.lower_only) {
+        grid = dim3((unsigned)(t1 * (t1 + 1) / 2), a.batch, 1);
+        entries = 0.5 * (double)a.n1 * (double)a.n1;
+    } else {
+        if (t1 > 65535) return ctx->fail(PGP_E_ARG, "gram: more than 65535 row tiles");
+        grid = dim3((unsigned)t2, (unsigned)t1, a.batch);
+        entries = (double)a.n1 * (double)a.n2;
+    }
+    Launch L(ctx, PC_GRAM, 8.0 * entries * a.batch);
+    kern<<<grid, kThreads, smem, ctx->stream>>>(a);
+    return check_launch(ctx, "gram_kernel");
+}
+
+int launch_gram(pgp_ctx* ctx, const GramArgs& a) {
+    if (a.n1 == 0 || a.n2 == 0) return 0;
+    if (a.lower_only && a.n1 != a.n2) return ctx->fail(PGP_E_ARG, "gram: lower_only needs a square matrix");
+    if (a.n_parts * a.ndim > 192)
+        return ctx->fail(PGP_E_ARG, "gram: n_parts * ndim > 192 exceeds the shared-memory tile");
+    size_t smem = ((sizeof(DevSpecHdr) + 15) / 16) * 16 + 2ull * a.n_parts * a.ndim * kTile * sizeof(double);
+    const bool g = a.hidx >= 0;
+    int st = a.n_parts == 1 ? a.single_type : -1;
+#define PGP_GRAM_CASE(T)                                             \
+    case T:                                                          \
+        return g ? launch_gram_t<T, true>(ctx, a, smem) : launch_gram_t<T, false>(ctx, a, smem);
+    switch (st) {
+        PGP_GRAM_CASE(PGP_SE)
+        PGP_GRAM_CASE(PGP_MATERN1)
+        PGP_GRAM_CASE(PGP_MATERN3)
+        PGP_GRAM_CASE(PGP_MATERN5)
+        PGP_GRAM_CASE(PGP_PERIODIC)
+        PGP_GRAM_CASE(PGP_RQ)
+        default:
+            return g ? launch_gram_t<-1, true>(ctx, a, smem) : launch_gram_t<-1, false>(ctx, a, smem);
+    }
+#undef PGP_GRAM_CASE
+}
+
+// ---------------------------------------------------------------------------
+// fused gradient trace: persistent CTAs over the lower-triangular tiles of
+// Q = K~^-1 - alpha alpha^T, recomputing K and every dK_h from the inputs.
+//   partial[cta][0]      = sum_i Q_ii
+//   partial[cta][1 + h]  = sum_ij Q_ij dK_h,ij   (full symmetric sum)
+// ---------------------------------------------------------------------------
+constexpr int kTraceCtasPerSm = 4;
+
+template <int PTYPE>
+__global__ void __launch_bounds__(kThreads) trace_kernel(TraceArgs a, int64_t n_tiles) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    DevSpecHdr* S = reinterpret_cast<DevSpecHdr*>(smem_raw);
+    double* Zs1 = reinterpret_cast<double*>(smem_raw + ((sizeof(DevSpecHdr) + 15) / 16) * 16);
+    double* Zs2 = Zs1 + a.n_parts * a.ndim * kTile;
+    double* red = Zs2 + a.n_parts * a.ndim * kTile;  // [8 warps][nhyper + 1]
+
+    const int ndim = a.ndim, n_parts = a.n_parts, nh = a.nhyper;
+    load_hdr(S, a.spec);
+    Tile t;
+
+    double acc[kMaxHyper + 1];
+    for (int h = 0; h <= nh; ++h) acc[h] = 0.0;
+
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        int ti, tj;
+        tri_decode(tile, &ti, &tj);
+        const int64_t i0 = (int64_t)ti * kTile, j0 = (int64_t)tj * kTile;
+        __syncthreads();  // previous tile fully consumed (also orders load_hdr)
+        stage_tile(Zs1, a.Z, a.n * ndim, a.n, i0, ndim, n_parts);
+        stage_tile(Zs2, a.Z, a.n * ndim, a.n, j0, ndim, n_parts);
+        __syncthreads();
+
+        // weights: w Q_ij with w = 2 below the diagonal, 1 on it, 0 above / outside
+        double wq[4][4];
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+            int64_t gi = i0 + t.row(x);
+            double ai = gi < a.n ? a.alpha[gi] : 0.0;
+#pragma unroll
+            for (int y = 0; y < 4; ++y) {
+                int64_t gj = j0 + t.col(y);
+                double w = 0.0;
+                if (gi < a.n && gj <= gi) {
+                    double q = a.P[gi * a.ldp + gj] - ai * a.alpha[gj];
+                    w = gi == gj ? q : 2.0 * q;
+                    if (gi == gj) acc[0] += q;
+                }
+                wq[x][y] = w;
+            }
+        }
+
+        if (PTYPE >= 0) {
+            double D[4][4];
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+#pragma unroll
+                for (int y = 0; y < 4; ++y) D[x][y] = 0.0;
+            for (int k = 0; k < ndim; ++k) {
+                double zi[4], zj[4];
+#pragma unroll
+                for (int x = 0; x < 4; ++x) zi[x] = Zs1[k * kTile + t.row(x)];
+                double2 q0 = *reinterpret_cast<const double2*>(&Zs2[k * kTile + 2 * t.tx]);
+                double2 q1 = *reinterpret_cast<const double2*>(&Zs2[k * kTile + 2 * t.tx + 32]);
+                zj[0] = q0.x; zj[1] = q0.y; zj[2] = q1.x; zj[3] = q1.y;
+#pragma unroll
+                for (int x = 0; x < 4; ++x)
+#pragma unroll
+                    for (int y = 0; y < 4; ++y) {
+                        double df = zi[x] - zj[y];
+                        D[x][y] += df * df;
+                    }
+            }
+            DevPart part = S->parts[0];
+            part.type = PTYPE;
+            double s_sf = 0.0, s_iso = 0.0, s_e0 = 0.0;
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+#pragma unroll
+                for (int y = 0; y < 4; ++y) {
+                    PartVal v;
+                    part_eval<true>(part, D[x][y], v);
+                    double w = wq[x][y];
+                    s_sf += w * v.g_sf;
+                    s_iso += w * v.g_iso;
+                    s_e0 += w * v.e0;
+                    D[x][y] = w * v.ardw;  // reuse as ARD weight
+                }
+            acc[1] += s_sf;
+            if (PTYPE == PGP_PERIODIC) {
+                acc[2] += s_iso;
+                acc[3] += s_e0;
+            } else if (part.iso) {
+                acc[2] += s_iso;
+                if (PTYPE == PGP_RQ) acc[3] += s_e0;
+            } else {
+                for (int k = 0; k < ndim; ++k) {
+                    double zi[4], zj[4];
+#pragma unroll
+                    for (int x = 0; x < 4; ++x) zi[x] = Zs1[k * kTile + t.row(x)];
+                    double2 q0 = *reinterpret_cast<const double2*>(&Zs2[k * kTile + 2 * t.tx]);
+                    double2 q1 = *reinterpret_cast<const double2*>(&Zs2[k * kTile + 2 * t.tx + 32]);
+                    zj[0] = q0.x; zj[1] = q0.y; zj[2] = q1.x; zj[3] = q1.y;
+                    double s = 0.0;
+#pragma unroll
+                    for (int x = 0; x < 4; ++x)
+#pragma unroll
+                        for (int y = 0; y < 4; ++y) {
+                            double df = zi[x] - zj[y];
+                            s += D[x][y] * (df * df);
+                        }
+                    acc[2 + k] += s;
+                }
+                if (PTYPE == PGP_RQ) acc[2 + ndim] += s_e0;
+            }
+        } else {
+#pragma unroll 1
+            for (int x = 0; x < 4; ++x)
+#pragma unroll 1
+                for (int y = 0; y < 4; ++y) {
+                    double w = wq[x][y];
+                    if (w == 0.0) continue;
+                    const double* z1 = Zs1 + t.row(x);
+                    const double* z2 = Zs2 + t.col(y);
+                    PartVal pv[kMaxParts];
+                    double val[kMaxNodes], adj[kMaxNodes];
+                    eval_parts<true>(*S, z1, z2, pv);
+                    tree_forward(*S, pv, val);
+                    tree_backward(*S, val, adj);
+                    for (int p = 0; p < n_parts; ++p) {
+                        const DevPart& dp = S->parts[p];
+                        const PartVal& v = pv[p];
+                        double C = w * adj[S->leaf_node[p]];
+                        double* g = acc + 1 + dp.hoff;
+                        g[0] += C * v.g_sf;
+                        if (dp.type == PGP_PERIODIC) {
+                            g[1] += C * v.g_iso;
+                            g[2] += C * v.e0;
+                        } else {
+                            int nell = dp.iso ? 1 : ndim;
+                            if (dp.iso) {
+                                g[1] += C * v.g_iso;
+                            } else {
+                                double cw = C * v.ardw;
+                                for (int k = 0; k < ndim; ++k) {
+                                    double df = z1[(p * ndim + k) * kTile] - z2[(p * ndim + k) * kTile];
+                                    g[1 + k] += cw * (df * df);
+                                }
+                            }
+                            if (dp.type == PGP_RQ) g[1 + nell] += C * v.e0;
+                        }
+                    }
+                }
+        }
+    }
+
+    // CTA reduction in a fixed order -> one row of partials per CTA
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    for (int h = 0; h <= nh; ++h) {
+        double v = acc[h];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) red[warp * (nh + 1) + h] = v;
+    }
+    __syncthreads();
+    for (int h = threadIdx.x; h <= nh; h += kThreads) {
+        double v = 0.0;
+        for (int w = 0; w < kThreads / 32; ++w) v += red[w * (nh + 1) + h];
+        a.partials[(int64_t)blockIdx.x * (nh + 1) + h] = v;
+    }
+}
+
+// dlZ[0] = -sn2 sum Q_ii ; dlZ[1+h] = -1/2 S_h ; dlZ[nh+1] = sum alpha
+__global__ void trace_finish_kernel(const DevSpec* spec, const double* partials, int64_t n_cta, int nh,
+                                    const double* alpha, int64_t n, double* dlZ) {
+    __shared__ double red[256];
+    const int h = blockIdx.x;  // 0..nh+1
+    double v = 0.0;
+    if (h <= nh) {
+        for (int64_t c = threadIdx.x; c < n_cta; c += blockDim.x) v += partials[c * (nh + 1) + h];
+    } else {
+        for (int64_t i = threadIdx.x; i < n; i += blockDim.x) v += alpha[i];
+    }
+    red[threadIdx.x] = v;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        double r = red[0];
+        if (h == 0) r = -spec->h.sn2 * r;
+        else if (h <= nh) r = -0.5 * r;
+        dlZ[h] = r;
+    }
+}
+
+int64_t trace_cta_count(int64_t n) {
+    int64_t t = ceil_div(n, kTile);
+    int64_t tiles = t * (t + 1) / 2;
+    return std::min<int64_t>(tiles, 148 * kTraceCtasPerSm);
+}
+
+template <int PTYPE>
+static int launch_trace_t(pgp_ctx* ctx, const TraceArgs& a, size_t smem, int64_t n_tiles, int grid) {
+    auto kern = trace_kernel<PTYPE>;
+    PGP_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    Launch L(ctx, PC_TRACE, 4.0 * (double)a.n * (double)a.n);
+    kern<<<grid, kThreads, smem, ctx->stream>>>(a, n_tiles);
+    return check_launch(ctx, "trace_kernel");
+}
+
+int launch_trace(pgp_ctx* ctx, const TraceArgs& a) {
+    if (a.n_parts * a.ndim > 192)
+        return ctx->fail(PGP_E_ARG, "trace: n_parts * ndim > 192 exceeds the shared-memory tile");
+    int64_t t = ceil_div(a.n, kTile);
+    int64_t n_tiles = t * (t + 1) / 2;
+    int grid = (int)trace_cta_count(a.n);
+    size_t smem = ((sizeof(DevSpecHdr) + 15) / 16) * 16 + 2ull * a.n_parts * a.ndim * kTile * sizeof(double) +
+                  8ull * (a.nhyper + 1) * sizeof(double);
+    int st = a.n_parts == 1 ? a.single_type : -1;
+    int rc;
+    switch (st) {
+        case PGP_SE: rc = launch_trace_t<PGP_SE>(ctx, a, smem, n_tiles, grid); break;
+        case PGP_MATERN1: rc = launch_trace_t<PGP_MATERN1>(ctx, a, smem, n_tiles, grid); break;
+        case PGP_MATERN3: rc = launch_trace_t<PGP_MATERN3>(ctx, a, smem, n_tiles, grid); break;
+        case PGP_MATERN5: rc = launch_trace_t<PGP_MATERN5>(ctx, a, smem, n_tiles, grid); break;
+        case PGP_PERIODIC: rc = launch_trace_t<PGP_PERIODIC>(ctx, a, smem, n_tiles, grid); break;
+        case PGP_RQ: rc = launch_trace_t<PGP_RQ>(ctx, a, smem, n_tiles, grid); break;
+        default: rc = launch_trace_t<-1>(ctx, a, smem, n_tiles, grid); break;
+    }
+    PGP_TRY(rc);
+    {
+        Launch L(ctx, PC_OTHER, 0.0);
+        trace_finish_kernel<<<a.nhyper + 2, 256, 0, ctx->stream>>>(a.spec, a.partials, grid, a.nhyper, a.alpha,
+                                                                  a.n, a.dlZ);
+    }
+    return check_launch(ctx, "trace_finish_kernel");
+}
+
+// ---------------------------------------------------------------------------
+// diagonal: k(x,x) and its hyper-gradients do not depend on x for these
+// stationary kernels (se.py:68-74 ...): evaluate once at distance 0 and fill.
+// ---------------------------------------------------------------------------
+__global__ void diag_kernel(const DevSpec* spec, int64_t n, int hmode, int nhyper, double* out) {
+    __shared__ double vals[kMaxHyper + 1];
+    if (threadIdx.x == 0) {
+        const DevSpecHdr& S = spec->h;
+        PartVal pv[kMaxParts];
+        double val[kMaxNodes], adj[kMaxNodes];
+        for (int p = 0; p < S.n_parts; ++p) part_eval<true>(S.parts[p], 0.0, pv[p]);
+        double K = tree_forward(S, pv, val);
+        if (!hmode) {
+            vals[0] = K;
+        } else {
+            tree_backward(S, val, adj);
+            for (int h = 0; h < nhyper; ++h) vals[h] = 0.0;
+            for (int p = 0; p < S.n_parts; ++p) {
+                const DevPart& dp = S.parts[p];
+                double C = adj[S.leaf_node[p]];
+                vals[dp.hoff] = C * pv[p].g_sf;
+                // every other slot is exactly zero at distance 0
+            }
+        }
+    }
+    __syncthreads();
+    int rows = hmode ? nhyper : 1;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < (int64_t)rows * n;
+         idx += (int64_t)gridDim.x * blockDim.x)
+        out[idx] = vals[idx / n];
+}
+
+int launch_diag(pgp_ctx* ctx, const DevSpec* d_spec, int64_t n, int hmode, int nhyper, double* d_out) {
+    if (n == 0) return 0;
+    int64_t total = (hmode ? nhyper : 1) * n;
+    int blocks = (int)std::min<int64_t>(ceil_div(total, 256), 148 * 4);
+    Launch L(ctx, PC_OTHER, 8.0 * total);
+    diag_kernel<<<blocks, 256, 0, ctx->stream>>>(d_spec, n, hmode, nhyper, d_out);
+    return check_launch(ctx, "diag_kernel");
+}
+
+}  // namespace pgp

@@ -1,0 +1,120 @@
+"""
+Exact GP regression on the device (pygp/inference/exact.py:20-143).
+
+`_update`, `loglikelihood` and `_marg_posterior(grad=False)` are single C-ABI
+calls (pgp_exact_update / _loglike / _predict); X, y, the factor L = R^T and
+a = R^-T (y - mean) stay in HBM between calls, so an optimiser step moves only
+the hyper vector in and (lZ, dlZ) out.
+"""
+
+import ctypes as C
+
+import numpy as np
+
+from .. import _lib
+from ..likelihoods import Gaussian
+from ._base import GP
+
+__all__ = ['ExactGP']
+
+
+class _DeviceModel(object):
+    """Owner of a `pgp_model*`; deep-copy clones the device buffers
+    (Parameterized.copy semantics, utils/models.py:47-55)."""
+
+    def __init__(self, ctx, handle):
+        self.ctx, self.handle = ctx, handle
+
+    @classmethod
+    def create(cls, kernel, X, y):
+        ctx = _lib.context()
+        X, y = _lib.as_f64(X, 2), _lib.as_f64(y, 1)
+        h = C.c_void_p()
+        _lib.check(ctx, _lib.lib().pgp_exact_create(ctx.handle, kernel._spec(), _lib.ptr(X),
+                                                    _lib.ptr(y), len(X), C.byref(h)))
+        return cls(ctx, h)
+
+    def __deepcopy__(self, memo):
+        h = C.c_void_p()
+        _lib.check(self.ctx, _lib.lib().pgp_model_clone(self.handle, C.byref(h)))
+        return _DeviceModel(self.ctx, h)
+
+    def __del__(self):
+        try:
+            if self.handle:
+                _lib.lib().pgp_model_destroy(self.handle)
+                self.handle = None
+        except Exception:       # interpreter shutdown
+            pass
+
+
+class ExactGP(GP):
+    def __init__(self, likelihood, kernel, mean):
+        if not isinstance(likelihood, Gaussian):
+            raise ValueError('exact inference requires a Gaussian likelihood')
+        super(ExactGP, self).__init__(likelihood, kernel, mean)
+        self._dev = None
+        self._ndev = 0          # rows already resident on the device
+
+    @classmethod
+    def from_gp(cls, gp):
+        newgp = cls(gp._likelihood.copy(), gp._kernel.copy(), gp._mean)
+        if gp.ndata > 0:
+            X, y = gp.data
+            newgp.add_data(X, y)
+        return newgp
+
+    def reset(self):
+        self._dev = None
+        self._ndev = 0
+        super(ExactGP, self).reset()
+
+    # -- device state ----------------------------------------------------------
+    def _update(self):
+        L = _lib.lib()
+        n = self.ndata
+        if self._dev is None:
+            self._dev = _DeviceModel.create(self._kernel, self._X, self._y)
+        elif self._ndev < n:
+            Xn, yn = _lib.as_f64(self._X[self._ndev:], 2), _lib.as_f64(self._y[self._ndev:], 1)
+            _lib.check(self._dev.ctx, L.pgp_exact_append(self._dev.handle, _lib.ptr(Xn), _lib.ptr(yn), len(Xn)))
+        self._ndev = n
+        hyp = _lib.as_f64(self.get_hyper())
+        _lib.check(self._dev.ctx, L.pgp_exact_update(self._dev.handle, _lib.ptr(hyp)))
+
+    def _factor(self):
+        n = self.ndata
+        R, a = np.empty((n, n)), np.empty(n)
+        _lib.check(self._dev.ctx, _lib.lib().pgp_exact_get_factor(self._dev.handle, _lib.ptr(R), _lib.ptr(a)))
+        return R, a
+
+    @property
+    def _R(self):
+        """Upper Cholesky factor as the reference stores it (exact.py:54)."""
+        return None if self._dev is None else self._factor()[0]
+
+    @property
+    def _a(self):
+        return None if self._dev is None else self._factor()[1]
+
+    # -- GP interface ------------------------------------------------------------
+    def loglikelihood(self, grad=False):
+        lZ = C.c_double()
+        dlZ = np.empty(self.nhyper) if grad else None
+        _lib.check(self._dev.ctx, _lib.lib().pgp_exact_loglike(
+            self._dev.handle, int(bool(grad)), C.byref(lZ), None if dlZ is None else _lib.ptr(dlZ)))
+        return (lZ.value, dlZ) if grad else lZ.value
+
+    def _marg_posterior(self, X, grad=False):
+        if grad:
+            raise NotImplementedError('posterior input-gradients are outside the B200 hot path (next: N1)')
+        X = _lib.as_f64(X, 2)
+        if self._X is None:
+            # prior: mean and k(x, x)   (exact.py:83-86)
+            return np.full(X.shape[0], self._mean), self._kernel.dget(X)
+        if X.shape[1] != self._kernel.ndim:
+            raise ValueError('test inputs have the wrong number of columns')
+        mu, s2 = np.empty(len(X)), np.empty(len(X))
+        _lib.check(self._dev.ctx, _lib.lib().pgp_exact_predict(
+            self._dev.handle, _lib.ptr(X), len(X), _lib.ptr(mu), _lib.ptr(s2)))
+        return mu, s2

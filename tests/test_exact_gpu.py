@@ -1,0 +1,167 @@
+"""Parity of the ExactGP hot path (pgp_exact_update / _loglike / _predict)
+with the oracle, the committed reference outputs and the survey's known
+answers.  Tolerances: 1e-10 relative on lZ / mu / s2, 1e-8 on gradients
+(BASELINE.json north_star)."""
+
+import numpy as np
+import numpy.testing as nt
+import pytest
+import scipy.optimize as spop
+
+from oracle.cases import GP_CASES, SURVEY_KAT, GP_SN, GP_MEAN, gp_inputs
+from oracle.pygp_oracle import make_kernel, OExactGP, synthetic_problem
+from gpu_util import product_kernel, assert_grad_close, assert_pred_close, LZ_RTOL
+
+pytestmark = pytest.mark.gpu
+
+EXACT = sorted(n for n, c in GP_CASES.items() if not c[3])
+
+
+def build(name):
+    import pygp_b200 as pygp
+    spec, N, d, _ = GP_CASES[name]
+    X, y, Xs, _ = gp_inputs(N, d)
+    gp = pygp.inference.ExactGP(pygp.likelihoods.Gaussian(GP_SN), product_kernel(spec), GP_MEAN)
+    gp.add_data(X, y)
+    return gp, Xs
+
+
+@pytest.mark.parametrize('name', EXACT)
+def test_vs_golden(name, golden):
+    g = golden['gp']
+    gp, Xs = build(name)
+    lZ, dlZ = gp.loglikelihood(True)
+    assert gp.loglikelihood() == lZ
+    mu, s2 = gp.posterior(Xs)
+    nt.assert_allclose(lZ, g[name + '/lZ'], rtol=LZ_RTOL)
+    assert_grad_close(dlZ, g[name + '/dlZ'])
+    assert_pred_close(mu, s2, g[name + '/mu'], g[name + '/s2'])
+    R, a = gp._R, gp._a
+    if R.shape[0] <= 64:
+        nt.assert_allclose(R, g[name + '/R'], rtol=1e-10, atol=1e-12)
+    nt.assert_allclose(a, g[name + '/a'], rtol=1e-9, atol=1e-10)
+    gp.set_hyper(g[name + '/hyper2'])          # the optimiser's access path
+    lZ, dlZ = gp.loglikelihood(True)
+    mu, s2 = gp.posterior(Xs)
+    nt.assert_allclose(lZ, g[name + '/lZ_h2'], rtol=LZ_RTOL)
+    assert_grad_close(dlZ, g[name + '/dlZ_h2'])
+    assert_pred_close(mu, s2, g[name + '/mu_h2'], g[name + '/s2_h2'])
+
+
+@pytest.mark.parametrize('name', sorted(set(SURVEY_KAT) & set(EXACT)))
+def test_vs_survey_kat(name):
+    lZ0, dlZ0, mu0, s20 = SURVEY_KAT[name]
+    gp, Xs = build(name)
+    lZ, dlZ = gp.loglikelihood(True)
+    mu, s2 = gp.posterior(Xs)
+    nt.assert_allclose(lZ, lZ0, rtol=LZ_RTOL)
+    assert_grad_close(dlZ, dlZ0)
+    assert_pred_close(mu, s2, mu0, s20)
+
+
+@pytest.mark.parametrize('spec,N,d,m', [
+    (('se', 1.0, 0.1, 1), 1000, 1, 500),                      # config C1
+    (('se', 1.0, [0.5*np.sqrt(8)]*8), 1537, 8, 300),          # C2-like, ragged N
+    (('matern', 1.0, [2.0]*16, 5), 2048, 16, 257),            # C3-like
+    (('matern', 1.0, [0.3, 0.2], 1), 700, 2, 64),
+    (('sum', ('se', 1.0, 0.5), ('periodic', 0.5, 1.0, 0.25)), 901, 1, 100),   # C5-like
+    (('rq', 0.8, [0.7, 0.9, 1.1], 1.5), 450, 3, 33),
+])
+def test_vs_oracle_medium(spec, N, d, m):
+    import pygp_b200 as pygp
+    X, y, Xs = synthetic_problem(N, d, m)
+    if spec[0] == 'sum':
+        X, Xs = np.sort(X, axis=0)*8, Xs*8
+    gp = pygp.inference.ExactGP(pygp.likelihoods.Gaussian(0.1), product_kernel(spec), 0.0)
+    gp.add_data(X, y)
+    ogp = OExactGP(0.1, make_kernel(spec), 0.0)
+    ogp.add_data(X, y)
+    lZ, dlZ = gp.loglikelihood(True)
+    olZ, odlZ = ogp.loglikelihood(True)
+    nt.assert_allclose(lZ, olZ, rtol=LZ_RTOL)
+    assert_grad_close(dlZ, odlZ)
+    mu, s2 = gp.posterior(Xs)
+    omu, os2 = ogp.posterior(Xs)
+    assert_pred_close(mu, s2, omu, os2, yscale=np.abs(y).max(), sf2=ogp._kernel.dget(Xs[:1])[0])
+    nt.assert_allclose(gp._a, ogp._a, rtol=1e-8, atol=1e-9*np.abs(ogp._a).max())
+
+
+def test_properties_large():
+    """Size-independent properties at a size the oracle would take minutes for:
+    L L^T reproduces K + sn2 I, a solves L a = r, and the analytic gradient
+    matches a central finite difference of lZ."""
+    import pygp_b200 as pygp
+    N, d = 4096 + 77, 4
+    X, y, _ = synthetic_problem(N, d)
+    k = pygp.kernels.SE(1.0, [0.6]*d)
+    gp = pygp.inference.ExactGP(pygp.likelihoods.Gaussian(0.1), k, 0.1)
+    gp.add_data(X, y)
+    R, a = gp._R, gp._a
+    assert np.all(np.triu(R) == R)
+    K = k.get(X) + 0.1**2*np.eye(N)
+    nt.assert_allclose(R.T @ R, K, rtol=1e-12, atol=1e-12)
+    nt.assert_allclose(R.T @ a, y - 0.1, rtol=1e-10, atol=1e-11)
+    lZ, dlZ = gp.loglikelihood(True)
+    nt.assert_allclose(lZ, -0.5*a@a - 0.5*N*np.log(2*np.pi) - np.log(np.diag(R)).sum(), rtol=1e-12)
+    h = gp.get_hyper()
+    for i in (0, 1, 3, len(h)-1):
+        e = np.zeros_like(h)
+        e[i] = 1e-5
+        fd = (gp.copy(h+e).loglikelihood() - gp.copy(h-e).loglikelihood()) / 2e-5
+        nt.assert_allclose(dlZ[i], fd, rtol=2e-6, atol=1e-6*np.abs(dlZ).max())
+
+
+def test_not_positive_definite_raises():
+    # the reference raises LinAlgError from scipy.linalg.cholesky (exact.py:54); no jitter
+    import pygp_b200 as pygp
+    X = np.r_[np.linspace(0, 1, 40), np.linspace(0, 1, 40)][:, None]     # duplicated rows
+    gp = pygp.inference.ExactGP(pygp.likelihoods.Gaussian(1e-12), pygp.kernels.SE(1.0, 5.0, ndim=1), 0.0)
+    with pytest.raises(np.linalg.LinAlgError):
+        gp.add_data(X, np.sin(X[:, 0]))
+
+
+def test_add_data_reset_copy_prior():
+    # reference tests/test_inference.py:39-79,132-145 (full-update branch of add_data)
+    import pygp_b200 as pygp
+    rng = np.random.RandomState(1)
+    X, y = rng.rand(10, 2), rng.rand(10)
+    X2, y2 = rng.rand(10, 2), rng.rand(10)
+    gp = pygp.inference.ExactGP(pygp.likelihoods.Gaussian(1), pygp.kernels.SE(1, 1, ndim=2), 0.0)
+    mu, s2 = gp.posterior(X2)                   # prior
+    nt.assert_array_equal(mu, np.zeros(10))
+    nt.assert_allclose(s2, np.ones(10))
+    gp.add_data(X, y)
+    gp1 = gp.copy()
+    gp1.add_data(X2, y2)
+    gp2 = pygp.inference.ExactGP(pygp.likelihoods.Gaussian(1), pygp.kernels.SE(1, 1, ndim=2), 0.0)
+    gp2.add_data(np.r_[X, X2], np.r_[y, y2])
+    nt.assert_allclose(gp1.posterior(X2), gp2.posterior(X2), rtol=1e-12)
+    nt.assert_allclose(gp1.loglikelihood(), gp2.loglikelihood(), rtol=1e-12)
+    assert gp.ndata == 10 and gp1.ndata == 20
+    p0 = gp.posterior(X2)
+    nt.assert_allclose(gp.copy().posterior(X2), p0, rtol=0, atol=0)
+    gp3 = gp.copy()
+    gp3.reset()
+    assert gp3.ndata == 0 and gp3.data == (None, None)
+    gp3.add_data(X, y)
+    nt.assert_allclose(gp3.posterior(X2), p0)
+    gp4 = pygp.inference.ExactGP.from_gp(gp)
+    nt.assert_allclose(gp4.posterior(X2), p0)
+    h = gp.get_hyper()
+    gp.set_hyper(h)
+    nt.assert_allclose(gp.get_hyper(), h)
+
+
+def test_loglikelihood_fd_basic():
+    # reference tests/test_inference.py:105-112 with BasicGP(1,1,1,0,ndim=2)
+    import pygp_b200 as pygp
+    rng = np.random.RandomState(1)
+    gp = pygp.BasicGP(1, 1, 1, 0, ndim=2)
+    X = rng.rand(10, 2)
+    gp.add_data(X, gp._likelihood.sample(rng.rand(10), rng))
+    x = gp.get_hyper()
+    _, g1 = gp.loglikelihood(grad=True)
+    g2 = spop.approx_fprime(x, lambda x_: gp.copy(x_).loglikelihood(), 1e-8)
+    nt.assert_allclose(g1, g2, rtol=1e-5, atol=1e-5)
+    for kern in ('se', 'matern1', 'matern3', 'matern5'):
+        _ = pygp.BasicGP.from_gp(pygp.BasicGP(1, 1, 1, 0, 2, kern))
