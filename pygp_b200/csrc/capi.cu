@@ -75,6 +75,7 @@ extern "C" void pgp_ctx_destroy(pgp_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     prof_clear(ctx);
+    pool_release(ctx);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -301,13 +302,15 @@ struct pgp_model {
 namespace {
 
 void model_free_work(pgp_model* m) {
-    cudaFree(m->d_Z); m->d_Z = nullptr;
-    cudaFree(m->d_F); m->d_F = nullptr;
-    cudaFree(m->d_G); m->d_G = nullptr;
-    cudaFree(m->d_H); m->d_H = nullptr;
+    pgp_ctx* ctx = m->ctx;
+    cudaStreamSynchronize(ctx->stream);  // pooled buffers may be handed out again at once
+    pool_free(ctx, m->d_Z, (size_t)m->spec.n_parts * m->n * m->ndim);
+    pool_free(ctx, m->d_F, (size_t)(m->n + 1) * m->ld);
+    pool_free(ctx, m->d_G, (size_t)m->n * m->ld);
+    pool_free(ctx, m->d_H, (size_t)m->n * m->ld);
     cudaFree(m->d_alpha); m->d_alpha = nullptr;
     cudaFree(m->d_partials); m->d_partials = nullptr;
-    cudaFree(m->d_Bc); m->d_Bc = nullptr;
+    pool_free(ctx, m->d_Bc, (size_t)m->bc_rows * m->ld);
     m->bc_rows = 0;
     m->factored = false;
 }
@@ -315,8 +318,8 @@ void model_free_work(pgp_model* m) {
 int model_alloc_work(pgp_model* m) {
     pgp_ctx* ctx = m->ctx;
     m->ld = lead_dim(m->n);
-    PGP_TRY(dev_alloc(ctx, &m->d_Z, (size_t)m->spec.n_parts * m->n * m->ndim));
-    PGP_TRY(dev_alloc(ctx, &m->d_F, (size_t)(m->n + 1) * m->ld));
+    PGP_TRY(pool_alloc(ctx, &m->d_Z, (size_t)m->spec.n_parts * m->n * m->ndim));
+    PGP_TRY(pool_alloc(ctx, &m->d_F, (size_t)(m->n + 1) * m->ld));
     PGP_TRY(dev_alloc(ctx, &m->d_alpha, (size_t)m->n));
     return 0;
 }
@@ -508,11 +511,11 @@ extern "C" int pgp_exact_loglike(pgp_model* m, int want_grad, double* lZ, double
     const int64_t n = m->n, ld = m->ld;
     const int nk = m->spec.nhyper;
     if (!m->d_G) {
-        PGP_TRY(dev_alloc(ctx, &m->d_G, (size_t)n * ld));
+        PGP_TRY(pool_alloc(ctx, &m->d_G, (size_t)n * ld));
         // blocks of G below the diagonal are never written: zero them once
         PGP_CUDA(ctx, cudaMemsetAsync(m->d_G, 0, sizeof(double) * n * ld, ctx->stream));
     }
-    if (!m->d_H) PGP_TRY(dev_alloc(ctx, &m->d_H, (size_t)n * ld));
+    if (!m->d_H) PGP_TRY(pool_alloc(ctx, &m->d_H, (size_t)n * ld));
     if (!m->d_partials) PGP_TRY(dev_alloc(ctx, &m->d_partials, (size_t)trace_cta_count(n) * (kMaxHyper + 1)));
     Mat F, G, H;
     F.p = m->d_F; F.ld = ld;
@@ -555,10 +558,10 @@ int predict_chunked(pgp_model* m, const double* Xs, bool xs_on_device, int64_t m
     int64_t chunk = std::max<int64_t>(256, (int64_t)(4ll << 30) / (ld * 8));
     chunk = std::min(chunk, ms);
     if (m->bc_rows < chunk) {
-        cudaFree(m->d_Bc);
-        m->d_Bc = nullptr;
+        PGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        pool_free(ctx, m->d_Bc, (size_t)m->bc_rows * ld);
         m->bc_rows = 0;
-        PGP_TRY(dev_alloc(ctx, &m->d_Bc, (size_t)chunk * ld));
+        PGP_TRY(pool_alloc(ctx, &m->d_Bc, (size_t)chunk * ld));
         m->bc_rows = chunk;
     }
     DevBuf xs, zs, o;

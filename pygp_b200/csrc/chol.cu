@@ -31,95 +31,167 @@ inline int64_t split_point(int64_t n) {
 }
 
 // ---------------------------------------------------------------------------
-// potrf_base: one CTA factors the n x n (n <= 64) diagonal block at (j0, j0)
+// potrf_base: one CTA factors the n x n (n <= 64) diagonal block at (j0, j0).
+// 16 x 16 threads, each owning a cyclic 4 x 4 register micro-tile (rows
+// ty + 16a, columns tx + 16b), so every thread stays busy as the trailing
+// matrix shrinks.  One barrier per column: the owners of column k publish it
+// (double-buffered), everybody derives 1/sqrt(pivot) redundantly and applies
+// the rank-1 update to its registers with 16 independent FMAs.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) potrf_base_kernel(double* F, int64_t ld, int64_t bstride,
                                                          int64_t j0, int n, int* info) {
-    __shared__ double A[kNB][kNB + 1];
-    __shared__ double col[kNB];
-    __shared__ double diag[kNB];
+    __shared__ double colbuf[2][kNB];
     double* Fb = F + (int64_t)blockIdx.x * bstride + j0 * ld + j0;
-    const int tid = threadIdx.x;
-    for (int idx = tid; idx < n * n; idx += 256) {
-        int r = idx / n, c = idx - r * n;
-        if (c <= r) A[r][c] = Fb[(int64_t)r * ld + c];
-    }
-    __syncthreads();
-    const int tx = tid & 15, ty = tid >> 4;
-    for (int k = 0; k < n; ++k) {
-        double d = A[k][k];
-        double s;
-        if (d > 0.0) {
-            s = sqrt(d);
-        } else {
-            // not positive definite (or NaN): report the first failing minor
-            if (tid == 0) atomicCAS(info + blockIdx.x, 0, (int)(j0 + k + 1));
-            s = nan("");
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+
+    double a[4][4];
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y) {
+            int r = ty + 16 * x, c = tx + 16 * y;
+            double v = (r == c) ? 1.0 : 0.0;  // identity padding outside the block
+            if (r < n && c <= r) v = Fb[(int64_t)r * ld + c];
+            a[x][y] = v;
         }
-        if (tid == k) diag[k] = s;
-        if (tid > k && tid < n) {
-            double l = A[tid][k] / s;
-            col[tid] = l;
-            A[tid][k] = l;
+
+    int buf = 0;
+#pragma unroll
+    for (int kb = 0; kb < 4; ++kb) {
+#pragma unroll 1
+        for (int kk = 0; kk < 16; ++kk) {
+            const int k = kb * 16 + kk;
+            if (k >= n) break;
+            if (tx == kk) {
+#pragma unroll
+                for (int x = 0; x < 4; ++x) colbuf[buf][ty + 16 * x] = a[x][kb];
+            }
+            __syncthreads();
+            const double d = colbuf[buf][k];
+            double inv;
+            if (d > 0.0) {
+                inv = rsqrt(d);
+            } else {
+                // not positive definite (or NaN): report the first failing minor
+                if (threadIdx.x == 0) atomicCAS(info + blockIdx.x, 0, (int)(j0 + k + 1));
+                inv = nan("");
+            }
+            double li[4], lj[4];
+#pragma unroll
+            for (int x = 0; x < 4; ++x) li[x] = (ty + 16 * x > k) ? colbuf[buf][ty + 16 * x] * inv : 0.0;
+#pragma unroll
+            for (int y = 0; y < 4; ++y) lj[y] = (tx + 16 * y > k) ? colbuf[buf][tx + 16 * y] * inv : 0.0;
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+#pragma unroll
+                for (int y = 0; y < 4; ++y) a[x][y] -= li[x] * lj[y];
+            if (tx == kk) {
+#pragma unroll
+                for (int x = 0; x < 4; ++x) {
+                    int r = ty + 16 * x;
+                    if (r > k) a[x][kb] = li[x];
+                    else if (r == k) a[x][kb] = (d > 0.0) ? sqrt(d) : nan("");
+                }
+            }
+            buf ^= 1;
         }
-        __syncthreads();
-        for (int i = k + 1 + ty; i < n; i += 16) {
-            double li = col[i];
-            for (int j = k + 1 + tx; j <= i; j += 16) A[i][j] -= li * col[j];
+    }
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y) {
+            int r = ty + 16 * x, c = tx + 16 * y;
+            if (r < n && c <= r) Fb[(int64_t)r * ld + c] = a[x][y];
         }
-        __syncthreads();
-    }
-    for (int idx = tid; idx < n * n; idx += 256) {
-        int r = idx / n, c = idx - r * n;
-        if (c < r) Fb[(int64_t)r * ld + c] = A[r][c];
-        else if (c == r) Fb[(int64_t)r * ld + c] = diag[r];
-    }
 }
 
 // ---------------------------------------------------------------------------
 // trsm_base: X = B T^-T for the n <= 64 columns [j0, j0+n) of `rows` rows of B,
 // T = L[j0.., j0..] lower.  One thread per row: the row lives in registers and
-// is forward-substituted against T broadcast from shared memory.
+// is forward-substituted against T broadcast from shared memory.  Both tiles
+// are staged with one batch of cp.async (a single exposed memory latency);
+// most launches are a fraction of a wave, so latency is what matters.
 // IDENT: B is the identity (rows are rows j0.. of I): used by the inverse.
 // ---------------------------------------------------------------------------
 constexpr int kTrsmRows = 128;
+constexpr int kBtLd = kNB + 2;  // 16-byte aligned rows, 2-way conflicts at most
+
+__device__ __forceinline__ void cp16(double* sdst, const double* gsrc, int bytes) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(sdst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gsrc), "r"(bytes));
+}
 
 template <bool IDENT>
 __global__ void __launch_bounds__(kTrsmRows) trsm_base_kernel(double* B, int64_t ldb, int64_t bstrideB,
                                                               int64_t rows, const double* L, int64_t ldl,
                                                               int64_t bstrideL, int64_t j0, int n) {
     extern __shared__ __align__(16) double sm[];
-    double* Lt = sm;                          // [64][64]  Lt[k][j] = T[j][k], j > k
+    double* Lraw = sm;                        // [64][64]  row-major copy of T, then in place:
+    double* Lt = sm;                          // [64][64]  Lt[k][j] = T[j][k], j > k, else 0
     double* rinv = Lt + kNB * kNB;            // [64]
-    double* Bt = rinv + kNB;                  // [128][65]
+    double* Bt = rinv + kNB;                  // [128][66]
     const int tid = threadIdx.x;
     const int b = blockIdx.y;
     const double* Lb = L + (int64_t)b * bstrideL + j0 * ldl + j0;
     double* Bb = B + (int64_t)b * bstrideB + j0;
     const int64_t r0 = (int64_t)blockIdx.x * kTrsmRows;
+    const bool aligned = ((ldl | ldb) & 1) == 0 && ((reinterpret_cast<uintptr_t>(Lb) | reinterpret_cast<uintptr_t>(Bb)) & 15) == 0;
 
-    for (int idx = tid; idx < kNB * kNB; idx += kTrsmRows) {
-        int j = idx >> 6, k = idx & 63;  // read row j of T along k (coalesced)
-        double v = 0.0;
-        if (j < n && k < j) v = Lb[(int64_t)j * ldl + k];
-        Lt[k * kNB + j] = v;
-        if (j == k) rinv[k] = (k < n) ? 1.0 / Lb[(int64_t)k * ldl + k] : 1.0;
-    }
-    for (int idx = tid; idx < kTrsmRows * kNB; idx += kTrsmRows) {
-        int r = idx >> 6, c = idx & 63;
-        double v = 0.0;
-        if (IDENT) {
-            v = (r0 + r == c) ? 1.0 : 0.0;
-        } else if (r0 + r < rows && c < n) {
-            v = Bb[(r0 + r) * ldb + c];
+    if (aligned) {
+        for (int idx = tid; idx < kNB * kNB / 2; idx += kTrsmRows) {
+            int j = idx >> 5, k = (idx & 31) * 2;
+            int rem = n - k;
+            int bytes = (j < n && rem > 0) ? (rem >= 2 ? 16 : 8) : 0;
+            cp16(Lraw + j * kNB + k, bytes ? Lb + (int64_t)j * ldl + k : Lb, bytes);
         }
-        Bt[r * (kNB + 1) + c] = v;
+        if (!IDENT) {
+            for (int idx = tid; idx < kTrsmRows * kNB / 2; idx += kTrsmRows) {
+                int r = idx >> 5, c = (idx & 31) * 2;
+                int rem = n - c;
+                int bytes = (r0 + r < rows && rem > 0) ? (rem >= 2 ? 16 : 8) : 0;
+                cp16(Bt + r * kBtLd + c, bytes ? Bb + (r0 + r) * ldb + c : Bb, bytes);
+            }
+        }
+        asm volatile("cp.async.commit_group;\n" ::);
+        asm volatile("cp.async.wait_group 0;\n" ::);
+    } else {
+        for (int idx = tid; idx < kNB * kNB; idx += kTrsmRows) {
+            int j = idx >> 6, k = idx & 63;
+            Lraw[idx] = (j < n && k < n) ? Lb[(int64_t)j * ldl + k] : 0.0;
+        }
+        if (!IDENT) {
+            for (int idx = tid; idx < kTrsmRows * kNB; idx += kTrsmRows) {
+                int r = idx >> 6, c = idx & 63;
+                Bt[r * kBtLd + c] = (r0 + r < rows && c < n) ? Bb[(r0 + r) * ldb + c] : 0.0;
+            }
+        }
+    }
+    __syncthreads();
+    // transpose + mask T in place through registers (the strict upper triangle
+    // of the global buffer is scratch and must not be used)
+    {
+        double tv[kNB * kNB / kTrsmRows];
+#pragma unroll
+        for (int q = 0; q < kNB * kNB / kTrsmRows; ++q) {
+            int idx = tid + q * kTrsmRows;
+            int k = idx >> 6, j = idx & 63;
+            tv[q] = (j < n && k < j) ? Lraw[j * kNB + k] : 0.0;
+        }
+        double dinv = 1.0;
+        if (tid < n) dinv = 1.0 / Lraw[tid * kNB + tid];
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < kNB * kNB / kTrsmRows; ++q) Lt[tid + q * kTrsmRows] = tv[q];
+        if (tid < kNB) rinv[tid] = dinv;
     }
     __syncthreads();
 
     double x[kNB];
 #pragma unroll
-    for (int c = 0; c < kNB; ++c) x[c] = Bt[tid * (kNB + 1) + c];
+    for (int c = 0; c < kNB; ++c) {
+        if (IDENT) x[c] = (r0 + tid == c) ? 1.0 : 0.0;
+        else x[c] = Bt[tid * kBtLd + c];
+    }
 #pragma unroll
     for (int k = 0; k < kNB; ++k) {
         x[k] *= rinv[k];
@@ -128,16 +200,16 @@ __global__ void __launch_bounds__(kTrsmRows) trsm_base_kernel(double* B, int64_t
         for (int j = k + 1; j < kNB; ++j) x[j] -= xk * Lt[k * kNB + j];
     }
 #pragma unroll
-    for (int c = 0; c < kNB; ++c) Bt[tid * (kNB + 1) + c] = x[c];
+    for (int c = 0; c < kNB; ++c) Bt[tid * kBtLd + c] = x[c];
     __syncthreads();
 
     for (int idx = tid; idx < kTrsmRows * kNB; idx += kTrsmRows) {
         int r = idx >> 6, c = idx & 63;
-        if (r0 + r < rows && c < n) Bb[(r0 + r) * ldb + c] = Bt[r * (kNB + 1) + c];
+        if (r0 + r < rows && c < n) Bb[(r0 + r) * ldb + c] = Bt[r * kBtLd + c];
     }
 }
 
-constexpr size_t kTrsmSmem = (kNB * kNB + kNB + kTrsmRows * (kNB + 1)) * sizeof(double);
+constexpr size_t kTrsmSmem = (kNB * kNB + kNB + kTrsmRows * kBtLd) * sizeof(double);
 
 int launch_potrf_base(pgp_ctx* ctx, const Mat& F, int64_t j0, int n, int* d_info) {
     Launch L(ctx, PC_POTRF, (double)n * n * n / 3.0 * F.batch);

@@ -41,6 +41,14 @@ struct pgp_ctx {
     // small pinned staging area for hypers / results
     double* h_pin = nullptr;
     size_t h_pin_doubles = 0;
+    // cache of large device buffers released by destroyed models: cudaMalloc /
+    // cudaFree of multi-GiB buffers cost ~0.1 s each, more than the transfer of
+    // the inputs they serve (the e2e path creates a model per call)
+    struct PoolEntry { void* p; size_t bytes; };
+    std::vector<PoolEntry> pool;
+    size_t pool_bytes = 0;
+    static constexpr size_t kPoolMin = (size_t)1 << 20;       // do not pool < 1 MiB
+    static constexpr size_t kPoolCap = (size_t)96 << 30;      // keep at most 96 GiB cached
 
     int fail(int code, const std::string& msg) {
         err = msg;
@@ -111,6 +119,49 @@ inline int dev_alloc(pgp_ctx* ctx, T** p, size_t count) {
         return ctx->fail(PGP_E_NOMEM, buf);
     }
     return 0;
+}
+
+// pooled allocation for the large per-model buffers
+template <class T>
+inline int pool_alloc(pgp_ctx* ctx, T** p, size_t count) {
+    size_t bytes = count * sizeof(T);
+    if (bytes >= pgp_ctx::kPoolMin) {
+        for (size_t i = 0; i < ctx->pool.size(); ++i) {
+            if (ctx->pool[i].bytes == bytes) {
+                *p = reinterpret_cast<T*>(ctx->pool[i].p);
+                ctx->pool_bytes -= bytes;
+                ctx->pool.erase(ctx->pool.begin() + i);
+                return 0;
+            }
+        }
+    }
+    int rc = dev_alloc(ctx, p, count);
+    if (rc == PGP_E_NOMEM && !ctx->pool.empty()) {  // give the cache back and retry
+        for (auto& e : ctx->pool) cudaFree(e.p);
+        ctx->pool.clear();
+        ctx->pool_bytes = 0;
+        rc = dev_alloc(ctx, p, count);
+    }
+    return rc;
+}
+
+template <class T>
+inline void pool_free(pgp_ctx* ctx, T*& p, size_t count) {
+    if (!p) return;
+    size_t bytes = count * sizeof(T);
+    if (bytes >= pgp_ctx::kPoolMin && ctx->pool_bytes + bytes <= pgp_ctx::kPoolCap) {
+        ctx->pool.push_back({(void*)p, bytes});
+        ctx->pool_bytes += bytes;
+    } else {
+        cudaFree(p);
+    }
+    p = nullptr;
+}
+
+inline void pool_release(pgp_ctx* ctx) {
+    for (auto& e : ctx->pool) cudaFree(e.p);
+    ctx->pool.clear();
+    ctx->pool_bytes = 0;
 }
 
 inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }

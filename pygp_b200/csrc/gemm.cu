@@ -16,6 +16,8 @@
 
 #include "gemm.cuh"
 
+#include <cstdlib>
+
 namespace pgp {
 
 namespace {
@@ -23,9 +25,13 @@ namespace {
 constexpr int BM = 128, BN = 128, BK = 16;
 constexpr int STAGES = 4;
 constexpr int LDS = BK + 4;  // padded shared row (doubles)
-constexpr int GEMM_THREADS = 256;
 constexpr int STAGE_DOUBLES = (BM + BN) * LDS;
 constexpr size_t GEMM_SMEM = (size_t)STAGES * STAGE_DOUBLES * sizeof(double);
+// CTAs are rasterised in groups of GROUP_M tile rows (column index fastest
+// inside a group) so that the ~148 CTAs in flight share a ~12 x 12 block of
+// tiles: each operand k-slice is then fetched from HBM once per wave and
+// served to the other CTAs from L2.
+constexpr int GROUP_M = 12;
 
 __device__ __forceinline__ void cp_async16(double* smem_dst, const double* gsrc, int src_bytes) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -45,11 +51,12 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 
 // one operand tile (128 rows x 16 k) -> shared; rows >= rows_valid and
 // k >= k_valid are zero-filled
+template <int THREADS>
 __device__ __forceinline__ void load_tile(double* sdst, const double* g, int64_t ld, int64_t row0,
                                           int64_t rows_total, int64_t k0, int64_t k_end) {
 #pragma unroll
-    for (int q = 0; q < (BM * BK / 2) / GEMM_THREADS; ++q) {
-        int c = threadIdx.x + q * GEMM_THREADS;
+    for (int q = 0; q < (BM * BK / 2) / THREADS; ++q) {
+        int c = threadIdx.x + q * THREADS;
         int row = c >> 3;
         int kc = (c & 7) * 2;
         int64_t gr = row0 + row;
@@ -63,11 +70,27 @@ __device__ __forceinline__ void load_tile(double* sdst, const double* g, int64_t
 
 }  // namespace
 
-__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_nt_kernel(GemmArgs a) {
+// WM x WN warps; each warp owns a (BM/WM) x (BN/WN) tile = MI x NJ DMMA tiles.
+template <int WM, int WN>
+__global__ void __launch_bounds__(WM * WN * 32, 1) gemm_nt_kernel(GemmArgs a, int tm, int tn) {
+    constexpr int THREADS = WM * WN * 32;
+    constexpr int MI = BM / WM / 8, NJ = BN / WN / 8;
     extern __shared__ __align__(16) double smem[];
 
-    const int64_t m0 = (int64_t)blockIdx.y * BM;
-    const int64_t n0 = (int64_t)blockIdx.x * BN;
+    // grouped rasterisation of the linear CTA index
+    int tile_m, tile_n;
+    {
+        const int pid = blockIdx.x;
+        const int per_group = GROUP_M * tn;
+        const int group = pid / per_group;
+        const int first_m = group * GROUP_M;
+        const int gsz = min(tm - first_m, GROUP_M);
+        const int local = pid - group * per_group;
+        tile_m = first_m + local % gsz;
+        tile_n = local / gsz;
+    }
+    const int64_t m0 = (int64_t)tile_m * BM;
+    const int64_t n0 = (int64_t)tile_n * BN;
     if (a.tri && n0 > m0 + BM - 1 + a.tri_off) return;
 
     const int b = blockIdx.z;
@@ -85,14 +108,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_nt_kernel(GemmArgs a) {
     const int KT = (int)((a.K - ks + BK - 1) / BK);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int wm = warp >> 2, wn = warp & 3;  // 2 x 4 warps
+    const int wm = warp / WN, wn = warp % WN;
     const int g = lane >> 2, t = lane & 3;
 
-    double acc[8][4][2];
+    double acc[MI][NJ][2];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < MI; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int j = 0; j < NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
     // prologue: fill STAGES-1 slots
 #pragma unroll
@@ -100,8 +123,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_nt_kernel(GemmArgs a) {
         if (s < KT) {
             double* As = smem + s * STAGE_DOUBLES;
             double* Bs = As + BM * LDS;
-            load_tile(As, A, a.lda, m0, a.M, ks + (int64_t)s * BK, a.K);
-            load_tile(Bs, B, a.ldb, n0, a.N, ks + (int64_t)s * BK, a.K);
+            load_tile<THREADS>(As, A, a.lda, m0, a.M, ks + (int64_t)s * BK, a.K);
+            load_tile<THREADS>(Bs, B, a.ldb, n0, a.N, ks + (int64_t)s * BK, a.K);
         }
         cp_async_commit();
     }
@@ -115,24 +138,24 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_nt_kernel(GemmArgs a) {
                 int s = nk % STAGES;
                 double* As = smem + s * STAGE_DOUBLES;
                 double* Bs = As + BM * LDS;
-                load_tile(As, A, a.lda, m0, a.M, ks + (int64_t)nk * BK, a.K);
-                load_tile(Bs, B, a.ldb, n0, a.N, ks + (int64_t)nk * BK, a.K);
+                load_tile<THREADS>(As, A, a.lda, m0, a.M, ks + (int64_t)nk * BK, a.K);
+                load_tile<THREADS>(Bs, B, a.ldb, n0, a.N, ks + (int64_t)nk * BK, a.K);
             }
             cp_async_commit();
         }
-        const double* As = smem + (kt % STAGES) * STAGE_DOUBLES + (wm * 64 + g) * LDS + t;
-        const double* Bs = smem + (kt % STAGES) * STAGE_DOUBLES + BM * LDS + (wn * 32 + g) * LDS + t;
+        const double* As = smem + (kt % STAGES) * STAGE_DOUBLES + (wm * (BM / WM) + g) * LDS + t;
+        const double* Bs = smem + (kt % STAGES) * STAGE_DOUBLES + BM * LDS + (wn * (BN / WN) + g) * LDS + t;
 #pragma unroll
         for (int kk = 0; kk < BK / 4; ++kk) {
-            double af[8], bf[4];
+            double af[MI], bf[NJ];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) af[i] = As[i * 8 * LDS + kk * 4];
+            for (int i = 0; i < MI; ++i) af[i] = As[i * 8 * LDS + kk * 4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) bf[j] = Bs[j * 8 * LDS + kk * 4];
+            for (int j = 0; j < NJ; ++j) bf[j] = Bs[j * 8 * LDS + kk * 4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+            for (int i = 0; i < MI; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+                for (int j = 0; j < NJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
         }
     }
     cp_async_wait<0>();
@@ -141,12 +164,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_nt_kernel(GemmArgs a) {
     const double alpha = a.alpha, beta = a.beta;
     const bool vec_ok = ((a.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        int64_t row = m0 + wm * 64 + i * 8 + g;
+    for (int i = 0; i < MI; ++i) {
+        int64_t row = m0 + wm * (BM / WM) + i * 8 + g;
         if (row >= a.M) continue;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            int64_t col = n0 + wn * 32 + j * 8 + 2 * t;
+        for (int j = 0; j < NJ; ++j) {
+            int64_t col = n0 + wn * (BN / WN) + j * 8 + 2 * t;
             if (col >= a.N) continue;
             double* p = C + row * a.ldc + col;
             double v0 = alpha * acc[i][j][0], v1 = alpha * acc[i][j][1];
@@ -174,14 +197,13 @@ int launch_gemm_nt(pgp_ctx* ctx, const GemmArgs& a) {
     if ((a.lda & 1) || (a.ldb & 1) || (reinterpret_cast<uintptr_t>(a.A) & 15) ||
         (reinterpret_cast<uintptr_t>(a.B) & 15) || ((a.strideA | a.strideB) & 1))
         return ctx->fail(PGP_E_ARG, "gemm_nt: A and B must be 16-byte aligned with even leading dimensions");
-    static bool attr_set = false;
-    if (!attr_set) {
-        PGP_CUDA(ctx, cudaFuncSetAttribute(gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)GEMM_SMEM));
-        attr_set = true;
-    }
+    static const int variant = [] { const char* e = getenv("PGP_GEMM_VARIANT"); return e ? atoi(e) : 0; }();
+    PGP_CUDA(ctx, cudaFuncSetAttribute(gemm_nt_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)GEMM_SMEM));
+    PGP_CUDA(ctx, cudaFuncSetAttribute(gemm_nt_kernel<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)GEMM_SMEM));
     int64_t tm = ceil_div(a.M, BM), tn = ceil_div(a.N, BN);
-    if (tm > 65535 || a.batch > 65535) return ctx->fail(PGP_E_ARG, "gemm_nt: grid too large");
+    if (tm * tn > 0x7fffffffLL || a.batch > 65535) return ctx->fail(PGP_E_ARG, "gemm_nt: grid too large");
     // algorithmic flops of this launch (roofline numerator): per tile row, the
     // columns on/below the diagonal times the contraction length actually needed
     double flops = 0.0;
@@ -194,7 +216,11 @@ int launch_gemm_nt(pgp_ctx* ctx, const GemmArgs& a) {
         flops += 2.0 * rows * cols * klen;
     }
     Launch L(ctx, PC_GEMM, flops * a.batch);
-    gemm_nt_kernel<<<dim3((unsigned)tn, (unsigned)tm, a.batch), GEMM_THREADS, GEMM_SMEM, ctx->stream>>>(a);
+    dim3 grid((unsigned)(tm * tn), 1, a.batch);
+    if (variant == 1)
+        gemm_nt_kernel<4, 4><<<grid, 512, GEMM_SMEM, ctx->stream>>>(a, (int)tm, (int)tn);
+    else
+        gemm_nt_kernel<2, 4><<<grid, 256, GEMM_SMEM, ctx->stream>>>(a, (int)tm, (int)tn);
     return check_launch(ctx, "gemm_nt_kernel");
 }
 

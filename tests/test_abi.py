@@ -45,7 +45,7 @@ def test_library_is_sm100a_only(built):
 
 
 def test_gemm_uses_fp64_tensor_pipe(built):
-    sass = subprocess.check_output(['cuobjdump', '-sass', '-fun', '_ZN3pgp14gemm_nt_kernelENS_8GemmArgsE',
+    sass = subprocess.check_output(['cuobjdump', '-sass', '-fun', '_ZN3pgp14gemm_nt_kernelILi2ELi4EEEvNS_8GemmArgsEii',
                                     built.LIB_PATH]).decode()
     assert sass.count('DMMA.8x8x4') >= 128
     assert 'LDGSTS' in sass          # cp.async staging
