@@ -4,12 +4,15 @@
 // FP64 mma shape lowers to DMMA.8x8x4 (checked with cuobjdump), so the kernel is
 // written against m8n8k4 directly.  Bound: FP64 tensor pipe.
 //
-// Tiling: CTA tile 128 x 128 x 16, 8 warps as 2 (M) x 4 (N), warp tile 64 x 32
-// = 8 x 4 DMMA tiles = 64 accumulator doubles per lane.  Operands are staged by
-// a 4-deep cp.async ring (16-byte chunks, zero-fill predication at the M/N/K
+// Tiling: CTA tile 128 x 128 x 32, 16 warps as 4 (M) x 4 (N), warp tile 32 x 32
+// = 4 x 4 DMMA tiles = 32 accumulator doubles per lane (the 8-warp 64 x 32
+// layouts stay selectable through PGP_GEMM_VARIANT for tuning; measured within
+// 3 % of each other, profiles/r01_gemm_variants.txt).  Operands are staged by a
+// 3-deep cp.async ring (16-byte chunks, zero-fill predication at the M/N/K
 // edges, so no padding of the matrices is needed).  Shared rows are padded to
-// 20 doubles: the DMMA fragment loads (lane -> row lane/4, k lane%4) of a
-// half-warp then fall in 16 distinct 8-byte banks.
+// BK + 4 doubles: the DMMA fragment loads (lane -> row lane/4, k lane%4) of a
+// half-warp then fall in 16 distinct 8-byte banks (ncu: 0 bank conflicts).
+// Fragments are double-buffered in registers across the 4-wide k steps.
 //
 // Structure flags let the same kernel serve every O(N^3) step of the factor,
 // the triangular inverse and V V^T without touching zero blocks (gemm.cuh).
@@ -22,16 +25,20 @@ namespace pgp {
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 16;
-constexpr int STAGES = 4;
-constexpr int LDS = BK + 4;  // padded shared row (doubles)
-constexpr int STAGE_DOUBLES = (BM + BN) * LDS;
-constexpr size_t GEMM_SMEM = (size_t)STAGES * STAGE_DOUBLES * sizeof(double);
+constexpr int BM = 128, BN = 128;
 // CTAs are rasterised in groups of GROUP_M tile rows (column index fastest
 // inside a group) so that the ~148 CTAs in flight share a ~12 x 12 block of
 // tiles: each operand k-slice is then fetched from HBM once per wave and
 // served to the other CTAs from L2.
 constexpr int GROUP_M = 12;
+
+template <int BK_, int STAGES_>
+struct Cfg {
+    static constexpr int BK = BK_, STAGES = STAGES_;
+    static constexpr int LDS = BK + 4;  // padded shared row (doubles): conflict-free fragment loads
+    static constexpr int STAGE_DOUBLES = (BM + BN) * LDS;
+    static constexpr size_t SMEM = (size_t)STAGES * STAGE_DOUBLES * sizeof(double);
+};
 
 __device__ __forceinline__ void cp_async16(double* smem_dst, const double* gsrc, int src_bytes) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -49,32 +56,16 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                  : "d"(a), "d"(b));
 }
 
-// one operand tile (128 rows x 16 k) -> shared; rows >= rows_valid and
-// k >= k_valid are zero-filled
-template <int THREADS>
-__device__ __forceinline__ void load_tile(double* sdst, const double* g, int64_t ld, int64_t row0,
-                                          int64_t rows_total, int64_t k0, int64_t k_end) {
-#pragma unroll
-    for (int q = 0; q < (BM * BK / 2) / THREADS; ++q) {
-        int c = threadIdx.x + q * THREADS;
-        int row = c >> 3;
-        int kc = (c & 7) * 2;
-        int64_t gr = row0 + row;
-        int64_t gk = k0 + kc;
-        int64_t rem = k_end - gk;
-        int bytes = (gr < rows_total && rem > 0) ? (rem >= 2 ? 16 : 8) : 0;
-        const double* src = bytes ? g + gr * ld + gk : g;
-        cp_async16(sdst + row * LDS + kc, src, bytes);
-    }
-}
-
 }  // namespace
 
 // WM x WN warps; each warp owns a (BM/WM) x (BN/WN) tile = MI x NJ DMMA tiles.
-template <int WM, int WN>
+template <int WM, int WN, class C>
 __global__ void __launch_bounds__(WM * WN * 32, 1) gemm_nt_kernel(GemmArgs a, int tm, int tn) {
     constexpr int THREADS = WM * WN * 32;
     constexpr int MI = BM / WM / 8, NJ = BN / WN / 8;
+    constexpr int BK = C::BK, STAGES = C::STAGES, LDS = C::LDS, STAGE_DOUBLES = C::STAGE_DOUBLES;
+    constexpr int CPR = BK / 2;                      // 16-byte chunks per operand row
+    constexpr int NCH = (BM * CPR) / THREADS;        // chunks per thread per operand tile
     extern __shared__ __align__(16) double smem[];
 
     // grouped rasterisation of the linear CTA index
@@ -96,7 +87,7 @@ __global__ void __launch_bounds__(WM * WN * 32, 1) gemm_nt_kernel(GemmArgs a, in
     const int b = blockIdx.z;
     const double* __restrict__ A = a.A + (int64_t)b * a.strideA;
     const double* __restrict__ B = a.B + (int64_t)b * a.strideB;
-    double* __restrict__ C = a.C + (int64_t)b * a.strideC;
+    double* __restrict__ Cm = a.C + (int64_t)b * a.strideC;
 
     int64_t ks = 0;
     if (a.krow) {
@@ -111,21 +102,46 @@ __global__ void __launch_bounds__(WM * WN * 32, 1) gemm_nt_kernel(GemmArgs a, in
     const int wm = warp / WN, wn = warp % WN;
     const int g = lane >> 2, t = lane & 3;
 
+    // per-thread copy descriptors, fixed for the whole k loop: chunk q of this
+    // thread covers row (tid + q THREADS) / CPR, k offset 2 ((tid + q THREADS) % CPR)
+    const double* srcA[NCH];
+    const double* srcB[NCH];
+    int soff[NCH], kof[NCH];
+    bool okA[NCH], okB[NCH];
+#pragma unroll
+    for (int q = 0; q < NCH; ++q) {
+        int c = threadIdx.x + q * THREADS;
+        int row = c / CPR;
+        kof[q] = (c % CPR) * 2;
+        soff[q] = row * LDS + kof[q];
+        okA[q] = m0 + row < a.M;
+        okB[q] = n0 + row < a.N;
+        srcA[q] = A + (okA[q] ? (m0 + row) * a.lda : 0) + ks + kof[q];
+        srcB[q] = B + (okB[q] ? (n0 + row) * a.ldb : 0) + ks + kof[q];
+    }
+    auto load_stage = [&](int slot, int ktile) {
+        double* As = smem + slot * STAGE_DOUBLES;
+        double* Bs = As + BM * LDS;
+        const int64_t koff = (int64_t)ktile * BK;
+        const int64_t kleft = a.K - ks - koff;  // valid k from this tile's start
+#pragma unroll
+        for (int q = 0; q < NCH; ++q) {
+            int64_t rem = kleft - kof[q];
+            int bytes = rem >= 2 ? 16 : (rem == 1 ? 8 : 0);
+            cp_async16(As + soff[q], okA[q] && bytes ? srcA[q] + koff : A, okA[q] ? bytes : 0);
+            cp_async16(Bs + soff[q], okB[q] && bytes ? srcB[q] + koff : B, okB[q] ? bytes : 0);
+        }
+    };
+
     double acc[MI][NJ][2];
 #pragma unroll
     for (int i = 0; i < MI; ++i)
 #pragma unroll
         for (int j = 0; j < NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-    // prologue: fill STAGES-1 slots
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
-        if (s < KT) {
-            double* As = smem + s * STAGE_DOUBLES;
-            double* Bs = As + BM * LDS;
-            load_tile<THREADS>(As, A, a.lda, m0, a.M, ks + (int64_t)s * BK, a.K);
-            load_tile<THREADS>(Bs, B, a.ldb, n0, a.N, ks + (int64_t)s * BK, a.K);
-        }
+        if (s < KT) load_stage(s, s);
         cp_async_commit();
     }
 
@@ -134,35 +150,38 @@ __global__ void __launch_bounds__(WM * WN * 32, 1) gemm_nt_kernel(GemmArgs a, in
         __syncthreads();
         {
             int nk = kt + STAGES - 1;
-            if (nk < KT) {
-                int s = nk % STAGES;
-                double* As = smem + s * STAGE_DOUBLES;
-                double* Bs = As + BM * LDS;
-                load_tile<THREADS>(As, A, a.lda, m0, a.M, ks + (int64_t)nk * BK, a.K);
-                load_tile<THREADS>(Bs, B, a.ldb, n0, a.N, ks + (int64_t)nk * BK, a.K);
-            }
+            if (nk < KT) load_stage(nk % STAGES, nk);
             cp_async_commit();
         }
         const double* As = smem + (kt % STAGES) * STAGE_DOUBLES + (wm * (BM / WM) + g) * LDS + t;
         const double* Bs = smem + (kt % STAGES) * STAGE_DOUBLES + BM * LDS + (wn * (BN / WN) + g) * LDS + t;
+        // fragments double-buffered in registers: the loads of step kk+1 are in
+        // flight while the DMMAs of step kk issue
+        double af[2][MI], bf[2][NJ];
+#pragma unroll
+        for (int i = 0; i < MI; ++i) af[0][i] = As[i * 8 * LDS];
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) bf[0][j] = Bs[j * 8 * LDS];
 #pragma unroll
         for (int kk = 0; kk < BK / 4; ++kk) {
-            double af[MI], bf[NJ];
+            const int cur = kk & 1, nxt = cur ^ 1;
+            if (kk + 1 < BK / 4) {
 #pragma unroll
-            for (int i = 0; i < MI; ++i) af[i] = As[i * 8 * LDS + kk * 4];
+                for (int i = 0; i < MI; ++i) af[nxt][i] = As[i * 8 * LDS + (kk + 1) * 4];
 #pragma unroll
-            for (int j = 0; j < NJ; ++j) bf[j] = Bs[j * 8 * LDS + kk * 4];
+                for (int j = 0; j < NJ; ++j) bf[nxt][j] = Bs[j * 8 * LDS + (kk + 1) * 4];
+            }
 #pragma unroll
             for (int i = 0; i < MI; ++i)
 #pragma unroll
-                for (int j = 0; j < NJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+                for (int j = 0; j < NJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[cur][i], bf[cur][j]);
         }
     }
     cp_async_wait<0>();
 
     // epilogue: lane owns C[row = 8i + g][col = 8j + 2t, +1] of its warp tile
     const double alpha = a.alpha, beta = a.beta;
-    const bool vec_ok = ((a.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+    const bool vec_ok = ((a.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(Cm) & 15) == 0);
 #pragma unroll
     for (int i = 0; i < MI; ++i) {
         int64_t row = m0 + wm * (BM / WM) + i * 8 + g;
@@ -171,7 +190,7 @@ __global__ void __launch_bounds__(WM * WN * 32, 1) gemm_nt_kernel(GemmArgs a, in
         for (int j = 0; j < NJ; ++j) {
             int64_t col = n0 + wn * (BN / WN) + j * 8 + 2 * t;
             if (col >= a.N) continue;
-            double* p = C + row * a.ldc + col;
+            double* p = Cm + row * a.ldc + col;
             double v0 = alpha * acc[i][j][0], v1 = alpha * acc[i][j][1];
             if (vec_ok && col + 1 < a.N) {
                 if (beta != 0.0) {
@@ -192,16 +211,23 @@ __global__ void __launch_bounds__(WM * WN * 32, 1) gemm_nt_kernel(GemmArgs a, in
     }
 }
 
+namespace {
+template <int WM, int WN, class C>
+int launch_variant(pgp_ctx* ctx, const GemmArgs& a, int64_t tm, int64_t tn) {
+    auto kern = gemm_nt_kernel<WM, WN, C>;
+    PGP_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    dim3 grid((unsigned)(tm * tn), 1, a.batch);
+    kern<<<grid, WM * WN * 32, C::SMEM, ctx->stream>>>(a, (int)tm, (int)tn);
+    return 0;
+}
+}  // namespace
+
 int launch_gemm_nt(pgp_ctx* ctx, const GemmArgs& a) {
     if (a.M <= 0 || a.N <= 0) return 0;
     if ((a.lda & 1) || (a.ldb & 1) || (reinterpret_cast<uintptr_t>(a.A) & 15) ||
         (reinterpret_cast<uintptr_t>(a.B) & 15) || ((a.strideA | a.strideB) & 1))
         return ctx->fail(PGP_E_ARG, "gemm_nt: A and B must be 16-byte aligned with even leading dimensions");
     static const int variant = [] { const char* e = getenv("PGP_GEMM_VARIANT"); return e ? atoi(e) : 0; }();
-    PGP_CUDA(ctx, cudaFuncSetAttribute(gemm_nt_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)GEMM_SMEM));
-    PGP_CUDA(ctx, cudaFuncSetAttribute(gemm_nt_kernel<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)GEMM_SMEM));
     int64_t tm = ceil_div(a.M, BM), tn = ceil_div(a.N, BN);
     if (tm * tn > 0x7fffffffLL || a.batch > 65535) return ctx->fail(PGP_E_ARG, "gemm_nt: grid too large");
     // algorithmic flops of this launch (roofline numerator): per tile row, the
@@ -216,11 +242,14 @@ int launch_gemm_nt(pgp_ctx* ctx, const GemmArgs& a) {
         flops += 2.0 * rows * cols * klen;
     }
     Launch L(ctx, PC_GEMM, flops * a.batch);
-    dim3 grid((unsigned)(tm * tn), 1, a.batch);
-    if (variant == 1)
-        gemm_nt_kernel<4, 4><<<grid, 512, GEMM_SMEM, ctx->stream>>>(a, (int)tm, (int)tn);
-    else
-        gemm_nt_kernel<2, 4><<<grid, 256, GEMM_SMEM, ctx->stream>>>(a, (int)tm, (int)tn);
+    int rc;
+    switch (variant) {
+        case 1: rc = launch_variant<4, 4, Cfg<16, 4>>(ctx, a, tm, tn); break;
+        case 2: rc = launch_variant<2, 4, Cfg<32, 3>>(ctx, a, tm, tn); break;
+        case 4: rc = launch_variant<2, 4, Cfg<16, 4>>(ctx, a, tm, tn); break;
+        default: rc = launch_variant<4, 4, Cfg<32, 3>>(ctx, a, tm, tn); break;
+    }
+    PGP_TRY(rc);
     return check_launch(ctx, "gemm_nt_kernel");
 }
 

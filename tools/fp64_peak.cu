@@ -67,9 +67,11 @@ int main() {
         int blocks = sms * (warps * 32 / threads);
         double ms = time_ms(dmma_loop, d, blocks, threads, iters);
         double tf = (double)blocks * (threads / 32) * iters * 16 * 512.0 / (ms * 1e-3) / 1e12;
+        fprintf(stderr, "warps/SM %2d: dmma %.2f TF", warps, tf);
         if (tf > best_dmma) { best_dmma = tf; wd = warps; }
         ms = time_ms(dfma_loop, d, blocks, threads, iters);
         double tf2 = (double)blocks * threads * iters * 16 * 2.0 / (ms * 1e-3) / 1e12;
+        fprintf(stderr, "  dfma %.2f TF\n", tf2);
         if (tf2 > best_dfma) { best_dfma = tf2; wf = warps; }
     }
     printf("{\"gpu\": \"%s\", \"sms\": %d, \"dmma_tflops\": %.2f, \"dmma_warps_per_sm\": %d, "
