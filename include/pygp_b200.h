@@ -175,6 +175,17 @@ int pgp_dev_gemm_nt(pgp_ctx* ctx, int64_t m, int64_t n, int64_t k,
                     double alpha, const double* d_A, int64_t lda,
                     const double* d_B, int64_t ldb,
                     double beta, double* d_C, int64_t ldc, int tri);
+/* general form: transA -> A stored (k, m); transB -> B stored (k, n), i.e.
+ * (0,0) C = A B^T, (0,1) C = A B, (1,1) C = A^T B.  splitk: 0 auto, 1 off,
+ * > 1 that many slices of the contraction (deterministic reduction). */
+int pgp_dev_gemm(pgp_ctx* ctx, int transA, int transB, int64_t m, int64_t n, int64_t k,
+                 double alpha, const double* d_A, int64_t lda,
+                 const double* d_B, int64_t ldb,
+                 double beta, double* d_C, int64_t ldc, int tri, int splitk);
+/* d_B (rows, ldb)[:, 0:n) <- B L^-T (notrans = 0, scipy solve_triangular(R, ., trans=True)
+ * on the transposed layout) or B L^-1 (notrans = 1); L (n, ldl) lower. */
+int pgp_dev_trsm(pgp_ctx* ctx, double* d_B, int64_t rows, int64_t ldb,
+                 const double* d_L, int64_t n, int64_t ldl, int notrans);
 /* in-place lower Cholesky of a device matrix (n, n) row-major with `extra`
  * further rows below it that receive the same right-solves (row n = r -> a). */
 int pgp_dev_potrf(pgp_ctx* ctx, double* d_F, int64_t n, int64_t ld, int64_t extra);

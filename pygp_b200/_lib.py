@@ -83,6 +83,9 @@ SIGNATURES = {
     'pgp_fitc_predict': (C.c_int, [_vp, _dp, _i64, _dp, _dp]),
     'pgp_dev_gemm_nt': (C.c_int, [_vp, _i64, _i64, _i64, C.c_double, _vp, _i64, _vp, _i64,
                                   C.c_double, _vp, _i64, C.c_int]),
+    'pgp_dev_gemm': (C.c_int, [_vp, C.c_int, C.c_int, _i64, _i64, _i64, C.c_double, _vp, _i64, _vp, _i64,
+                               C.c_double, _vp, _i64, C.c_int, C.c_int]),
+    'pgp_dev_trsm': (C.c_int, [_vp, _vp, _i64, _i64, _vp, _i64, _i64, C.c_int]),
     'pgp_dev_potrf': (C.c_int, [_vp, _vp, _i64, _i64, _i64]),
 }
 

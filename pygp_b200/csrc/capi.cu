@@ -76,6 +76,7 @@ extern "C" void pgp_ctx_destroy(pgp_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     prof_clear(ctx);
     pool_release(ctx);
+    if (ctx->gemm_ws) cudaFree(ctx->gemm_ws);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -785,6 +786,32 @@ extern "C" int pgp_dev_gemm_nt(pgp_ctx* ctx, int64_t m, int64_t n, int64_t k, do
     g.alpha = alpha; g.beta = beta;
     g.tri = tri;
     return launch_gemm_nt(ctx, g);
+}
+
+extern "C" int pgp_dev_gemm(pgp_ctx* ctx, int transA, int transB, int64_t m, int64_t n, int64_t k, double alpha,
+                            const double* d_A, int64_t lda, const double* d_B, int64_t ldb, double beta, double* d_C,
+                            int64_t ldc, int tri, int splitk) {
+    if (!ctx) return PGP_E_ARG;
+    PGP_TRY(set_device(ctx));
+    GemmArgs g;
+    g.A = d_A; g.lda = lda; g.transA = transA;
+    g.B = d_B; g.ldb = ldb; g.transB = transB;
+    g.C = d_C; g.ldc = ldc;
+    g.M = m; g.N = n; g.K = k;
+    g.alpha = alpha; g.beta = beta;
+    g.tri = tri;
+    g.splitk = splitk;
+    return launch_gemm(ctx, g);
+}
+
+extern "C" int pgp_dev_trsm(pgp_ctx* ctx, double* d_B, int64_t rows, int64_t ldb, const double* d_L, int64_t n,
+                            int64_t ldl, int notrans) {
+    if (!ctx) return PGP_E_ARG;
+    PGP_TRY(set_device(ctx));
+    Mat B, L;
+    B.p = d_B; B.ld = ldb;
+    L.p = const_cast<double*>(d_L); L.ld = ldl;
+    return notrans ? trsm_right_l(ctx, B, rows, L, n) : trsm_right_lt(ctx, B, rows, L, n);
 }
 
 extern "C" int pgp_dev_potrf(pgp_ctx* ctx, double* d_F, int64_t n, int64_t ld, int64_t extra) {

@@ -121,7 +121,10 @@ __device__ __forceinline__ void cp16(double* sdst, const double* gsrc, int bytes
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gsrc), "r"(bytes));
 }
 
-template <bool IDENT>
+// NOTRANS: solve X T = B instead (back substitution over the columns, T used
+// row-wise): the no-transpose right solve FITC needs (B = L^-1 (V ell),
+// fitc.py:197, and chol(A)^-1 beta, fitc.py:188).
+template <bool IDENT, bool NOTRANS>
 __global__ void __launch_bounds__(kTrsmRows) trsm_base_kernel(double* B, int64_t ldb, int64_t bstrideB,
                                                               int64_t rows, const double* L, int64_t ldl,
                                                               int64_t bstrideL, int64_t j0, int n) {
@@ -175,7 +178,8 @@ __global__ void __launch_bounds__(kTrsmRows) trsm_base_kernel(double* B, int64_t
         for (int q = 0; q < kNB * kNB / kTrsmRows; ++q) {
             int idx = tid + q * kTrsmRows;
             int k = idx >> 6, j = idx & 63;
-            tv[q] = (j < n && k < j) ? Lraw[j * kNB + k] : 0.0;
+            if (NOTRANS) tv[q] = (k < n && j < k) ? Lraw[k * kNB + j] : 0.0;   // Lt[k][j] = T[k][j], j < k
+            else tv[q] = (j < n && k < j) ? Lraw[j * kNB + k] : 0.0;
         }
         double dinv = 1.0;
         if (tid < n) dinv = 1.0 / Lraw[tid * kNB + tid];
@@ -192,12 +196,22 @@ __global__ void __launch_bounds__(kTrsmRows) trsm_base_kernel(double* B, int64_t
         if (IDENT) x[c] = (r0 + tid == c) ? 1.0 : 0.0;
         else x[c] = Bt[tid * kBtLd + c];
     }
+    if (NOTRANS) {
 #pragma unroll
-    for (int k = 0; k < kNB; ++k) {
-        x[k] *= rinv[k];
-        const double xk = x[k];
+        for (int k = kNB - 1; k >= 0; --k) {
+            x[k] *= rinv[k];
+            const double xk = x[k];
 #pragma unroll
-        for (int j = k + 1; j < kNB; ++j) x[j] -= xk * Lt[k * kNB + j];
+            for (int j = 0; j < k; ++j) x[j] -= xk * Lt[k * kNB + j];
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < kNB; ++k) {
+            x[k] *= rinv[k];
+            const double xk = x[k];
+#pragma unroll
+            for (int j = k + 1; j < kNB; ++j) x[j] -= xk * Lt[k * kNB + j];
+        }
     }
 #pragma unroll
     for (int c = 0; c < kNB; ++c) Bt[tid * kBtLd + c] = x[c];
@@ -217,10 +231,10 @@ int launch_potrf_base(pgp_ctx* ctx, const Mat& F, int64_t j0, int n, int* d_info
     return check_launch(ctx, "potrf_base_kernel");
 }
 
-template <bool IDENT>
+template <bool IDENT, bool NOTRANS = false>
 int launch_trsm_base(pgp_ctx* ctx, const Mat& B, int64_t rows, const Mat& L, int64_t j0, int n) {
     if (rows <= 0) return 0;
-    auto kern = trsm_base_kernel<IDENT>;
+    auto kern = trsm_base_kernel<IDENT, NOTRANS>;
     PGP_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTrsmSmem));
     int64_t blocks = ceil_div(rows, kTrsmRows);
     Launch Lc(ctx, PC_TRSM, (double)rows * n * n * B.batch);
@@ -269,6 +283,24 @@ int trsm_rec(pgp_ctx* ctx, const Mat& B, int64_t rows, const Mat& L, int64_t j0,
     return trsm_rec(ctx, B, rows, L, c0, n2);
 }
 
+// X L = B on columns [j0, j0+n): solve the right block first, then eliminate it
+// from the left block with an NN GEMM (L21 is read with k as its row index)
+int trsm_nt_rec(pgp_ctx* ctx, const Mat& B, int64_t rows, const Mat& L, int64_t j0, int64_t n) {
+    if (n <= kNB) return launch_trsm_base<false, true>(ctx, B, rows, L, j0, (int)n);
+    int64_t n1 = split_point(n), n2 = n - n1, c0 = j0 + n1;
+    PGP_TRY(trsm_nt_rec(ctx, B, rows, L, c0, n2));
+    GemmArgs g;
+    g.A = B.p + c0; g.lda = B.ld;                    // X2 (rows, n2)
+    g.B = L.p + c0 * L.ld + j0; g.ldb = L.ld;        // L21 (n2, n1), k = row
+    g.C = B.p + j0; g.ldc = B.ld;                    // B1 (rows, n1)
+    g.M = rows; g.N = n1; g.K = n2;
+    g.alpha = -1.0; g.beta = 1.0;
+    g.transB = 1;
+    g.splitk = 1;
+    PGP_TRY(launch_gemm(ctx, g));
+    return trsm_nt_rec(ctx, B, rows, L, j0, n1);
+}
+
 int inv_rec(pgp_ctx* ctx, const Mat& G, const Mat& L, int64_t j0, int64_t n) {
     if (n <= kNB) {
         Mat B = G;
@@ -296,6 +328,12 @@ int potrf_lower(pgp_ctx* ctx, const Mat& F, int64_t n, int64_t extra, int* d_inf
 int trsm_right_lt(pgp_ctx* ctx, const Mat& B, int64_t rows, const Mat& L, int64_t n) {
     if (n <= 0 || rows <= 0) return 0;
     return trsm_rec(ctx, B, rows, L, 0, n);
+}
+
+int trsm_right_l(pgp_ctx* ctx, const Mat& B, int64_t rows, const Mat& L, int64_t n) {
+    if (n <= 0 || rows <= 0) return 0;
+    if (B.batch != 1 || L.batch != 1) return ctx->fail(PGP_E_ARG, "trsm_right_l: not batched");
+    return trsm_nt_rec(ctx, B, rows, L, 0, n);
 }
 
 int inv_upper(pgp_ctx* ctx, const Mat& G, const Mat& L, int64_t n) {

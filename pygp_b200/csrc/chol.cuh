@@ -27,6 +27,9 @@ int potrf_lower(pgp_ctx* ctx, const Mat& F, int64_t n, int64_t extra, int* d_inf
 // B[:, 0:n) <- B L^-T for `rows` rows of B (same column space as L).
 int trsm_right_lt(pgp_ctx* ctx, const Mat& B, int64_t rows, const Mat& L, int64_t n);
 
+// B[:, 0:n) <- B L^-1 (no transpose) for `rows` rows of B.
+int trsm_right_l(pgp_ctx* ctx, const Mat& B, int64_t rows, const Mat& L, int64_t n);
+
 // G (pre-zeroed outside its upper triangle) <- L^-T, upper triangular.
 int inv_upper(pgp_ctx* ctx, const Mat& G, const Mat& L, int64_t n);
 

@@ -41,6 +41,9 @@ struct pgp_ctx {
     // small pinned staging area for hypers / results
     double* h_pin = nullptr;
     size_t h_pin_doubles = 0;
+    // split-K workspace of the GEMM (grown on demand, stream-ordered reuse)
+    double* gemm_ws = nullptr;
+    size_t gemm_ws_doubles = 0;
     // cache of large device buffers released by destroyed models: cudaMalloc /
     // cudaFree of multi-GiB buffers cost ~0.1 s each, more than the transfer of
     // the inputs they serve (the e2e path creates a model per call)

@@ -1,4 +1,5 @@
-// gemm.cu -- FP64 tensor-core GEMM for sm_100a:  C = beta C + alpha A B^T.
+// gemm.cu -- FP64 tensor-core GEMM for sm_100a:  C = beta C + alpha op(A) op(B)^T
+// (NT form for the factorisation; TN / NN forms for FITC, see gemm.cuh).
 //
 // Why mma.sync and not tcgen05: tcgen05.mma has no f64 kind; on sm_100a every
 // FP64 mma shape lowers to DMMA.8x8x4 (checked with cuobjdump), so the kernel is
@@ -19,6 +20,7 @@
 
 #include "gemm.cuh"
 
+#include <algorithm>
 #include <cstdlib>
 
 namespace pgp {
@@ -36,7 +38,9 @@ template <int BK_, int STAGES_>
 struct Cfg {
     static constexpr int BK = BK_, STAGES = STAGES_;
     static constexpr int LDS = BK + 4;  // padded shared row (doubles): conflict-free fragment loads
-    static constexpr int STAGE_DOUBLES = (BM + BN) * LDS;
+    static constexpr int LDT = BM + 4;  // row of a transposed-operand tile ([k][m]); 132 = 4 mod 16
+    static constexpr int TILE_DOUBLES = BM * LDS > BK * LDT ? BM * LDS : BK * LDT;
+    static constexpr int STAGE_DOUBLES = 2 * TILE_DOUBLES;
     static constexpr size_t SMEM = (size_t)STAGES * STAGE_DOUBLES * sizeof(double);
 };
 
@@ -59,13 +63,20 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 }  // namespace
 
 // WM x WN warps; each warp owns a (BM/WM) x (BN/WN) tile = MI x NJ DMMA tiles.
-template <int WM, int WN, class C>
-__global__ void __launch_bounds__(WM * WN * 32, 1) gemm_nt_kernel(GemmArgs a, int tm, int tn) {
+// TA / TB: the operand is stored with the contraction index as its ROW index
+// (A is (K, M) row-major / B is (K, N) row-major); its tile is then staged as
+// [k][m] with a row of BM + 4 doubles, which keeps the fragment loads
+// (lane -> m = lane/4, k = lane%4) conflict-free as well: 132 = 4 (mod 16).
+template <int WM, int WN, class C, bool TA, bool TB>
+__global__ void __launch_bounds__(WM * WN * 32, 1) gemm_kernel(GemmArgs a, int tm, int tn) {
     constexpr int THREADS = WM * WN * 32;
     constexpr int MI = BM / WM / 8, NJ = BN / WN / 8;
-    constexpr int BK = C::BK, STAGES = C::STAGES, LDS = C::LDS, STAGE_DOUBLES = C::STAGE_DOUBLES;
-    constexpr int CPR = BK / 2;                      // 16-byte chunks per operand row
+    constexpr int BK = C::BK, STAGES = C::STAGES, LDS = C::LDS, LDT = C::LDT;
+    constexpr int TILE_DOUBLES = C::TILE_DOUBLES, STAGE_DOUBLES = C::STAGE_DOUBLES;
+    constexpr int CPR = BK / 2;                      // 16-byte chunks per operand row (k contiguous)
+    constexpr int CPT = BM / 2;                      // ... per row of a transposed tile (m contiguous)
     constexpr int NCH = (BM * CPR) / THREADS;        // chunks per thread per operand tile
+    static_assert(BM == BN, "square CTA tile assumed by the copy descriptors");
     extern __shared__ __align__(16) double smem[];
 
     // grouped rasterisation of the linear CTA index
@@ -89,47 +100,92 @@ __global__ void __launch_bounds__(WM * WN * 32, 1) gemm_nt_kernel(GemmArgs a, in
     const double* __restrict__ B = a.B + (int64_t)b * a.strideB;
     double* __restrict__ Cm = a.C + (int64_t)b * a.strideC;
 
-    int64_t ks = 0;
+    // contraction range of this CTA: [ks, ke)
+    int64_t ks = 0, ke = a.K;
     if (a.krow) {
         ks = m0 + a.krow_off;
         if (ks < 0) ks = 0;
         ks = ks / BK * BK;
         if (ks > a.K) ks = a.K;
     }
-    const int KT = (int)((a.K - ks + BK - 1) / BK);
+    if (a.splitk > 1) {  // blockIdx.y = slice of the contraction; partial result to the workspace
+        const int64_t per = (a.K + a.splitk - 1) / a.splitk;
+        const int64_t kc = (per + BK - 1) / BK * BK;
+        ks = (int64_t)blockIdx.y * kc;
+        ke = min(a.K, ks + kc);
+        if (ks > ke) ks = ke;
+        Cm = a.ws + ((int64_t)b * a.splitk + blockIdx.y) * a.M * a.ldws;
+    }
+    const int KT = (int)((ke - ks + BK - 1) / BK);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wm = warp / WN, wn = warp % WN;
     const int g = lane >> 2, t = lane & 3;
 
-    // per-thread copy descriptors, fixed for the whole k loop: chunk q of this
-    // thread covers row (tid + q THREADS) / CPR, k offset 2 ((tid + q THREADS) % CPR)
+    // per-thread copy descriptors, fixed for the whole k loop.
+    //   normal operand:     chunk c -> row c / CPR, k offset 2 (c % CPR)
+    //   transposed operand: chunk c -> k row c / CPT, m offset 2 (c % CPT)
     const double* srcA[NCH];
     const double* srcB[NCH];
-    int soff[NCH], kof[NCH];
-    bool okA[NCH], okB[NCH];
+    int soffA[NCH], soffB[NCH], kofA[NCH], kofB[NCH];
+    int bytA[NCH], bytB[NCH];  // bytes valid along the non-contraction direction (transposed) or 16/0 (normal)
 #pragma unroll
     for (int q = 0; q < NCH; ++q) {
         int c = threadIdx.x + q * THREADS;
-        int row = c / CPR;
-        kof[q] = (c % CPR) * 2;
-        soff[q] = row * LDS + kof[q];
-        okA[q] = m0 + row < a.M;
-        okB[q] = n0 + row < a.N;
-        srcA[q] = A + (okA[q] ? (m0 + row) * a.lda : 0) + ks + kof[q];
-        srcB[q] = B + (okB[q] ? (n0 + row) * a.ldb : 0) + ks + kof[q];
+        if (!TA) {
+            int row = c / CPR;
+            kofA[q] = (c % CPR) * 2;
+            soffA[q] = row * LDS + kofA[q];
+            bool ok = m0 + row < a.M;
+            bytA[q] = ok ? 16 : 0;
+            srcA[q] = A + (ok ? (m0 + row) * a.lda : 0) + ks + kofA[q];
+        } else {
+            int kr = c / CPT, mo = (c % CPT) * 2;
+            kofA[q] = kr;
+            soffA[q] = kr * LDT + mo;
+            int64_t rem = a.M - (m0 + mo);
+            bytA[q] = rem >= 2 ? 16 : (rem == 1 ? 8 : 0);
+            srcA[q] = A + (ks + kr) * a.lda + (bytA[q] ? m0 + mo : 0);
+        }
+        if (!TB) {
+            int row = c / CPR;
+            kofB[q] = (c % CPR) * 2;
+            soffB[q] = row * LDS + kofB[q];
+            bool ok = n0 + row < a.N;
+            bytB[q] = ok ? 16 : 0;
+            srcB[q] = B + (ok ? (n0 + row) * a.ldb : 0) + ks + kofB[q];
+        } else {
+            int kr = c / CPT, no = (c % CPT) * 2;
+            kofB[q] = kr;
+            soffB[q] = kr * LDT + no;
+            int64_t rem = a.N - (n0 + no);
+            bytB[q] = rem >= 2 ? 16 : (rem == 1 ? 8 : 0);
+            srcB[q] = B + (ks + kr) * a.ldb + (bytB[q] ? n0 + no : 0);
+        }
     }
     auto load_stage = [&](int slot, int ktile) {
         double* As = smem + slot * STAGE_DOUBLES;
-        double* Bs = As + BM * LDS;
+        double* Bs = As + TILE_DOUBLES;
         const int64_t koff = (int64_t)ktile * BK;
-        const int64_t kleft = a.K - ks - koff;  // valid k from this tile's start
+        const int64_t kleft = ke - ks - koff;  // valid k from this tile's start
 #pragma unroll
         for (int q = 0; q < NCH; ++q) {
-            int64_t rem = kleft - kof[q];
-            int bytes = rem >= 2 ? 16 : (rem == 1 ? 8 : 0);
-            cp_async16(As + soff[q], okA[q] && bytes ? srcA[q] + koff : A, okA[q] ? bytes : 0);
-            cp_async16(Bs + soff[q], okB[q] && bytes ? srcB[q] + koff : B, okB[q] ? bytes : 0);
+            if (!TA) {
+                int64_t rem = kleft - kofA[q];
+                int bytes = bytA[q] ? (rem >= 2 ? 16 : (rem == 1 ? 8 : 0)) : 0;
+                cp_async16(As + soffA[q], bytes ? srcA[q] + koff : A, bytes);
+            } else {
+                int bytes = kofA[q] < kleft ? bytA[q] : 0;
+                cp_async16(As + soffA[q], bytes ? srcA[q] + koff * a.lda : A, bytes);
+            }
+            if (!TB) {
+                int64_t rem = kleft - kofB[q];
+                int bytes = bytB[q] ? (rem >= 2 ? 16 : (rem == 1 ? 8 : 0)) : 0;
+                cp_async16(Bs + soffB[q], bytes ? srcB[q] + koff : B, bytes);
+            } else {
+                int bytes = kofB[q] < kleft ? bytB[q] : 0;
+                cp_async16(Bs + soffB[q], bytes ? srcB[q] + koff * a.ldb : B, bytes);
+            }
         }
     };
 
@@ -145,6 +201,11 @@ __global__ void __launch_bounds__(WM * WN * 32, 1) gemm_nt_kernel(GemmArgs a, in
         cp_async_commit();
     }
 
+    // fragment addressing: element (row r of the warp tile, k) lives at
+    //   normal: r * LDS + k          transposed: k * LDT + r
+    constexpr int A_RS = TA ? 1 : LDS, A_KS = TA ? LDT : 1;
+    constexpr int B_RS = TB ? 1 : LDS, B_KS = TB ? LDT : 1;
+
     for (int kt = 0; kt < KT; ++kt) {
         cp_async_wait<STAGES - 2>();
         __syncthreads();
@@ -153,23 +214,23 @@ __global__ void __launch_bounds__(WM * WN * 32, 1) gemm_nt_kernel(GemmArgs a, in
             if (nk < KT) load_stage(nk % STAGES, nk);
             cp_async_commit();
         }
-        const double* As = smem + (kt % STAGES) * STAGE_DOUBLES + (wm * (BM / WM) + g) * LDS + t;
-        const double* Bs = smem + (kt % STAGES) * STAGE_DOUBLES + BM * LDS + (wn * (BN / WN) + g) * LDS + t;
+        const double* As = smem + (kt % STAGES) * STAGE_DOUBLES + (wm * (BM / WM) + g) * A_RS + t * A_KS;
+        const double* Bs = smem + (kt % STAGES) * STAGE_DOUBLES + TILE_DOUBLES + (wn * (BN / WN) + g) * B_RS + t * B_KS;
         // fragments double-buffered in registers: the loads of step kk+1 are in
         // flight while the DMMAs of step kk issue
         double af[2][MI], bf[2][NJ];
 #pragma unroll
-        for (int i = 0; i < MI; ++i) af[0][i] = As[i * 8 * LDS];
+        for (int i = 0; i < MI; ++i) af[0][i] = As[i * 8 * A_RS];
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) bf[0][j] = Bs[j * 8 * LDS];
+        for (int j = 0; j < NJ; ++j) bf[0][j] = Bs[j * 8 * B_RS];
 #pragma unroll
         for (int kk = 0; kk < BK / 4; ++kk) {
             const int cur = kk & 1, nxt = cur ^ 1;
             if (kk + 1 < BK / 4) {
 #pragma unroll
-                for (int i = 0; i < MI; ++i) af[nxt][i] = As[i * 8 * LDS + (kk + 1) * 4];
+                for (int i = 0; i < MI; ++i) af[nxt][i] = As[i * 8 * A_RS + (kk + 1) * 4 * A_KS];
 #pragma unroll
-                for (int j = 0; j < NJ; ++j) bf[nxt][j] = Bs[j * 8 * LDS + (kk + 1) * 4];
+                for (int j = 0; j < NJ; ++j) bf[nxt][j] = Bs[j * 8 * B_RS + (kk + 1) * 4 * B_KS];
             }
 #pragma unroll
             for (int i = 0; i < MI; ++i)
@@ -180,8 +241,10 @@ __global__ void __launch_bounds__(WM * WN * 32, 1) gemm_nt_kernel(GemmArgs a, in
     cp_async_wait<0>();
 
     // epilogue: lane owns C[row = 8i + g][col = 8j + 2t, +1] of its warp tile
-    const double alpha = a.alpha, beta = a.beta;
-    const bool vec_ok = ((a.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(Cm) & 15) == 0);
+    const bool part = a.splitk > 1;
+    const double alpha = part ? 1.0 : a.alpha, beta = part ? 0.0 : a.beta;
+    const int64_t ldc = part ? a.ldws : a.ldc;
+    const bool vec_ok = ((ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(Cm) & 15) == 0);
 #pragma unroll
     for (int i = 0; i < MI; ++i) {
         int64_t row = m0 + wm * (BM / WM) + i * 8 + g;
@@ -190,7 +253,7 @@ __global__ void __launch_bounds__(WM * WN * 32, 1) gemm_nt_kernel(GemmArgs a, in
         for (int j = 0; j < NJ; ++j) {
             int64_t col = n0 + wn * (BN / WN) + j * 8 + 2 * t;
             if (col >= a.N) continue;
-            double* p = Cm + row * a.ldc + col;
+            double* p = Cm + row * ldc + col;
             double v0 = alpha * acc[i][j][0], v1 = alpha * acc[i][j][1];
             if (vec_ok && col + 1 < a.N) {
                 if (beta != 0.0) {
@@ -211,25 +274,70 @@ __global__ void __launch_bounds__(WM * WN * 32, 1) gemm_nt_kernel(GemmArgs a, in
     }
 }
 
+// C = beta C + alpha sum_s ws[s]  (fixed summation order: deterministic)
+__global__ void splitk_reduce_kernel(GemmArgs a) {
+    const int b = blockIdx.z;
+    const int64_t total = a.M * a.N;
+    double* Cm = a.C + (int64_t)b * a.strideC;
+    const double* ws = a.ws + (int64_t)b * a.splitk * a.M * a.ldws;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = idx / a.N, c = idx - r * a.N;
+        if (a.tri && c > r + a.tri_off) continue;
+        double s = 0.0;
+        for (int k = 0; k < a.splitk; ++k) s += ws[((int64_t)k * a.M + r) * a.ldws + c];
+        double* p = Cm + r * a.ldc + c;
+        *p = a.beta != 0.0 ? a.beta * *p + a.alpha * s : a.alpha * s;
+    }
+}
+
 namespace {
-template <int WM, int WN, class C>
+template <int WM, int WN, class C, bool TA, bool TB>
 int launch_variant(pgp_ctx* ctx, const GemmArgs& a, int64_t tm, int64_t tn) {
-    auto kern = gemm_nt_kernel<WM, WN, C>;
+    auto kern = gemm_kernel<WM, WN, C, TA, TB>;
     PGP_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
-    dim3 grid((unsigned)(tm * tn), 1, a.batch);
+    dim3 grid((unsigned)(tm * tn), (unsigned)std::max(a.splitk, 1), a.batch);
     kern<<<grid, WM * WN * 32, C::SMEM, ctx->stream>>>(a, (int)tm, (int)tn);
     return 0;
 }
 }  // namespace
 
-int launch_gemm_nt(pgp_ctx* ctx, const GemmArgs& a) {
+int launch_gemm(pgp_ctx* ctx, const GemmArgs& a_in) {
+    GemmArgs a = a_in;
     if (a.M <= 0 || a.N <= 0) return 0;
     if ((a.lda & 1) || (a.ldb & 1) || (reinterpret_cast<uintptr_t>(a.A) & 15) ||
         (reinterpret_cast<uintptr_t>(a.B) & 15) || ((a.strideA | a.strideB) & 1))
-        return ctx->fail(PGP_E_ARG, "gemm_nt: A and B must be 16-byte aligned with even leading dimensions");
+        return ctx->fail(PGP_E_ARG, "gemm: A and B must be 16-byte aligned with even leading dimensions");
+    if ((a.transA || a.transB) && (a.krow || a.batch != 1))
+        return ctx->fail(PGP_E_ARG, "gemm: krow / batch are only supported for the NT form");
     static const int variant = [] { const char* e = getenv("PGP_GEMM_VARIANT"); return e ? atoi(e) : 0; }();
     int64_t tm = ceil_div(a.M, BM), tn = ceil_div(a.N, BN);
-    if (tm * tn > 0x7fffffffLL || a.batch > 65535) return ctx->fail(PGP_E_ARG, "gemm_nt: grid too large");
+    if (tm * tn > 0x7fffffffLL || a.batch > 65535) return ctx->fail(PGP_E_ARG, "gemm: grid too large");
+    // split the contraction when the output has too few tiles to fill the GPU
+    // (FITC: p x p results contracted over n >> p): partials go to a workspace
+    // and are summed in a fixed order
+    a.splitk = 1;
+    if (a_in.splitk != 1 && !a.krow && a.batch == 1) {
+        int64_t tiles = a.tri ? tm * (tm + 1) / 2 : tm * tn;
+        int64_t want = a_in.splitk > 1 ? a_in.splitk : (2 * ctx->sm_count) / std::max<int64_t>(tiles, 1);
+        int64_t max_by_k = a.K / 2048;  // keep >= 2048 contraction steps per slice
+        int64_t S = std::min<int64_t>(std::min<int64_t>(want, max_by_k), 64);
+        if (a_in.splitk > 1) S = std::min<int64_t>(a_in.splitk, std::max<int64_t>(a.K / 32, 1));
+        if (S > 1) {
+            a.splitk = (int)S;
+            a.ldws = round_up(a.N, 2);
+            size_t need = (size_t)S * a.M * a.ldws;
+            if (ctx->gemm_ws_doubles < need) {
+                PGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                if (ctx->gemm_ws) cudaFree(ctx->gemm_ws);
+                ctx->gemm_ws = nullptr;
+                ctx->gemm_ws_doubles = 0;
+                PGP_TRY(dev_alloc(ctx, &ctx->gemm_ws, need));
+                ctx->gemm_ws_doubles = need;
+            }
+            a.ws = ctx->gemm_ws;
+        }
+    }
     // algorithmic flops of this launch (roofline numerator): per tile row, the
     // columns on/below the diagonal times the contraction length actually needed
     double flops = 0.0;
@@ -241,16 +349,35 @@ int launch_gemm_nt(pgp_ctx* ctx, const GemmArgs& a) {
         if (a.krow) klen = std::min(std::max((double)a.K - (mid + (double)a.krow_off), 0.0), (double)a.K);
         flops += 2.0 * rows * cols * klen;
     }
-    Launch L(ctx, PC_GEMM, flops * a.batch);
-    int rc;
-    switch (variant) {
-        case 1: rc = launch_variant<4, 4, Cfg<16, 4>>(ctx, a, tm, tn); break;
-        case 2: rc = launch_variant<2, 4, Cfg<32, 3>>(ctx, a, tm, tn); break;
-        case 4: rc = launch_variant<2, 4, Cfg<16, 4>>(ctx, a, tm, tn); break;
-        default: rc = launch_variant<4, 4, Cfg<32, 3>>(ctx, a, tm, tn); break;
+    {
+        Launch L(ctx, PC_GEMM, flops * a.batch);
+        int rc;
+        if (a.transA && a.transB) rc = launch_variant<4, 4, Cfg<32, 3>, true, true>(ctx, a, tm, tn);
+        else if (a.transA) rc = launch_variant<4, 4, Cfg<32, 3>, true, false>(ctx, a, tm, tn);
+        else if (a.transB) rc = launch_variant<4, 4, Cfg<32, 3>, false, true>(ctx, a, tm, tn);
+        else switch (variant) {
+            case 1: rc = launch_variant<4, 4, Cfg<16, 4>, false, false>(ctx, a, tm, tn); break;
+            case 2: rc = launch_variant<2, 4, Cfg<32, 3>, false, false>(ctx, a, tm, tn); break;
+            case 4: rc = launch_variant<2, 4, Cfg<16, 4>, false, false>(ctx, a, tm, tn); break;
+            default: rc = launch_variant<4, 4, Cfg<32, 3>, false, false>(ctx, a, tm, tn); break;
+        }
+        PGP_TRY(rc);
+        PGP_TRY(check_launch(ctx, "gemm_kernel"));
     }
-    PGP_TRY(rc);
-    return check_launch(ctx, "gemm_nt_kernel");
+    if (a.splitk > 1) {
+        Launch L(ctx, PC_OTHER, 8.0 * a.splitk * a.M * a.N);
+        int blocks = (int)std::min<int64_t>(ceil_div(a.M * a.N, 256), (int64_t)ctx->sm_count * 8);
+        splitk_reduce_kernel<<<dim3(blocks, 1, a.batch), 256, 0, ctx->stream>>>(a);
+        PGP_TRY(check_launch(ctx, "splitk_reduce_kernel"));
+    }
+    return 0;
+}
+
+int launch_gemm_nt(pgp_ctx* ctx, const GemmArgs& a) {
+    GemmArgs g = a;
+    g.transA = g.transB = 0;
+    g.splitk = 1;
+    return launch_gemm(ctx, g);
 }
 
 }  // namespace pgp

@@ -26,8 +26,21 @@ struct GemmArgs {
     int64_t krow_off = 0;
     int batch = 1;
     int64_t strideA = 0, strideB = 0, strideC = 0;
+    // general forms (launch_gemm): transA -> A is stored (K x M) row-major,
+    // transB -> B is stored (K x N) row-major, i.e.
+    //   NT (0,0): C = A B^T     NN (0,1): C = A B     TN (1,1): C = A^T B
+    int transA = 0, transB = 0;
+    // contraction split: 0 = automatic (few output tiles, long K), 1 = off,
+    // > 1 = that many slices.  Partials go to the context workspace and are
+    // reduced in a fixed order (deterministic).
+    int splitk = 1;
+    double* ws = nullptr;   // set by the launcher
+    int64_t ldws = 0;
 };
 
+// NT form, no split (the factorisation's work-horse)
 int launch_gemm_nt(pgp_ctx* ctx, const GemmArgs& a);
+// any form; honours transA / transB / splitk
+int launch_gemm(pgp_ctx* ctx, const GemmArgs& a);
 
 }  // namespace pgp

@@ -153,8 +153,9 @@ __global__ void __launch_bounds__(kThreads) gram_kernel(GramArgs a) {
     const int ndim = a.ndim, n_parts = a.n_parts;
 
     load_hdr(S, a.spec + b);
-    stage_tile(Zs1, a.Z1 + (int64_t)b * n_parts * a.n1 * ndim, a.n1 * ndim, a.n1, i0, ndim, n_parts);
-    stage_tile(Zs2, a.Z2 + (int64_t)b * n_parts * a.n2 * ndim, a.n2 * ndim, a.n2, j0, ndim, n_parts);
+    const int64_t zs1 = a.zs1 ? a.zs1 : a.n1 * ndim, zs2 = a.zs2 ? a.zs2 : a.n2 * ndim;
+    stage_tile(Zs1, a.Z1 + (int64_t)b * n_parts * zs1, zs1, a.n1, i0, ndim, n_parts);
+    stage_tile(Zs2, a.Z2 + (int64_t)b * n_parts * zs2, zs2, a.n2, j0, ndim, n_parts);
     __syncthreads();
 
     Tile t;
@@ -288,6 +289,116 @@ int launch_gram(pgp_ctx* ctx, const GramArgs& a) {
 #undef PGP_GRAM_CASE
 }
 
+// accumulate sum_{entries of one 64 x 64 tile} wq * dK_h for every hyper h into
+// acc[1 + h] (the caller owns acc[0]); K and all dK_h are recomputed from the
+// staged inputs, nothing is read from memory.
+template <int PTYPE>
+__device__ __forceinline__ void trace_tile(const DevSpecHdr* S, const double* Zs1, const double* Zs2, int ndim,
+                                           int n_parts, const Tile& t, double (&wq)[4][4], double* acc) {
+    if (PTYPE >= 0) {
+        double D[4][4];
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+            for (int y = 0; y < 4; ++y) D[x][y] = 0.0;
+        for (int k = 0; k < ndim; ++k) {
+            double zi[4], zj[4];
+#pragma unroll
+            for (int x = 0; x < 4; ++x) zi[x] = Zs1[k * kTile + t.row(x)];
+            double2 q0 = *reinterpret_cast<const double2*>(&Zs2[k * kTile + 2 * t.tx]);
+            double2 q1 = *reinterpret_cast<const double2*>(&Zs2[k * kTile + 2 * t.tx + 32]);
+            zj[0] = q0.x; zj[1] = q0.y; zj[2] = q1.x; zj[3] = q1.y;
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+#pragma unroll
+                for (int y = 0; y < 4; ++y) {
+                    double df = zi[x] - zj[y];
+                    D[x][y] += df * df;
+                }
+        }
+        DevPart part = S->parts[0];
+        part.type = PTYPE;
+        double s_sf = 0.0, s_iso = 0.0, s_e0 = 0.0;
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+            for (int y = 0; y < 4; ++y) {
+                PartVal v;
+                part_eval<true>(part, D[x][y], v);
+                double w = wq[x][y];
+                s_sf += w * v.g_sf;
+                s_iso += w * v.g_iso;
+                s_e0 += w * v.e0;
+                D[x][y] = w * v.ardw;  // reuse as ARD weight
+            }
+        acc[1] += s_sf;
+        if (PTYPE == PGP_PERIODIC) {
+            acc[2] += s_iso;
+            acc[3] += s_e0;
+        } else if (part.iso) {
+            acc[2] += s_iso;
+            if (PTYPE == PGP_RQ) acc[3] += s_e0;
+        } else {
+            for (int k = 0; k < ndim; ++k) {
+                double zi[4], zj[4];
+#pragma unroll
+                for (int x = 0; x < 4; ++x) zi[x] = Zs1[k * kTile + t.row(x)];
+                double2 q0 = *reinterpret_cast<const double2*>(&Zs2[k * kTile + 2 * t.tx]);
+                double2 q1 = *reinterpret_cast<const double2*>(&Zs2[k * kTile + 2 * t.tx + 32]);
+                zj[0] = q0.x; zj[1] = q0.y; zj[2] = q1.x; zj[3] = q1.y;
+                double s = 0.0;
+#pragma unroll
+                for (int x = 0; x < 4; ++x)
+#pragma unroll
+                    for (int y = 0; y < 4; ++y) {
+                        double df = zi[x] - zj[y];
+                        s += D[x][y] * (df * df);
+                    }
+                acc[2 + k] += s;
+            }
+            if (PTYPE == PGP_RQ) acc[2 + ndim] += s_e0;
+        }
+    } else {
+#pragma unroll 1
+        for (int x = 0; x < 4; ++x)
+#pragma unroll 1
+            for (int y = 0; y < 4; ++y) {
+                double w = wq[x][y];
+                if (w == 0.0) continue;
+                const double* z1 = Zs1 + t.row(x);
+                const double* z2 = Zs2 + t.col(y);
+                PartVal pv[kMaxParts];
+                double val[kMaxNodes], adj[kMaxNodes];
+                eval_parts<true>(*S, z1, z2, pv);
+                tree_forward(*S, pv, val);
+                tree_backward(*S, val, adj);
+                for (int p = 0; p < n_parts; ++p) {
+                    const DevPart& dp = S->parts[p];
+                    const PartVal& v = pv[p];
+                    double C = w * adj[S->leaf_node[p]];
+                    double* g = acc + 1 + dp.hoff;
+                    g[0] += C * v.g_sf;
+                    if (dp.type == PGP_PERIODIC) {
+                        g[1] += C * v.g_iso;
+                        g[2] += C * v.e0;
+                    } else {
+                        int nell = dp.iso ? 1 : ndim;
+                        if (dp.iso) {
+                            g[1] += C * v.g_iso;
+                        } else {
+                            double cw = C * v.ardw;
+                            for (int k = 0; k < ndim; ++k) {
+                                double df = z1[(p * ndim + k) * kTile] - z2[(p * ndim + k) * kTile];
+                                g[1 + k] += cw * (df * df);
+                            }
+                        }
+                        if (dp.type == PGP_RQ) g[1 + nell] += C * v.e0;
+                    }
+                }
+            }
+    }
+}
+
 // ---------------------------------------------------------------------------
 // fused gradient trace: persistent CTAs over the lower-triangular tiles of
 // Q = K~^-1 - alpha alpha^T, recomputing K and every dK_h from the inputs.
@@ -339,108 +450,7 @@ __global__ void __launch_bounds__(kThreads) trace_kernel(TraceArgs a, int64_t n_
             }
         }
 
-        if (PTYPE >= 0) {
-            double D[4][4];
-#pragma unroll
-            for (int x = 0; x < 4; ++x)
-#pragma unroll
-                for (int y = 0; y < 4; ++y) D[x][y] = 0.0;
-            for (int k = 0; k < ndim; ++k) {
-                double zi[4], zj[4];
-#pragma unroll
-                for (int x = 0; x < 4; ++x) zi[x] = Zs1[k * kTile + t.row(x)];
-                double2 q0 = *reinterpret_cast<const double2*>(&Zs2[k * kTile + 2 * t.tx]);
-                double2 q1 = *reinterpret_cast<const double2*>(&Zs2[k * kTile + 2 * t.tx + 32]);
-                zj[0] = q0.x; zj[1] = q0.y; zj[2] = q1.x; zj[3] = q1.y;
-#pragma unroll
-                for (int x = 0; x < 4; ++x)
-#pragma unroll
-                    for (int y = 0; y < 4; ++y) {
-                        double df = zi[x] - zj[y];
-                        D[x][y] += df * df;
-                    }
-            }
-            DevPart part = S->parts[0];
-            part.type = PTYPE;
-            double s_sf = 0.0, s_iso = 0.0, s_e0 = 0.0;
-#pragma unroll
-            for (int x = 0; x < 4; ++x)
-#pragma unroll
-                for (int y = 0; y < 4; ++y) {
-                    PartVal v;
-                    part_eval<true>(part, D[x][y], v);
-                    double w = wq[x][y];
-                    s_sf += w * v.g_sf;
-                    s_iso += w * v.g_iso;
-                    s_e0 += w * v.e0;
-                    D[x][y] = w * v.ardw;  // reuse as ARD weight
-                }
-            acc[1] += s_sf;
-            if (PTYPE == PGP_PERIODIC) {
-                acc[2] += s_iso;
-                acc[3] += s_e0;
-            } else if (part.iso) {
-                acc[2] += s_iso;
-                if (PTYPE == PGP_RQ) acc[3] += s_e0;
-            } else {
-                for (int k = 0; k < ndim; ++k) {
-                    double zi[4], zj[4];
-#pragma unroll
-                    for (int x = 0; x < 4; ++x) zi[x] = Zs1[k * kTile + t.row(x)];
-                    double2 q0 = *reinterpret_cast<const double2*>(&Zs2[k * kTile + 2 * t.tx]);
-                    double2 q1 = *reinterpret_cast<const double2*>(&Zs2[k * kTile + 2 * t.tx + 32]);
-                    zj[0] = q0.x; zj[1] = q0.y; zj[2] = q1.x; zj[3] = q1.y;
-                    double s = 0.0;
-#pragma unroll
-                    for (int x = 0; x < 4; ++x)
-#pragma unroll
-                        for (int y = 0; y < 4; ++y) {
-                            double df = zi[x] - zj[y];
-                            s += D[x][y] * (df * df);
-                        }
-                    acc[2 + k] += s;
-                }
-                if (PTYPE == PGP_RQ) acc[2 + ndim] += s_e0;
-            }
-        } else {
-#pragma unroll 1
-            for (int x = 0; x < 4; ++x)
-#pragma unroll 1
-                for (int y = 0; y < 4; ++y) {
-                    double w = wq[x][y];
-                    if (w == 0.0) continue;
-                    const double* z1 = Zs1 + t.row(x);
-                    const double* z2 = Zs2 + t.col(y);
-                    PartVal pv[kMaxParts];
-                    double val[kMaxNodes], adj[kMaxNodes];
-                    eval_parts<true>(*S, z1, z2, pv);
-                    tree_forward(*S, pv, val);
-                    tree_backward(*S, val, adj);
-                    for (int p = 0; p < n_parts; ++p) {
-                        const DevPart& dp = S->parts[p];
-                        const PartVal& v = pv[p];
-                        double C = w * adj[S->leaf_node[p]];
-                        double* g = acc + 1 + dp.hoff;
-                        g[0] += C * v.g_sf;
-                        if (dp.type == PGP_PERIODIC) {
-                            g[1] += C * v.g_iso;
-                            g[2] += C * v.e0;
-                        } else {
-                            int nell = dp.iso ? 1 : ndim;
-                            if (dp.iso) {
-                                g[1] += C * v.g_iso;
-                            } else {
-                                double cw = C * v.ardw;
-                                for (int k = 0; k < ndim; ++k) {
-                                    double df = z1[(p * ndim + k) * kTile] - z2[(p * ndim + k) * kTile];
-                                    g[1 + k] += cw * (df * df);
-                                }
-                            }
-                            if (dp.type == PGP_RQ) g[1 + nell] += C * v.e0;
-                        }
-                    }
-                }
-        }
+        trace_tile<PTYPE>(S, Zs1, Zs2, ndim, n_parts, t, wq, acc);
     }
 
     // CTA reduction in a fixed order -> one row of partials per CTA
@@ -458,6 +468,131 @@ __global__ void __launch_bounds__(kThreads) trace_kernel(TraceArgs a, int64_t n_
         for (int w = 0; w < kThreads / 32; ++w) v += red[w * (nh + 1) + h];
         a.partials[(int64_t)blockIdx.x * (nh + 1) + h] = v;
     }
+}
+
+// ---------------------------------------------------------------------------
+// rectangular trace: out[h] += scale * sum_ij W_ij dK_h(x1_i, x2_j) over a full
+// (n1, n2) block.  FITC's gradient is three of these (fitc.cu):
+//   mode 0: W = Wd (dense, ldw)                       -> sum(dKuu o Cuu)
+//   mode 1: W = 2 (al_i w_j - q_i Bt_ij + T2_ij)      -> sum(dKxu o Cxu),
+//           built on the fly so Cxu is never written.
+// partials[cta][h]; reduced by trace_rect_finish_kernel in a fixed order.
+// ---------------------------------------------------------------------------
+template <int PTYPE>
+__global__ void __launch_bounds__(kThreads) trace_rect_kernel(TraceRectArgs a, int64_t t2, int64_t n_tiles) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    DevSpecHdr* S = reinterpret_cast<DevSpecHdr*>(smem_raw);
+    double* Zs1 = reinterpret_cast<double*>(smem_raw + ((sizeof(DevSpecHdr) + 15) / 16) * 16);
+    double* Zs2 = Zs1 + a.n_parts * a.ndim * kTile;
+    double* red = Zs2 + a.n_parts * a.ndim * kTile;  // [8 warps][nhyper + 1]
+
+    const int ndim = a.ndim, n_parts = a.n_parts, nh = a.nhyper;
+    load_hdr(S, a.spec);
+    Tile t;
+
+    double acc[kMaxHyper + 1];
+    for (int h = 0; h <= nh; ++h) acc[h] = 0.0;
+
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t ti = tile / t2, tj = tile - ti * t2;
+        const int64_t i0 = ti * kTile, j0 = tj * kTile;
+        __syncthreads();
+        stage_tile(Zs1, a.Z1, a.n1 * ndim, a.n1, i0, ndim, n_parts);
+        stage_tile(Zs2, a.Z2, a.n2 * ndim, a.n2, j0, ndim, n_parts);
+        __syncthreads();
+
+        double wq[4][4];
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+            const int64_t gi = i0 + t.row(x);
+            const bool rok = gi < a.n1;
+            double ai = 0.0, qi = 0.0;
+            if (a.mode == 1 && rok) { ai = a.al[gi]; qi = a.q[gi]; }
+#pragma unroll
+            for (int y = 0; y < 4; ++y) {
+                const int64_t gj = j0 + t.col(y);
+                double w = 0.0;
+                if (rok && gj < a.n2) {
+                    if (a.mode == 0) w = a.Wd[gi * a.ldw + gj];
+                    else w = 2.0 * (ai * a.wv[gj] - qi * a.Bt[gi * a.ldw + gj] + a.T2[gi * a.ldw + gj]);
+                }
+                wq[x][y] = w;
+            }
+        }
+        trace_tile<PTYPE>(S, Zs1, Zs2, ndim, n_parts, t, wq, acc);
+    }
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    for (int h = 1; h <= nh; ++h) {
+        double v = acc[h];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) red[warp * (nh + 1) + h] = v;
+    }
+    __syncthreads();
+    for (int h = 1 + threadIdx.x; h <= nh; h += kThreads) {
+        double v = 0.0;
+        for (int w = 0; w < kThreads / 32; ++w) v += red[w * (nh + 1) + h];
+        a.partials[(int64_t)blockIdx.x * (nh + 1) + h] = v;
+    }
+}
+
+__global__ void trace_rect_finish_kernel(const double* partials, int64_t n_cta, int nh, double scale, double* out) {
+    __shared__ double red[256];
+    const int h = blockIdx.x + 1;  // 1..nh
+    double v = 0.0;
+    for (int64_t c = threadIdx.x; c < n_cta; c += blockDim.x) v += partials[c * (nh + 1) + h];
+    red[threadIdx.x] = v;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[h - 1] += scale * red[0];
+}
+
+int64_t trace_rect_cta_count(int64_t n1, int64_t n2) {
+    int64_t tiles = ceil_div(n1, kTile) * ceil_div(n2, kTile);
+    return std::min<int64_t>(tiles, 148 * kTraceCtasPerSm);
+}
+
+template <int PTYPE>
+static int launch_trace_rect_t(pgp_ctx* ctx, const TraceRectArgs& a, size_t smem, int64_t t2, int64_t n_tiles,
+                               int grid) {
+    auto kern = trace_rect_kernel<PTYPE>;
+    PGP_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    Launch L(ctx, PC_TRACE, (a.mode == 0 ? 8.0 : 16.0) * (double)a.n1 * (double)a.n2);
+    kern<<<grid, kThreads, smem, ctx->stream>>>(a, t2, n_tiles);
+    return check_launch(ctx, "trace_rect_kernel");
+}
+
+int launch_trace_rect(pgp_ctx* ctx, const TraceRectArgs& a) {
+    if (a.n1 <= 0 || a.n2 <= 0) return 0;
+    if (a.n_parts * a.ndim > 192)
+        return ctx->fail(PGP_E_ARG, "trace: n_parts * ndim > 192 exceeds the shared-memory tile");
+    int64_t t2 = ceil_div(a.n2, kTile);
+    int64_t n_tiles = ceil_div(a.n1, kTile) * t2;
+    int grid = (int)trace_rect_cta_count(a.n1, a.n2);
+    size_t smem = ((sizeof(DevSpecHdr) + 15) / 16) * 16 + 2ull * a.n_parts * a.ndim * kTile * sizeof(double) +
+                  8ull * (a.nhyper + 1) * sizeof(double);
+    int st = a.n_parts == 1 ? a.single_type : -1;
+    int rc;
+    switch (st) {
+        case PGP_SE: rc = launch_trace_rect_t<PGP_SE>(ctx, a, smem, t2, n_tiles, grid); break;
+        case PGP_MATERN1: rc = launch_trace_rect_t<PGP_MATERN1>(ctx, a, smem, t2, n_tiles, grid); break;
+        case PGP_MATERN3: rc = launch_trace_rect_t<PGP_MATERN3>(ctx, a, smem, t2, n_tiles, grid); break;
+        case PGP_MATERN5: rc = launch_trace_rect_t<PGP_MATERN5>(ctx, a, smem, t2, n_tiles, grid); break;
+        case PGP_PERIODIC: rc = launch_trace_rect_t<PGP_PERIODIC>(ctx, a, smem, t2, n_tiles, grid); break;
+        case PGP_RQ: rc = launch_trace_rect_t<PGP_RQ>(ctx, a, smem, t2, n_tiles, grid); break;
+        default: rc = launch_trace_rect_t<-1>(ctx, a, smem, t2, n_tiles, grid); break;
+    }
+    PGP_TRY(rc);
+    {
+        Launch L(ctx, PC_OTHER, 0.0);
+        trace_rect_finish_kernel<<<a.nhyper, 256, 0, ctx->stream>>>(a.partials, grid, a.nhyper, a.scale, a.out);
+    }
+    return check_launch(ctx, "trace_rect_finish_kernel");
 }
 
 // dlZ[0] = -sn2 sum Q_ii ; dlZ[1+h] = -1/2 S_h ; dlZ[nh+1] = sum alpha

@@ -17,6 +17,8 @@ struct GramArgs {
     const double* Z1 = nullptr;      // [batch][parts][n1][d]
     const double* Z2 = nullptr;      // [batch][parts][n2][d] (may alias Z1)
     int64_t n1 = 0, n2 = 0;
+    int64_t zs1 = 0, zs2 = 0;        // doubles between the leaves' copies (0: n1 * ndim / n2 * ndim);
+                                     // lets Z1 / Z2 be a row window of a larger scaled array
     int ndim = 0, n_parts = 0;
     double* out = nullptr;           // [batch] (n1, ldo)
     int64_t ldo = 0;
@@ -45,6 +47,30 @@ struct TraceArgs {
 int64_t trace_cta_count(int64_t n);
 // dlZ = [-sn2 tr(Q), -1/2 sum(Q o dK_h)..., sum(alpha)]   (exact.py:131-141)
 int launch_trace(pgp_ctx* ctx, const TraceArgs& a);
+
+// out[h] += scale * sum_ij W_ij dK_h(x1_i, x2_j), h < nhyper, over a full
+// rectangular block; W dense (mode 0) or FITC's Cxu built on the fly (mode 1).
+struct TraceRectArgs {
+    const DevSpec* spec = nullptr;
+    const double* Z1 = nullptr;      // [parts][n1][d]
+    const double* Z2 = nullptr;      // [parts][n2][d]
+    int64_t n1 = 0, n2 = 0;
+    int ndim = 0, n_parts = 0, nhyper = 0;
+    int mode = 0;
+    const double* Wd = nullptr;      // mode 0: (n1, ldw)
+    const double* Bt = nullptr;      // mode 1: (n1, ldw)
+    const double* T2 = nullptr;      // mode 1: (n1, ldw)
+    const double* al = nullptr;      // mode 1: (n1) alpha
+    const double* q = nullptr;       // mode 1: (n1)
+    const double* wv = nullptr;      // mode 1: (n2) w
+    int64_t ldw = 0;
+    double scale = 1.0;
+    double* partials = nullptr;      // [trace_rect_cta_count][nhyper + 1]
+    double* out = nullptr;           // device (nhyper), accumulated into
+    int single_type = -1;
+};
+int64_t trace_rect_cta_count(int64_t n1, int64_t n2);
+int launch_trace_rect(pgp_ctx* ctx, const TraceRectArgs& a);
 
 // out[h][i] = d k(x_i, x_i) / d hyper_h for h < nhyper (hmode=1) or k(x_i,x_i) (hmode=0)
 int launch_diag(pgp_ctx* ctx, const DevSpec* d_spec, int64_t n, int hmode, int nhyper, double* d_out);

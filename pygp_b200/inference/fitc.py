@@ -1,0 +1,114 @@
+"""
+FITC sparse pseudo-input GP on the device (pygp/inference/fitc.py:19-232).
+
+Same constructor, properties and error behaviour as the reference; `_update`,
+`loglikelihood` and `_marg_posterior(grad=False)` are single C-ABI calls
+(pgp_fitc_update / _loglike / _predict).  X, y, U and every (n, p) intermediate
+stay in HBM; only the hyper vector goes in and (lZ, dlZ) / (mu, s2) come out.
+"""
+
+import ctypes as C
+
+import numpy as np
+
+from .. import _lib
+from ..likelihoods import Gaussian
+from ._base import GP
+
+__all__ = ['FITC']
+
+
+class _DeviceFITC(object):
+    """Owner of a `pgp_fitc*`.  A deep copy (Parameterized.copy) starts without
+    device state; the copy's next `_update` uploads its own."""
+
+    def __init__(self, ctx, handle):
+        self.ctx, self.handle = ctx, handle
+
+    @classmethod
+    def create(cls, kernel, U, X, y):
+        ctx = _lib.context()
+        U, X, y = _lib.as_f64(U, 2), _lib.as_f64(X, 2), _lib.as_f64(y, 1)
+        h = C.c_void_p()
+        _lib.check(ctx, _lib.lib().pgp_fitc_create(ctx.handle, kernel._spec(), _lib.ptr(U), len(U),
+                                                   _lib.ptr(X), _lib.ptr(y), len(X), C.byref(h)))
+        return cls(ctx, h)
+
+    def __deepcopy__(self, memo):
+        return None
+
+    def __del__(self):
+        try:
+            if self.handle:
+                _lib.lib().pgp_fitc_destroy(self.handle)
+                self.handle = None
+        except Exception:       # interpreter shutdown
+            pass
+
+
+class FITC(GP):
+    """GP inference using sparse pseudo-inputs."""
+
+    def __init__(self, likelihood, kernel, mean, U):
+        # exact FITC inference only works with Gaussian likelihoods (fitc.py:24-26)
+        if not isinstance(likelihood, Gaussian):
+            raise ValueError('exact inference requires a Gaussian likelihood')
+        super(FITC, self).__init__(likelihood, kernel, mean)
+        self._U = np.array(U, ndmin=2, dtype=float, copy=True)
+        if self._U.shape[1] != self._kernel.ndim:
+            raise ValueError('pseudo-inputs have the wrong number of columns')
+        self._dev = None
+        self._ndev = 0
+
+    def reset(self):
+        self._dev = None
+        self._ndev = 0
+        super(FITC, self).reset()
+
+    @property
+    def pseudoinputs(self):
+        """The pseudo-input points."""
+        return self._U
+
+    @classmethod
+    def from_gp(cls, gp, U=None):
+        if U is None:
+            if hasattr(gp, 'pseudoinputs'):
+                U = gp.pseudoinputs.copy()
+            else:
+                raise ValueError('gp has no pseudoinputs and none are given')
+        newgp = cls(gp._likelihood.copy(), gp._kernel.copy(), gp._mean, U)
+        if gp.ndata > 0:
+            X, y = gp.data
+            newgp.add_data(X, y)
+        return newgp
+
+    def _update(self):
+        if self._dev is None or self._ndev != self.ndata:
+            # FITC has no incremental update in the reference either (every
+            # add_data re-runs _update on all the data, _base.py:133-141)
+            self._dev = None
+            self._dev = _DeviceFITC.create(self._kernel, self._U, self._X, self._y)
+            self._ndev = self.ndata
+        hyp = _lib.as_f64(self.get_hyper())
+        _lib.check(self._dev.ctx, _lib.lib().pgp_fitc_update(self._dev.handle, _lib.ptr(hyp)))
+
+    def loglikelihood(self, grad=False):
+        lZ = C.c_double()
+        dlZ = np.empty(self.nhyper) if grad else None
+        _lib.check(self._dev.ctx, _lib.lib().pgp_fitc_loglike(
+            self._dev.handle, int(bool(grad)), C.byref(lZ), None if dlZ is None else _lib.ptr(dlZ)))
+        return (lZ.value, dlZ) if grad else lZ.value
+
+    def _marg_posterior(self, X, grad=False):
+        if grad:
+            raise NotImplementedError('posterior input-gradients are outside the B200 hot path (next: N1)')
+        X = _lib.as_f64(X, 2)
+        if self._X is None:
+            return np.full(X.shape[0], self._mean), self._kernel.dget(X)
+        if X.shape[1] != self._kernel.ndim:
+            raise ValueError('test inputs have the wrong number of columns')
+        mu, s2 = np.empty(len(X)), np.empty(len(X))
+        _lib.check(self._dev.ctx, _lib.lib().pgp_fitc_predict(
+            self._dev.handle, _lib.ptr(X), len(X), _lib.ptr(mu), _lib.ptr(s2)))
+        return mu, s2

@@ -47,8 +47,8 @@ def test_library_is_sm100a_only(built):
 def test_gemm_uses_fp64_tensor_pipe(built):
     sass = subprocess.check_output(['cuobjdump', '-sass', built.LIB_PATH]).decode()
     funcs = sass.split('Function : ')
-    gemm = [f for f in funcs if 'gemm_nt_kernel' in f.split('\n', 1)[0]]
-    assert gemm, 'no gemm_nt_kernel in the library'
+    gemm = [f for f in funcs if 'gemm_kernel' in f.split('\n', 1)[0]]
+    assert len(gemm) >= 4, 'NT / NN / TN forms of gemm_kernel expected in the library'
     for f in gemm:
         assert f.count("DMMA.8x8x4") >= 64       # one k-tile of FP64 tensor-core work per warp
         assert 'LDGSTS' in f                     # cp.async staging

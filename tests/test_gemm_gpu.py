@@ -90,3 +90,77 @@ def test_potrf_reports_failing_minor():
     dF = torch.tensor(K, device='cuda')
     torch.cuda.synchronize()
     assert L.pgp_dev_potrf(ctx.handle, dF.data_ptr(), n, n, 0) == 101      # LAPACK-style info
+
+
+@pytest.mark.parametrize('tA,tB', [(0, 1), (1, 1), (1, 0)])
+@pytest.mark.parametrize('m,n,k,splitk', [(128, 128, 64, 1), (130, 67, 333, 1), (33, 33, 5000, 0), (65, 96, 9000, 7),
+                                          (1, 200, 64, 1), (257, 1, 1000, 3), (8, 8, 40, 1), (2048, 40, 40, 1)])
+def test_gemm_general_forms(tA, tB, m, n, k, splitk):
+    """TN / NN / TT-style operand layouts and the split contraction (FITC)."""
+    import torch
+    _lib, ctx, L = _ctx()
+    rng = np.random.RandomState(m + 3*n + 7*k + tA + 2*tB)
+    ev = lambda x: x + (x % 2)
+    A = rng.randn(m, k)
+    B = rng.randn(n, k)
+    As = np.zeros((k, ev(m) + 2)) if tA else np.zeros((m, ev(k) + 2))
+    Bs = np.zeros((k, ev(n))) if tB else np.zeros((n, ev(k)))
+    if tA: As[:, :m] = A.T
+    else: As[:, :k] = A
+    if tB: Bs[:, :n] = B.T
+    else: Bs[:, :k] = B
+    ldc = ev(n) + 4
+    C0 = rng.randn(m, ldc)
+    dA, dB, dC = (torch.tensor(x, device='cuda') for x in (As, Bs, C0))
+    torch.cuda.synchronize()
+    _lib.check(ctx, L.pgp_dev_gemm(ctx.handle, tA, tB, m, n, k, -0.5, dA.data_ptr(), As.shape[1], dB.data_ptr(),
+                                   Bs.shape[1], 1.0, dC.data_ptr(), ldc, 0, splitk))
+    ctx.sync()
+    C = dC.cpu().numpy()
+    ref = C0.copy()
+    ref[:, :n] = C0[:, :n] - 0.5*(A @ B.T)
+    nt.assert_allclose(C, ref, rtol=1e-12, atol=1e-12*np.sqrt(k))
+
+
+def test_gemm_tn_tri_splitk():
+    """A = I + V^T V on the lower tiles with the contraction split (fitc.cu)."""
+    import torch
+    _lib, ctx, L = _ctx()
+    rng = np.random.RandomState(5)
+    n, p = 20000, 200
+    V = rng.randn(n, p)/np.sqrt(n)
+    C0 = np.eye(p)
+    dV, dC = torch.tensor(V, device='cuda'), torch.tensor(C0, device='cuda')
+    torch.cuda.synchronize()
+    _lib.check(ctx, L.pgp_dev_gemm(ctx.handle, 1, 1, p, p, n, 1.0, dV.data_ptr(), p, dV.data_ptr(), p, 1.0,
+                                   dC.data_ptr(), p, 1, 0))
+    ctx.sync()
+    C = dC.cpu().numpy()
+    ref = np.eye(p) + V.T @ V
+    low = np.tril_indices(p)
+    nt.assert_allclose(C[low], ref[low], rtol=1e-12, atol=1e-13)
+    up = np.triu_indices(p, 1)
+    nt.assert_array_equal(C[up], 0.0)
+
+
+@pytest.mark.parametrize('n,rows', [(1, 3), (64, 1), (65, 130), (200, 257), (513, 1), (1000, 300)])
+@pytest.mark.parametrize('notrans', [0, 1])
+def test_trsm_forms(n, rows, notrans):
+    import torch
+    import scipy.linalg as sla
+    _lib, ctx, L = _ctx()
+    rng = np.random.RandomState(n + rows)
+    T = np.tril(rng.randn(n, n))/np.sqrt(n) + 2*np.eye(n)
+    B = rng.randn(rows, n)
+    ld = n + (n % 2) + 2
+    Tb = rng.randn(n, ld)            # garbage above the diagonal must be ignored
+    Tb[:, :n] = np.where(np.tril(np.ones((n, n))) > 0, T, Tb[:, :n])
+    Bb = np.zeros((rows, ld)); Bb[:, :n] = B
+    dT, dB = torch.tensor(Tb, device='cuda'), torch.tensor(Bb, device='cuda')
+    torch.cuda.synchronize()
+    _lib.check(ctx, L.pgp_dev_trsm(ctx.handle, dB.data_ptr(), rows, ld, dT.data_ptr(), n, ld, notrans))
+    ctx.sync()
+    X = dB.cpu().numpy()[:, :n]
+    # notrans: X T = B  ->  X = (T^-T B^T)^T ; else X T^T = B -> X = (T^-1 B^T)^T
+    ref = sla.solve_triangular(T, B.T, lower=True, trans=1 if notrans else 0).T
+    nt.assert_allclose(X, ref, rtol=1e-10, atol=1e-10)

@@ -106,3 +106,24 @@ def test_live_reference():
     pygp = ref_loader.load()
     make_golden.kernel_golden(pygp)
     make_golden.gp_golden(pygp)
+
+
+@pytest.mark.parametrize('name', ['fitc_se_2d', 'fitc_ard4_500'])
+def test_fitc_device_model(name):
+    """The regrouped FITC algebra the device runs (oracle/fitc_model.py: transposed
+    layout, gradient as three elementwise traces) equals fitc.py's own loop."""
+    from oracle import fitc_model as fm
+    spec, N, d, _ = GP_CASES[name]
+    X, y, Xs, U = gp_inputs(N, d, True)
+    k = make_kernel(spec)
+    gp = OFITC(GP_SN, k, GP_MEAN, U)
+    gp.add_data(X, y)
+    lZ, dlZ = gp.loglikelihood(True)
+    mu, s2 = gp.posterior(Xs)
+    st = fm.fitc_update(k, GP_SN**2, GP_MEAN, U, X, y)
+    lZ2, dlZ2 = fm.fitc_loglike(k, st, U, X, True)
+    mu2, s22 = fm.fitc_predict(k, st, U, Xs)
+    nt.assert_allclose(lZ2, lZ, rtol=1e-11)
+    nt.assert_allclose(dlZ2, dlZ, rtol=1e-9, atol=1e-9*np.abs(dlZ).max())
+    nt.assert_allclose(mu2, mu, rtol=1e-11, atol=1e-12)
+    nt.assert_allclose(s22, s2, rtol=1e-10, atol=1e-13)
