@@ -87,6 +87,13 @@ class MCMC(object):
         """Moment-matched mixture over the sampled models (mcmc.py:75-93)."""
         if grad:
             raise NotImplementedError('posterior input-gradients are outside the B200 hot path (next: N1)')
+        from .. import sharding
+        model = self._model
+        if (sharding.world()[1] > 1 and isinstance(model, ExactGP) and model.ndata > 0
+                and len(self._hypers) > 0):
+            # one process per GPU, identical chains (same rng) on every rank: the
+            # n sampled models are split across the ranks (SURVEY.md 8e)
+            return sharding.sharded_mixture_posterior(model, self._hypers, model._kernel.transform(X))
         mu_, s2_ = self._component_posteriors(X)
         mu = np.mean(mu_, axis=0)
         s2 = np.mean(s2_ + (mu_ - mu)**2, axis=0)

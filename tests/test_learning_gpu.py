@@ -141,3 +141,35 @@ def test_batched_loglike_vs_single(spec, n, d, B):
     for b in (0, B-1):
         og.set_hyper(H[b])
         nt.assert_allclose(lZ[b], og.loglikelihood(), rtol=LZ_RTOL)
+
+
+def test_sharding_single_rank_uses_device_path():
+    """pygp_b200.sharding without a process group (world size 1) runs the real
+    batched device calls; the N > 1 logic is covered on CPU (tests/test_sharding.py)
+    and on GPUs by tools/dist_check.py."""
+    import copy
+    import pygp_b200 as pygp
+    from pygp_b200 import sharding
+    X, y, Xs = synthetic_problem(150, 3, 17)
+    spec = ('se', 1.0, [0.5, 0.6, 0.7])
+    gp = pygp.inference.ExactGP(pygp.likelihoods.Gaussian(0.1), product_kernel(spec), 0.0)
+    gp.add_data(X, y)
+    H = gp.get_hyper() + np.random.RandomState(2).uniform(-0.3, 0.3, size=(5, gp.nhyper))
+    lZ = sharding.sharded_batched_loglike(gp, H)
+    ref = []
+    for h in H:
+        o = OExactGP(0.1, make_kernel(spec), 0.0)
+        o.add_data(X, y)
+        o.set_hyper(h)
+        ref.append((o.loglikelihood(),) + o.posterior(Xs))
+    nt.assert_allclose(lZ, [r[0] for r in ref], rtol=LZ_RTOL)
+    mu, s2 = sharding.sharded_mixture_posterior(gp, H, Xs)
+    mu_ = np.array([r[1] for r in ref])
+    s2_ = np.array([r[2] for r in ref])
+    mu0 = mu_.mean(0)
+    nt.assert_allclose(mu, mu0, rtol=1e-10, atol=1e-10)
+    nt.assert_allclose(s2, np.mean(s2_ + (mu_ - mu0)**2, axis=0), rtol=1e-9, atol=1e-10)
+    m2, v2 = sharding.sharded_posterior(gp, Xs)
+    m0, v0 = gp.posterior(Xs)
+    nt.assert_array_equal(m2, m0)
+    nt.assert_array_equal(v2, v0)
