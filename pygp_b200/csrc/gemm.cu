@@ -22,6 +22,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 
 namespace pgp {
 
@@ -122,70 +123,112 @@ __global__ void __launch_bounds__(WM * WN * 32, 1) gemm_kernel(GemmArgs a, int t
     const int wm = warp / WN, wn = warp % WN;
     const int g = lane >> 2, t = lane & 3;
 
-    // per-thread copy descriptors, fixed for the whole k loop.
+    // per-thread copy descriptors, fixed for the whole k loop.  Chunk q of a thread
+    // is chunk (tid + q THREADS) of the tile, so consecutive q differ by a constant
+    // row (normal: THREADS / CPR rows) or k (transposed: THREADS / CPT) offset and
+    // one base pointer + one shared-memory offset per operand is all that stays
+    // live in registers across the loop.
     //   normal operand:     chunk c -> row c / CPR, k offset 2 (c % CPR)
     //   transposed operand: chunk c -> k row c / CPT, m offset 2 (c % CPT)
-    const double* srcA[NCH];
-    const double* srcB[NCH];
-    int soffA[NCH], soffB[NCH], kofA[NCH], kofB[NCH];
-    int bytA[NCH], bytB[NCH];  // bytes valid along the non-contraction direction (transposed) or 16/0 (normal)
-#pragma unroll
-    for (int q = 0; q < NCH; ++q) {
-        int c = threadIdx.x + q * THREADS;
+    constexpr int RQ = THREADS / CPR;   // rows between consecutive chunks of a thread (normal)
+    constexpr int KQ = THREADS / CPT;   // k rows between them (transposed)
+    static_assert(THREADS % CPR == 0 && THREADS % CPT == 0, "chunk stride must be whole rows");
+    const double* srcA0;
+    const double* srcB0;
+    int soffA0, soffB0, kA0, kB0, okA, okB;   // ok*: normal -> bit q = row valid; transposed -> bytes valid along m/n
+    {
+        const int c = threadIdx.x;
         if (!TA) {
-            int row = c / CPR;
-            kofA[q] = (c % CPR) * 2;
-            soffA[q] = row * LDS + kofA[q];
-            bool ok = m0 + row < a.M;
-            bytA[q] = ok ? 16 : 0;
-            srcA[q] = A + (ok ? (m0 + row) * a.lda : 0) + ks + kofA[q];
+            const int row = c / CPR;
+            kA0 = (c % CPR) * 2;
+            soffA0 = row * LDS + kA0;
+            okA = 0;
+#pragma unroll
+            for (int q = 0; q < NCH; ++q) okA |= (m0 + row + q * RQ < a.M) << q;
+            srcA0 = A + (m0 + row) * a.lda + ks + kA0;
         } else {
-            int kr = c / CPT, mo = (c % CPT) * 2;
-            kofA[q] = kr;
-            soffA[q] = kr * LDT + mo;
-            int64_t rem = a.M - (m0 + mo);
-            bytA[q] = rem >= 2 ? 16 : (rem == 1 ? 8 : 0);
-            srcA[q] = A + (ks + kr) * a.lda + (bytA[q] ? m0 + mo : 0);
+            const int kr = c / CPT, mo = (c % CPT) * 2;
+            kA0 = kr;
+            soffA0 = kr * LDT + mo;
+            const int64_t rem = a.M - (m0 + mo);
+            okA = rem >= 2 ? 16 : (rem == 1 ? 8 : 0);
+            srcA0 = A + (ks + kr) * a.lda + (okA ? m0 + mo : 0);
         }
         if (!TB) {
-            int row = c / CPR;
-            kofB[q] = (c % CPR) * 2;
-            soffB[q] = row * LDS + kofB[q];
-            bool ok = n0 + row < a.N;
-            bytB[q] = ok ? 16 : 0;
-            srcB[q] = B + (ok ? (n0 + row) * a.ldb : 0) + ks + kofB[q];
+            const int row = c / CPR;
+            kB0 = (c % CPR) * 2;
+            soffB0 = row * LDS + kB0;
+            okB = 0;
+#pragma unroll
+            for (int q = 0; q < NCH; ++q) okB |= (n0 + row + q * RQ < a.N) << q;
+            srcB0 = B + (n0 + row) * a.ldb + ks + kB0;
         } else {
-            int kr = c / CPT, no = (c % CPT) * 2;
-            kofB[q] = kr;
-            soffB[q] = kr * LDT + no;
-            int64_t rem = a.N - (n0 + no);
-            bytB[q] = rem >= 2 ? 16 : (rem == 1 ? 8 : 0);
-            srcB[q] = B + (ks + kr) * a.ldb + (bytB[q] ? n0 + no : 0);
+            const int kr = c / CPT, no = (c % CPT) * 2;
+            kB0 = kr;
+            soffB0 = kr * LDT + no;
+            const int64_t rem = a.N - (n0 + no);
+            okB = rem >= 2 ? 16 : (rem == 1 ? 8 : 0);
+            srcB0 = B + (ks + kr) * a.ldb + (okB ? n0 + no : 0);
         }
     }
-    auto load_stage = [&](int slot, int ktile) {
+    // one 16-byte copy of k-tile `ktile` into ring slot `slot`: c < NCH -> chunk c
+    // of the A tile, else chunk c - NCH of the B tile (c is a compile-time constant
+    // at every call site)
+    auto load_chunk = [&](int slot, int ktile, int c) {
         double* As = smem + slot * STAGE_DOUBLES;
         double* Bs = As + TILE_DOUBLES;
         const int64_t koff = (int64_t)ktile * BK;
-        const int64_t kleft = ke - ks - koff;  // valid k from this tile's start
-#pragma unroll
-        for (int q = 0; q < NCH; ++q) {
+        const int kleft = (int)min((int64_t)BK, ke - ks - koff);  // valid k in this tile
+        if (c < NCH) {
+            const int q = c;
             if (!TA) {
-                int64_t rem = kleft - kofA[q];
-                int bytes = bytA[q] ? (rem >= 2 ? 16 : (rem == 1 ? 8 : 0)) : 0;
-                cp_async16(As + soffA[q], bytes ? srcA[q] + koff : A, bytes);
+                const int rem = kleft - kA0;
+                const int bytes = ((okA >> q) & 1) ? (rem >= 2 ? 16 : (rem == 1 ? 8 : 0)) : 0;
+                cp_async16(As + soffA0 + q * RQ * LDS, bytes ? srcA0 + (int64_t)q * RQ * a.lda + koff : A, bytes);
             } else {
-                int bytes = kofA[q] < kleft ? bytA[q] : 0;
-                cp_async16(As + soffA[q], bytes ? srcA[q] + koff * a.lda : A, bytes);
+                const int bytes = kA0 + q * KQ < kleft ? okA : 0;
+                cp_async16(As + soffA0 + q * KQ * LDT, bytes ? srcA0 + (koff + q * KQ) * a.lda : A, bytes);
             }
+        } else {
+            const int q = c - NCH;
             if (!TB) {
-                int64_t rem = kleft - kofB[q];
-                int bytes = bytB[q] ? (rem >= 2 ? 16 : (rem == 1 ? 8 : 0)) : 0;
-                cp_async16(Bs + soffB[q], bytes ? srcB[q] + koff : B, bytes);
+                const int rem = kleft - kB0;
+                const int bytes = ((okB >> q) & 1) ? (rem >= 2 ? 16 : (rem == 1 ? 8 : 0)) : 0;
+                cp_async16(Bs + soffB0 + q * RQ * LDS, bytes ? srcB0 + (int64_t)q * RQ * a.ldb + koff : B, bytes);
             } else {
-                int bytes = kofB[q] < kleft ? bytB[q] : 0;
-                cp_async16(Bs + soffB[q], bytes ? srcB[q] + koff * a.ldb : B, bytes);
+                const int bytes = kB0 + q * KQ < kleft ? okB : 0;
+                cp_async16(Bs + soffB0 + q * KQ * LDT, bytes ? srcB0 + (koff + q * KQ) * a.ldb : B, bytes);
             }
+        }
+    };
+    auto load_stage = [&](int slot, int ktile) {
+#pragma unroll
+        for (int c = 0; c < 2 * NCH; ++c) load_chunk(slot, ktile, c);
+    };
+
+    // fast path for interior tiles (every row / column of the CTA tile valid and the
+    // k-tile complete): no predicates, one pointer bump per k-tile, immediates per
+    // chunk.  The general path above costs ~40 scalar instructions per copy, which
+    // the 16 warps execute between their DMMAs.
+    const bool full_mn = (m0 + BM <= a.M) && (n0 + BN <= a.N);
+    const unsigned sdA0 = (unsigned)__cvta_generic_to_shared(smem) + (unsigned)soffA0 * 8u;
+    const unsigned sdB0 = (unsigned)__cvta_generic_to_shared(smem) + (unsigned)(TILE_DOUBLES + soffB0) * 8u;
+    const int64_t stepA = TA ? (int64_t)BK * a.lda : BK, stepB = TB ? (int64_t)BK * a.ldb : BK;
+    const int64_t qA = TA ? (int64_t)KQ * a.lda : (int64_t)RQ * a.lda;   // source stride between chunks
+    const int64_t qB = TB ? (int64_t)KQ * a.ldb : (int64_t)RQ * a.ldb;
+    constexpr unsigned QSA = (TA ? KQ * LDT : RQ * LDS) * 8u;            // destination stride (bytes)
+    constexpr unsigned QSB = (TB ? KQ * LDT : RQ * LDS) * 8u;
+    const double* gA = srcA0 + (int64_t)(STAGES - 1) * stepA;             // k-tile kt + STAGES - 1
+    const double* gB = srcB0 + (int64_t)(STAGES - 1) * stepB;
+    auto load_fast = [&](int slot, int c) {
+        const unsigned so = (unsigned)slot * (unsigned)(STAGE_DOUBLES * 8);
+        if (c < NCH) {
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sdA0 + so + (unsigned)c * QSA),
+                         "l"(gA + (int64_t)c * qA));
+        } else {
+            const int q = c - NCH;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sdB0 + so + (unsigned)q * QSB),
+                         "l"(gB + (int64_t)q * qB));
         }
     };
 
@@ -206,38 +249,69 @@ __global__ void __launch_bounds__(WM * WN * 32, 1) gemm_kernel(GemmArgs a, int t
     constexpr int A_RS = TA ? 1 : LDS, A_KS = TA ? LDT : 1;
     constexpr int B_RS = TB ? 1 : LDS, B_KS = TB ? LDT : 1;
 
-    for (int kt = 0; kt < KT; ++kt) {
-        cp_async_wait<STAGES - 2>();
-        __syncthreads();
-        {
-            int nk = kt + STAGES - 1;
-            if (nk < KT) load_stage(nk % STAGES, nk);
-            cp_async_commit();
-        }
-        const double* As = smem + (kt % STAGES) * STAGE_DOUBLES + (wm * (BM / WM) + g) * A_RS + t * A_KS;
-        const double* Bs = smem + (kt % STAGES) * STAGE_DOUBLES + TILE_DOUBLES + (wn * (BN / WN) + g) * B_RS + t * B_KS;
-        // fragments double-buffered in registers: the loads of step kk+1 are in
-        // flight while the DMMAs of step kk issue
-        double af[2][MI], bf[2][NJ];
+    // The copies of k-tile kt + STAGES - 1 are issued INTERLEAVED with the DMMAs of
+    // k-tile kt (CPS per 4-wide k-step) instead of in one burst after the barrier:
+    // a burst of 2 NCH LDGSTS per thread from all 16 warps backs up the LSU and
+    // starves the tensor pipe for several hundred cycles per k-tile
+    // (tools/dmma_probe.cu: the same loop without the copies runs at 35.9 TFLOP/s).
+    constexpr int KSTEPS = BK / 4;
+    constexpr int CPS = (2 * NCH + KSTEPS - 1) / KSTEPS;
+    auto main_loop = [&](auto fast_tag, int kt_begin, int kt_end) {
+        constexpr bool FAST = decltype(fast_tag)::value;
+        for (int kt = kt_begin; kt < kt_end; ++kt) {
+            cp_async_wait<STAGES - 2>();
+            __syncthreads();
+            const int nk = kt + STAGES - 1;
+            const bool do_load = FAST || nk < KT;
+            const int nslot = nk % STAGES;
+            const double* As = smem + (kt % STAGES) * STAGE_DOUBLES + (wm * (BM / WM) + g) * A_RS + t * A_KS;
+            const double* Bs = smem + (kt % STAGES) * STAGE_DOUBLES + TILE_DOUBLES + (wn * (BN / WN) + g) * B_RS + t * B_KS;
+            // fragments double-buffered in registers: the loads of step kk+1 are in
+            // flight while the DMMAs of step kk issue
+            double af[2][MI], bf[2][NJ];
 #pragma unroll
-        for (int i = 0; i < MI; ++i) af[0][i] = As[i * 8 * A_RS];
+            for (int i = 0; i < MI; ++i) af[0][i] = As[i * 8 * A_RS];
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) bf[0][j] = Bs[j * 8 * B_RS];
+            for (int j = 0; j < NJ; ++j) bf[0][j] = Bs[j * 8 * B_RS];
 #pragma unroll
-        for (int kk = 0; kk < BK / 4; ++kk) {
-            const int cur = kk & 1, nxt = cur ^ 1;
-            if (kk + 1 < BK / 4) {
+            for (int kk = 0; kk < KSTEPS; ++kk) {
+                const int cur = kk & 1, nxt = cur ^ 1;
+                if (kk + 1 < KSTEPS) {
 #pragma unroll
-                for (int i = 0; i < MI; ++i) af[nxt][i] = As[i * 8 * A_RS + (kk + 1) * 4 * A_KS];
+                    for (int i = 0; i < MI; ++i) af[nxt][i] = As[i * 8 * A_RS + (kk + 1) * 4 * A_KS];
 #pragma unroll
-                for (int j = 0; j < NJ; ++j) bf[nxt][j] = Bs[j * 8 * B_RS + (kk + 1) * 4 * B_KS];
+                    for (int j = 0; j < NJ; ++j) bf[nxt][j] = Bs[j * 8 * B_RS + (kk + 1) * 4 * B_KS];
+                }
+                if (FAST) {
+#pragma unroll
+                    for (int c = kk * CPS; c < (kk + 1) * CPS && c < 2 * NCH; ++c) load_fast(nslot, c);
+                } else if (do_load) {
+#pragma unroll
+                    for (int c = kk * CPS; c < (kk + 1) * CPS && c < 2 * NCH; ++c) load_chunk(nslot, nk, c);
+                }
+#pragma unroll
+                for (int i = 0; i < MI; ++i)
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[cur][i], bf[cur][j]);
             }
-#pragma unroll
-            for (int i = 0; i < MI; ++i)
-#pragma unroll
-                for (int j = 0; j < NJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[cur][i], bf[cur][j]);
+            cp_async_commit();
+            if (FAST) {
+                gA += stepA;
+                gB += stepB;
+            }
         }
+    };
+    // iterations whose prefetched k-tile (kt + STAGES - 1) is complete run the
+    // predicate-free loop when the CTA tile is interior; the rest (k tail, edge
+    // tiles) run the general one
+    int kt_fast = 0;
+    if (full_mn) {
+        int64_t nfull = (ke - ks) / BK - (STAGES - 1);
+        kt_fast = (int)(nfull > 0 ? nfull : 0);
+        if (kt_fast > KT) kt_fast = KT;
     }
+    main_loop(std::true_type{}, 0, kt_fast);
+    main_loop(std::false_type{}, kt_fast, KT);
     cp_async_wait<0>();
 
     // epilogue: lane owns C[row = 8i + g][col = 8j + 2t, +1] of its warp tile
