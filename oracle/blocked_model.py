@@ -12,7 +12,8 @@ Device formulation:
     L (K~ = L L^T, L = R^T of the reference) and row N is a = L^-1 r.
   * chol_rec(j0, n): factor columns [j0, j0+n) for ALL rows below.
   * trsm_rec(B, j0, n): B[:, j0:j0+n] <- B L^-T restricted to those columns.
-  * V = L^-T (upper) by a structured TRSM of the identity; K~^-1 = V V^T.
+  * V = L^-T (upper) bottom-up: diagonal blocks, then pairs of blocks of
+    doubling size (V12 = -(V11 L21^T) V22); K~^-1 = V V^T.
 """
 
 import numpy as np
@@ -83,21 +84,24 @@ def trsm_rec(B, L, j0, n):
     trsm_rec(B, L, j0+n1, n - n1)
 
 
-def inv_upper_rec(G, L, j0, n):
-    """G[j0:j0+n, j0:j0+n] <- L[j0.., j0..]^-T (upper), G pre-zeroed.
-    Structured TRSM of the identity: top-right block = -V11 L21^T V22."""
-    if n <= NB:
-        G[j0:j0+n, j0:j0+n] = np.eye(n)
-        trsm_base(G[j0:j0+n], L, j0, n)      # rows j0..j0+n of identity
-        return
-    n1 = split(n)
-    inv_upper_rec(G, L, j0, n1)
-    c0 = j0 + n1
-    # T = -V11 L21^T  (A = V11 upper triangular: k >= row)
-    G[j0:c0, c0:j0+n] = -(G[j0:c0, j0:c0] @ L[c0:j0+n, j0:c0].T)
-    # V12 = T L22^-T : general TRSM on rows j0..c0
-    trsm_rec(G[j0:c0], L, c0, n - n1)
-    inv_upper_rec(G, L, c0, n - n1)
+def inv_upper(G, L, n):
+    """G[0:n, 0:n] <- L^-T (upper), G pre-zeroed: bottom-up as chol.cu does.
+    Diagonal 64-blocks by substitution on the identity, then for block sizes
+    b = 64, 128, ... every pair of neighbouring blocks:
+        V12 = -(V11 L21^T) V22     (V11, V22 upper triangular)"""
+    for j0 in range(0, n, NB):
+        m = min(NB, n - j0)
+        G[j0:j0+m, j0:j0+m] = np.eye(m)
+        trsm_base(G[j0:j0+m], L, j0, m)
+    b = NB
+    while b < n:
+        for o in range(0, n, 2*b):
+            n2 = min(n, o + 2*b) - (o + b)
+            if n2 <= 0:
+                continue
+            T = -(G[o:o+b, o:o+b] @ L[o+b:o+b+n2, o:o+b].T)
+            G[o:o+b, o+b:o+b+n2] = T @ G[o+b:o+b+n2, o+b:o+b+n2]
+        b *= 2
 
 
 def device_model(kernel, sn, mean, X, y, want_grad=True, Xs=None):
@@ -116,7 +120,7 @@ def device_model(kernel, sn, mean, X, y, want_grad=True, Xs=None):
     out['lZ'] = lZ
     if want_grad:
         G = np.zeros((N, N))
-        inv_upper_rec(G, L, 0, N)
+        inv_upper(G, L, N)
         alpha = G @ a                         # alpha = L^-T a
         Pm = np.tril(G @ G.T)                 # K~^-1, lower (lauum: k >= max(i,j))
         Q = Pm - np.tril(np.outer(alpha, alpha))

@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <new>
 
 #include "chol.cuh"
@@ -94,6 +95,21 @@ extern "C" int64_t pgp_ctx_launch_count(pgp_ctx* ctx) { return ctx ? ctx->launch
 extern "C" int pgp_ctx_profile(pgp_ctx* ctx, int enable) {
     if (!ctx) return PGP_E_ARG;
     PGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    // development aid: PGP_PROF_DUMP=<file> appends one line per recorded launch
+    if (const char* path = getenv("PGP_PROF_DUMP")) {
+        if (!ctx->prof.empty()) {
+            if (FILE* f = fopen(path, "a")) {
+                for (auto& r : ctx->prof) {
+                    float ms = 0.f;
+                    cudaEventElapsedTime(&ms, r.e0, r.e1);
+                    fprintf(f, "%d %.6f %.6e %lld %lld %lld %d\n", r.cls, ms, r.work, (long long)r.m, (long long)r.n,
+                            (long long)r.k, r.flags);
+                }
+                fprintf(f, "# end\n");
+                fclose(f);
+            }
+        }
+    }
     prof_clear(ctx);
     ctx->profile = enable != 0;
     return 0;
@@ -522,7 +538,7 @@ extern "C" int pgp_exact_loglike(pgp_model* m, int want_grad, double* lZ, double
     F.p = m->d_F; F.ld = ld;
     G.p = m->d_G; G.ld = ld;
     H.p = m->d_H; H.ld = ld;
-    PGP_TRY(inv_upper(ctx, G, F, n));                                       // V = L^-T
+    PGP_TRY(inv_upper(ctx, G, F, n, H));                                     // V = L^-T
     PGP_TRY(launch_gemv_upper(ctx, m->d_G, ld, m->d_F + n * ld, n, m->d_alpha));  // alpha = V a
     PGP_TRY(syrk_upper_lower(ctx, H, G, n));                                // K~^-1 = V V^T
     TraceArgs t;

@@ -13,7 +13,8 @@
 //   Every flop above the 64-wide base case is a DMMA GEMM with K >= 64, and
 //   three quarters of them have K >= n/4.  Appending r = y - mean as row n
 //   turns the TRSV of exact.py:55 into one more row of the same solves.
-//   inv_upper: V = L^-T as a structured TRSM of the identity (n^3/3 flops),
+//   inv_upper: V = L^-T bottom-up over pairs of blocks, two batched GEMMs per
+//       level (n^3/3 flops, ~2 log2(n/64) launches),
 //   syrk_upper_lower: K~^-1 = V V^T on the lower tiles with k >= row (n^3/3).
 
 #include "chol.cuh"
@@ -127,14 +128,23 @@ __device__ __forceinline__ void cp16(double* sdst, const double* gsrc, int bytes
 template <bool IDENT, bool NOTRANS>
 __global__ void __launch_bounds__(kTrsmRows) trsm_base_kernel(double* B, int64_t ldb, int64_t bstrideB,
                                                               int64_t rows, const double* L, int64_t ldl,
-                                                              int64_t bstrideL, int64_t j0, int n) {
+                                                              int64_t bstrideL, int64_t j0, int n, int64_t ndiag) {
     extern __shared__ __align__(16) double sm[];
+    int b = blockIdx.y;
+    if (ndiag > 0) {
+        // every diagonal block of an ndiag x ndiag triangle in one launch:
+        // blockIdx.y = block index; B rows are rows j0.. of G (IDENT only)
+        j0 = (int64_t)blockIdx.y * kNB;
+        n = (int)min((int64_t)kNB, ndiag - j0);
+        rows = n;
+        B += j0 * ldb;
+        b = 0;
+    }
     double* Lraw = sm;                        // [64][64]  row-major copy of T, then in place:
     double* Lt = sm;                          // [64][64]  Lt[k][j] = T[j][k], j > k, else 0
     double* rinv = Lt + kNB * kNB;            // [64]
     double* Bt = rinv + kNB;                  // [128][66]
     const int tid = threadIdx.x;
-    const int b = blockIdx.y;
     const double* Lb = L + (int64_t)b * bstrideL + j0 * ldl + j0;
     double* Bb = B + (int64_t)b * bstrideB + j0;
     const int64_t r0 = (int64_t)blockIdx.x * kTrsmRows;
@@ -239,8 +249,19 @@ int launch_trsm_base(pgp_ctx* ctx, const Mat& B, int64_t rows, const Mat& L, int
     int64_t blocks = ceil_div(rows, kTrsmRows);
     Launch Lc(ctx, PC_TRSM, (double)rows * n * n * B.batch);
     kern<<<dim3((unsigned)blocks, B.batch), kTrsmRows, kTrsmSmem, ctx->stream>>>(
-        B.p, B.ld, B.bstride, rows, L.p, L.ld, L.bstride, j0, n);
+        B.p, B.ld, B.bstride, rows, L.p, L.ld, L.bstride, j0, n, 0);
     return check_launch(ctx, "trsm_base_kernel");
+}
+
+// G's diagonal 64-blocks <- (L's diagonal blocks)^-T, all in one launch
+int launch_inv_diag_blocks(pgp_ctx* ctx, const Mat& G, const Mat& L, int64_t n) {
+    auto kern = trsm_base_kernel<true, false>;
+    PGP_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTrsmSmem));
+    int64_t nblk = ceil_div(n, (int64_t)kNB);
+    if (nblk > 65535) return ctx->fail(PGP_E_ARG, "triangular inverse: more than 65535 diagonal blocks");
+    Launch Lc(ctx, PC_TRSM, (double)n * kNB * kNB / 3.0);
+    kern<<<dim3(1, (unsigned)nblk), kTrsmRows, kTrsmSmem, ctx->stream>>>(G.p, G.ld, 0, 0, L.p, L.ld, 0, 0, 0, n);
+    return check_launch(ctx, "trsm_base_kernel(diag)");
 }
 
 int gemm_update(pgp_ctx* ctx, const double* A, int64_t lda, int64_t sA, const double* Bm, int64_t ldb,
@@ -301,23 +322,6 @@ int trsm_nt_rec(pgp_ctx* ctx, const Mat& B, int64_t rows, const Mat& L, int64_t 
     return trsm_nt_rec(ctx, B, rows, L, j0, n1);
 }
 
-int inv_rec(pgp_ctx* ctx, const Mat& G, const Mat& L, int64_t j0, int64_t n) {
-    if (n <= kNB) {
-        Mat B = G;
-        B.p = G.p + j0 * G.ld;
-        return launch_trsm_base<true>(ctx, B, n, L, j0, (int)n);
-    }
-    int64_t n1 = split_point(n), n2 = n - n1, c0 = j0 + n1;
-    PGP_TRY(inv_rec(ctx, G, L, j0, n1));
-    // G[j0:c0, c0:c0+n2] = -V11 L21^T ; V11 upper triangular -> k >= row
-    PGP_TRY(gemm_update(ctx, G.p + j0 * G.ld + j0, G.ld, G.bstride, L.p + c0 * L.ld + j0, L.ld, L.bstride,
-                        G.p + j0 * G.ld + c0, G.ld, G.bstride, n1, n2, n1, -1.0, 0.0, 0, /*krow=*/1, G.batch));
-    Mat B = G;
-    B.p = G.p + j0 * G.ld;
-    PGP_TRY(trsm_rec(ctx, B, n1, L, c0, n2));
-    return inv_rec(ctx, G, L, c0, n2);
-}
-
 }  // namespace
 
 int potrf_lower(pgp_ctx* ctx, const Mat& F, int64_t n, int64_t extra, int* d_info) {
@@ -336,9 +340,53 @@ int trsm_right_l(pgp_ctx* ctx, const Mat& B, int64_t rows, const Mat& L, int64_t
     return trsm_nt_rec(ctx, B, rows, L, 0, n);
 }
 
-int inv_upper(pgp_ctx* ctx, const Mat& G, const Mat& L, int64_t n) {
+// V = L^-T bottom-up: the diagonal 64-blocks first (one launch), then for block
+// sizes b = 64, 128, ... every pair of neighbouring b-blocks at once:
+//     V = [V11 V12; 0 V22],   V12 = -(V11 L21^T) V22
+// as two BATCHED DMMA GEMMs per level (batch = number of pairs, uniform stride
+// 2b (ld + 1)); T = -V11 L21^T goes through the scratch matrix S at the position
+// of V12.  ~2 log2(n/64) launches instead of the ~3000 of a top-down recursion,
+// and no GEMM with fewer than b rows.  Triangular operands shorten the
+// contraction (krow: V11 upper, kcol: V22 upper): n^3/3 flops in total.
+int inv_upper(pgp_ctx* ctx, const Mat& G, const Mat& L, int64_t n, const Mat& S) {
     if (n <= 0) return 0;
-    return inv_rec(ctx, G, L, 0, n);
+    if (G.batch != 1) return ctx->fail(PGP_E_ARG, "inv_upper: not batched");
+    PGP_TRY(launch_inv_diag_blocks(ctx, G, L, n));
+    for (int64_t b = kNB; b < n; b *= 2) {
+        const int64_t full = n / (2 * b);                  // pairs with two complete blocks
+        const int64_t rest = n - full * 2 * b;             // trailing rows: a ragged pair if rest > b
+        for (int pass = 0; pass < 2; ++pass) {
+            int64_t batch, n2, off;
+            if (pass == 0) { batch = full; n2 = b; off = 0; }
+            else { batch = rest > b ? 1 : 0; n2 = rest - b; off = full * 2 * b; }
+            if (batch <= 0) continue;
+            const int64_t stride = 2 * b * (G.ld + 1);
+            const int64_t strideL = 2 * b * (L.ld + 1), strideS = 2 * b * (S.ld + 1);
+            for (int64_t b0 = 0; b0 < batch; b0 += 32768) {
+                const int bc = (int)std::min<int64_t>(32768, batch - b0);
+                const int64_t o = off + b0 * 2 * b;        // first row / column of this group of pairs
+                GemmArgs g1;                                // T = -V11 L21^T
+                g1.A = G.p + o * (G.ld + 1); g1.lda = G.ld; g1.strideA = stride;
+                g1.B = L.p + (o + b) * L.ld + o; g1.ldb = L.ld; g1.strideB = strideL;
+                g1.C = S.p + o * S.ld + o + b; g1.ldc = S.ld; g1.strideC = strideS;
+                g1.M = b; g1.N = n2; g1.K = b;
+                g1.alpha = -1.0; g1.beta = 0.0;
+                g1.krow = 1;
+                g1.batch = bc;
+                PGP_TRY(launch_gemm(ctx, g1));
+                GemmArgs g2;                                // V12 = T V22
+                g2.A = g1.C; g2.lda = S.ld; g2.strideA = strideS;
+                g2.B = G.p + (o + b) * (G.ld + 1); g2.ldb = G.ld; g2.strideB = stride; g2.transB = 1;
+                g2.C = G.p + o * G.ld + o + b; g2.ldc = G.ld; g2.strideC = stride;
+                g2.M = b; g2.N = n2; g2.K = n2;
+                g2.alpha = 1.0; g2.beta = 0.0;
+                g2.kcol = 1;
+                g2.batch = bc;
+                PGP_TRY(launch_gemm(ctx, g2));
+            }
+        }
+    }
+    return 0;
 }
 
 int syrk_upper_lower(pgp_ctx* ctx, const Mat& H, const Mat& G, int64_t n) {

@@ -30,8 +30,9 @@ int trsm_right_lt(pgp_ctx* ctx, const Mat& B, int64_t rows, const Mat& L, int64_
 // B[:, 0:n) <- B L^-1 (no transpose) for `rows` rows of B.
 int trsm_right_l(pgp_ctx* ctx, const Mat& B, int64_t rows, const Mat& L, int64_t n);
 
-// G (pre-zeroed outside its upper triangle) <- L^-T, upper triangular.
-int inv_upper(pgp_ctx* ctx, const Mat& G, const Mat& L, int64_t n);
+// G (pre-zeroed outside its upper triangle) <- L^-T, upper triangular.  S is
+// scratch of the same shape (its strict upper blocks are overwritten).
+int inv_upper(pgp_ctx* ctx, const Mat& G, const Mat& L, int64_t n, const Mat& S);
 
 // H lower triangle <- G G^T with G upper triangular (= K~^-1 when G = L^-T).
 int syrk_upper_lower(pgp_ctx* ctx, const Mat& H, const Mat& G, int64_t n);

@@ -19,6 +19,8 @@ struct ProfRec {
     cudaEvent_t e0, e1;
     int cls;
     double work;
+    int64_t m = 0, n = 0, k = 0;   // GEMM shape (PGP_PROF_DUMP)
+    int flags = 0;
 };
 
 struct Status {
@@ -96,6 +98,12 @@ struct Launch {
             cudaEventRecord(r.e0, ctx->stream);
             ctx->prof.push_back(r);
             idx = (int)ctx->prof.size() - 1;
+        }
+    }
+    void shape(int64_t m, int64_t n, int64_t k, int flags) {
+        if (idx >= 0) {
+            ProfRec& r = ctx->prof[idx];
+            r.m = m; r.n = n; r.k = k; r.flags = flags;
         }
     }
     ~Launch() {

@@ -109,6 +109,11 @@ __global__ void __launch_bounds__(WM * WN * 32, 1) gemm_kernel(GemmArgs a, int t
         ks = ks / BK * BK;
         if (ks > a.K) ks = a.K;
     }
+    if (a.kcol) {  // B is upper triangular in (k, col): the contraction may stop at the tile's last column
+        int64_t kend = n0 + BN + a.kcol_off;
+        if (kend < ke) ke = kend;
+        if (ke < ks) ke = ks;
+    }
     if (a.splitk > 1) {  // blockIdx.y = slice of the contraction; partial result to the workspace
         const int64_t per = (a.K + a.splitk - 1) / a.splitk;
         const int64_t kc = (per + BK - 1) / BK * BK;
@@ -382,8 +387,8 @@ int launch_gemm(pgp_ctx* ctx, const GemmArgs& a_in) {
     if ((a.lda & 1) || (a.ldb & 1) || (reinterpret_cast<uintptr_t>(a.A) & 15) ||
         (reinterpret_cast<uintptr_t>(a.B) & 15) || ((a.strideA | a.strideB) & 1))
         return ctx->fail(PGP_E_ARG, "gemm: A and B must be 16-byte aligned with even leading dimensions");
-    if ((a.transA || a.transB) && (a.krow || a.batch != 1))
-        return ctx->fail(PGP_E_ARG, "gemm: krow / batch are only supported for the NT form");
+    if (a.transA && a.krow) return ctx->fail(PGP_E_ARG, "gemm: krow needs A stored (M, K)");
+    if (a.kcol && !a.transB) return ctx->fail(PGP_E_ARG, "gemm: kcol needs B stored (K, N)");
     static const int variant = [] { const char* e = getenv("PGP_GEMM_VARIANT"); return e ? atoi(e) : 0; }();
     int64_t tm = ceil_div(a.M, BM), tn = ceil_div(a.N, BN);
     if (tm * tn > 0x7fffffffLL || a.batch > 65535) return ctx->fail(PGP_E_ARG, "gemm: grid too large");
@@ -391,7 +396,7 @@ int launch_gemm(pgp_ctx* ctx, const GemmArgs& a_in) {
     // (FITC: p x p results contracted over n >> p): partials go to a workspace
     // and are summed in a fixed order
     a.splitk = 1;
-    if (a_in.splitk != 1 && !a.krow && a.batch == 1) {
+    if (a_in.splitk != 1 && !a.krow && !a.kcol && a.batch == 1) {
         int64_t tiles = a.tri ? tm * (tm + 1) / 2 : tm * tn;
         int64_t want = a_in.splitk > 1 ? a_in.splitk : (2 * ctx->sm_count) / std::max<int64_t>(tiles, 1);
         int64_t max_by_k = a.K / 2048;  // keep >= 2048 contraction steps per slice
@@ -421,10 +426,19 @@ int launch_gemm(pgp_ctx* ctx, const GemmArgs& a_in) {
         double cols = (double)a.N, klen = (double)a.K;
         if (a.tri) cols = std::min(std::max(mid + (double)a.tri_off + 1.0, 0.0), (double)a.N);
         if (a.krow) klen = std::min(std::max((double)a.K - (mid + (double)a.krow_off), 0.0), (double)a.K);
+        if (a.kcol) {
+            // sum over the columns j of (j + 1 + off - kstart) clipped to [0, K - kstart]; exact for the
+            // regular triangular cases used here (kstart = K - klen)
+            double kstart = (double)a.K - klen, hi = (double)a.N + (double)a.kcol_off;   // k-end of the last column
+            double lo_end = 1.0 + (double)a.kcol_off;
+            double avg_end = 0.5 * (std::min(std::max(lo_end, kstart), (double)a.K) + std::min(std::max(hi, kstart), (double)a.K));
+            klen = std::max(avg_end - kstart, 0.0);
+        }
         flops += 2.0 * rows * cols * klen;
     }
     {
         Launch L(ctx, PC_GEMM, flops * a.batch);
+        L.shape(a.M, a.N, a.K, a.tri | (a.krow << 1) | (a.transA << 2) | (a.transB << 3) | (a.kcol << 4) | (a.batch << 8));
         int rc;
         if (a.transA && a.transB) rc = launch_variant<4, 4, Cfg<32, 3>, true, true>(ctx, a, tm, tn);
         else if (a.transA) rc = launch_variant<4, 4, Cfg<32, 3>, true, false>(ctx, a, tm, tn);

@@ -24,6 +24,11 @@ struct GemmArgs {
     // V V^T (k >= max(i, j) = i on the lower tiles).
     int krow = 0;
     int64_t krow_off = 0;
+    // kcol (with transB): B is upper-triangular in (k, col): B[k][j] == 0 for
+    // k > j + kcol_off, so the contraction of tile column j0 may stop at
+    // k = j0 + BN + kcol_off.  Used by the bottom-up triangular inverse.
+    int kcol = 0;
+    int64_t kcol_off = 0;
     int batch = 1;
     int64_t strideA = 0, strideB = 0, strideC = 0;
     // general forms (launch_gemm): transA -> A is stored (K x M) row-major,

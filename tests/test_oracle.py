@@ -127,3 +127,24 @@ def test_fitc_device_model(name):
     nt.assert_allclose(dlZ2, dlZ, rtol=1e-9, atol=1e-9*np.abs(dlZ).max())
     nt.assert_allclose(mu2, mu, rtol=1e-11, atol=1e-12)
     nt.assert_allclose(s22, s2, rtol=1e-10, atol=1e-13)
+
+
+@pytest.mark.parametrize('N', [63, 64, 129, 257, 700])
+def test_exact_device_model(N):
+    """The blocked formulation the device runs (oracle/blocked_model.py: recursive
+    right-looking Cholesky with r riding along, bottom-up triangular inverse,
+    lower-triangle trace) reaches the parity bars against the oracle."""
+    from oracle import blocked_model as bm
+    from oracle.pygp_oracle import synthetic_problem
+    X, y, Xs = synthetic_problem(N, 3, 9)
+    spec = ('matern', 1.0, [0.5, 0.6, 0.7], 5)
+    gp = OExactGP(0.1, make_kernel(spec), 0.2)
+    gp.add_data(X, y)
+    lZ, dlZ = gp.loglikelihood(True)
+    mu, s2 = gp.posterior(Xs)
+    out = bm.device_model(make_kernel(spec), 0.1, 0.2, X, y, True, Xs)
+    assert out['info'] == 0
+    nt.assert_allclose(out['lZ'], lZ, rtol=1e-11)
+    nt.assert_allclose(out['dlZ'], dlZ, rtol=1e-9, atol=1e-9*np.abs(dlZ).max())
+    nt.assert_allclose(out['mu'], mu, rtol=1e-10, atol=1e-11)
+    nt.assert_allclose(out['s2'], s2, rtol=1e-10, atol=1e-12)
