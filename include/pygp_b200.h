@@ -140,6 +140,15 @@ int pgp_exact_predict_dev(pgp_model* m, const double* d_Xs, int64_t ms,
 /* the factor as the reference holds it: upper R (n, n) C-order, a (n) */
 int pgp_exact_get_factor(pgp_model* m, double* R_out, double* a_out);
 
+/* Hooks for a factorisation computed outside pgp_exact_update (the 1-D
+ * block-column distributed Cholesky, pygp_b200/distchol.py): the device buffer
+ * that holds L (lower, row-major, ld doubles per row, n + 1 rows: row n = a),
+ * and "adopt": compile the hyper vector, rebuild the scaled inputs and lZ from
+ * the buffer's current content, and mark the model factored -- after which
+ * pgp_exact_loglike / _predict behave as after pgp_exact_update (exact.py:50-55). */
+int pgp_exact_factor_buffer(pgp_model* m, double** d_F, int64_t* ld);
+int pgp_exact_adopt_factor(pgp_model* m, const double* hyp);
+
 /* ---- batched small-N path: learning/sampling.py:146, meta/mcmc.py:75-93 ---- */
 /* B independent ExactGP._update + loglikelihood() sharing X, y.
  * hyps (B, nhyper_gp); lZ (B); info (B) per-problem potrf info (0 = ok). */
@@ -186,6 +195,9 @@ int pgp_dev_gemm(pgp_ctx* ctx, int transA, int transB, int64_t m, int64_t n, int
  * on the transposed layout) or B L^-1 (notrans = 1); L (n, ldl) lower. */
 int pgp_dev_trsm(pgp_ctx* ctx, double* d_B, int64_t rows, int64_t ldb,
                  const double* d_L, int64_t n, int64_t ldl, int notrans);
+/* strided device-to-device copy on the context stream (pitches and width in bytes) */
+int pgp_dev_copy2d(pgp_ctx* ctx, void* d_dst, int64_t dpitch, const void* d_src, int64_t spitch,
+                   int64_t width_bytes, int64_t rows);
 /* in-place lower Cholesky of a device matrix (n, n) row-major with `extra`
  * further rows below it that receive the same right-solves (row n = r -> a). */
 int pgp_dev_potrf(pgp_ctx* ctx, double* d_F, int64_t n, int64_t ld, int64_t extra);

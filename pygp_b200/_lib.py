@@ -74,6 +74,8 @@ SIGNATURES = {
     'pgp_exact_predict': (C.c_int, [_vp, _dp, _i64, _dp, _dp]),
     'pgp_exact_predict_dev': (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     'pgp_exact_get_factor': (C.c_int, [_vp, _dp, _dp]),
+    'pgp_exact_factor_buffer': (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_i64)]),
+    'pgp_exact_adopt_factor': (C.c_int, [_vp, _dp]),
     'pgp_batched_loglike': (C.c_int, [_vp, _sp, _dp, _dp, _i64, _dp, _i64, _dp, _ip]),
     'pgp_batched_predict': (C.c_int, [_vp, _sp, _dp, _dp, _i64, _dp, _i64, _dp, _i64, _dp, _dp, _ip]),
     'pgp_fitc_create': (C.c_int, [_vp, _sp, _dp, _i64, _dp, _dp, _i64, C.POINTER(_vp)]),
@@ -86,6 +88,7 @@ SIGNATURES = {
     'pgp_dev_gemm': (C.c_int, [_vp, C.c_int, C.c_int, _i64, _i64, _i64, C.c_double, _vp, _i64, _vp, _i64,
                                C.c_double, _vp, _i64, C.c_int, C.c_int]),
     'pgp_dev_trsm': (C.c_int, [_vp, _vp, _i64, _i64, _vp, _i64, _i64, C.c_int]),
+    'pgp_dev_copy2d': (C.c_int, [_vp, _vp, _i64, _vp, _i64, _i64, _i64]),
     'pgp_dev_potrf': (C.c_int, [_vp, _vp, _i64, _i64, _i64]),
 }
 

@@ -195,6 +195,7 @@ int gram_device(pgp_ctx* ctx, const pgp_kernel_spec* spec, const double* hyp, co
     g.out = d_out;
     g.ldo = ldo;
     g.hidx = hidx;
+    g.symmetric = d_X2 == nullptr;   // Kernel.get(X) / grad(X): exactly symmetric, as with cdist
     g.single_type = single_type(spec);
     PGP_TRY(launch_gram(ctx, g));
     PGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -517,6 +518,38 @@ extern "C" int pgp_exact_update(pgp_model* m, const double* hyp) {
     return 0;
 }
 
+// ---- distributed factorisation hooks (pygp_b200/distchol.py) ------------------
+extern "C" int pgp_exact_factor_buffer(pgp_model* m, double** d_F, int64_t* ld) {
+    if (!m || !d_F || !ld) return PGP_E_ARG;
+    *d_F = m->d_F;
+    *ld = m->ld;
+    return 0;
+}
+
+extern "C" int pgp_exact_adopt_factor(pgp_model* m, const double* hyp) {
+    if (!m) return PGP_E_ARG;
+    pgp_ctx* ctx = m->ctx;
+    if (!hyp) return ctx->fail(PGP_E_ARG, "null hyper vector");
+    PGP_TRY(set_device(ctx));
+    const int nk = m->spec.nhyper;
+    const double sn2 = std::exp(hyp[0] * 2);
+    PGP_TRY(compile_spec(&m->spec, hyp + 1, sn2, hyp[1 + nk], &m->hspec, &ctx->err));
+    PGP_CUDA(ctx, cudaMemcpyAsync(m->d_spec, &m->hspec, sizeof(DevSpec), cudaMemcpyHostToDevice, ctx->stream));
+    PGP_TRY(launch_scale(ctx, m->d_spec, m->d_X, m->n, m->ndim, m->spec.n_parts, m->d_Z, 1));
+    Mat F;
+    F.p = m->d_F;
+    F.ld = m->ld;
+    PGP_TRY(launch_loglik(ctx, F, m->n, m->d_res));
+    double* hp = ctx->h_pin;
+    PGP_CUDA(ctx, cudaMemcpyAsync(hp, m->d_res, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    PGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    m->lZ = hp[0];
+    m->info = 0;
+    m->factored = std::isfinite(m->lZ);
+    if (!m->factored) return ctx->fail(PGP_E_STATE, "adopted factor is not finite");
+    return 0;
+}
+
 extern "C" int pgp_exact_loglike(pgp_model* m, int want_grad, double* lZ, double* dlZ) {
     if (!m) return PGP_E_ARG;
     pgp_ctx* ctx = m->ctx;
@@ -828,6 +861,16 @@ extern "C" int pgp_dev_trsm(pgp_ctx* ctx, double* d_B, int64_t rows, int64_t ldb
     B.p = d_B; B.ld = ldb;
     L.p = const_cast<double*>(d_L); L.ld = ldl;
     return notrans ? trsm_right_l(ctx, B, rows, L, n) : trsm_right_lt(ctx, B, rows, L, n);
+}
+
+extern "C" int pgp_dev_copy2d(pgp_ctx* ctx, void* d_dst, int64_t dpitch, const void* d_src, int64_t spitch,
+                              int64_t width_bytes, int64_t rows) {
+    if (!ctx) return PGP_E_ARG;
+    if (rows <= 0 || width_bytes <= 0) return 0;
+    PGP_TRY(set_device(ctx));
+    PGP_CUDA(ctx, cudaMemcpy2DAsync(d_dst, (size_t)dpitch, d_src, (size_t)spitch, (size_t)width_bytes, (size_t)rows,
+                                    cudaMemcpyDeviceToDevice, ctx->stream));
+    return 0;
 }
 
 extern "C" int pgp_dev_potrf(pgp_ctx* ctx, double* d_F, int64_t n, int64_t ld, int64_t extra) {

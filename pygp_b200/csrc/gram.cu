@@ -145,9 +145,10 @@ __global__ void __launch_bounds__(kThreads) gram_kernel(GramArgs a) {
     double* Zs1 = reinterpret_cast<double*>(smem_raw + ((sizeof(DevSpecHdr) + 15) / 16) * 16);
     double* Zs2 = Zs1 + a.n_parts * a.ndim * kTile;
 
-    const int b = a.lower_only ? blockIdx.y : blockIdx.z;
+    const bool tri_grid = a.lower_only || a.symmetric;
+    const int b = tri_grid ? blockIdx.y : blockIdx.z;
     int ti, tj;
-    if (a.lower_only) tri_decode(blockIdx.x, &ti, &tj);
+    if (tri_grid) tri_decode(blockIdx.x, &ti, &tj);
     else { ti = blockIdx.y; tj = blockIdx.x; }
     const int64_t i0 = (int64_t)ti * kTile, j0 = (int64_t)tj * kTile;
     const int ndim = a.ndim, n_parts = a.n_parts;
@@ -243,6 +244,38 @@ __global__ void __launch_bounds__(kThreads) gram_kernel(GramArgs a) {
             }
         }
     }
+
+    // symmetric full-square build (X2 = X1): the tile above the diagonal is the
+    // transpose of this one -- k and every dk/dhyper are symmetric in (x1, x2) --
+    // so it is written from a shared-memory transpose instead of being
+    // recomputed: half the FP64 work per byte written.
+    if (a.symmetric && ti != tj) {
+        double* T = Zs2 + n_parts * ndim * kTile;   // [64][kTile + 1]
+        constexpr int TP = kTile + 1;
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+            for (int y = 0; y < 4; ++y) T[t.row(x) * TP + t.col(y)] = res[x][y];
+        __syncthreads();
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+            const int64_t gi = j0 + t.row(x);          // row of the mirrored tile
+            if (gi >= a.n2) continue;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int c = t.col(2 * h);
+                const int64_t gj = i0 + c;
+                const double v0 = T[c * TP + t.row(x)], v1 = T[(c + 1) * TP + t.row(x)];
+                double* dst = out + gi * a.ldo + gj;
+                if (vec_ok && gj + 1 < a.n1) {
+                    *reinterpret_cast<double2*>(dst) = make_double2(v0, v1);
+                } else {
+                    if (gj < a.n1) dst[0] = v0;
+                    if (gj + 1 < a.n1) dst[1] = v1;
+                }
+            }
+        }
+    }
 }
 
 template <int PTYPE, bool GRAD1>
@@ -252,9 +285,9 @@ static int launch_gram_t(pgp_ctx* ctx, const GramArgs& a, size_t smem) {
     int64_t t1 = ceil_div(a.n1, kTile), t2 = ceil_div(a.n2, kTile);
     dim3 grid;
     double entries;
-    if (a.lower_only) {
+    if (a.lower_only || a.symmetric) {
         grid = dim3((unsigned)(t1 * (t1 + 1) / 2), a.batch, 1);
-        entries = 0.5 * (double)a.n1 * (double)a.n1;
+        entries = (a.symmetric ? 1.0 : 0.5) * (double)a.n1 * (double)a.n1;
     } else {
         if (t1 > 65535) return ctx->fail(PGP_E_ARG, "gram: more than 65535 row tiles");
         grid = dim3((unsigned)t2, (unsigned)t1, a.batch);
@@ -267,10 +300,12 @@ static int launch_gram_t(pgp_ctx* ctx, const GramArgs& a, size_t smem) {
 
 int launch_gram(pgp_ctx* ctx, const GramArgs& a) {
     if (a.n1 == 0 || a.n2 == 0) return 0;
-    if (a.lower_only && a.n1 != a.n2) return ctx->fail(PGP_E_ARG, "gram: lower_only needs a square matrix");
+    if ((a.lower_only || a.symmetric) && a.n1 != a.n2)
+        return ctx->fail(PGP_E_ARG, "gram: lower_only / symmetric need a square matrix");
     if (a.n_parts * a.ndim > 192)
         return ctx->fail(PGP_E_ARG, "gram: n_parts * ndim > 192 exceeds the shared-memory tile");
     size_t smem = ((sizeof(DevSpecHdr) + 15) / 16) * 16 + 2ull * a.n_parts * a.ndim * kTile * sizeof(double);
+    if (a.symmetric) smem += (size_t)kTile * (kTile + 1) * sizeof(double);
     const bool g = a.hidx >= 0;
     int st = a.n_parts == 1 ? a.single_type : -1;
 #define PGP_GRAM_CASE(T)                                             \

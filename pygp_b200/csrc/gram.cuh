@@ -24,6 +24,7 @@ struct GramArgs {
     int64_t ldo = 0;
     int64_t out_bstride = 0;
     int lower_only = 0;              // skip tiles strictly above the diagonal
+    int symmetric = 0;               // Z2 == Z1, full square: compute lower tiles, mirror them
     int add_noise = 0;               // out[i][i] += spec.sn2
     int hidx = -1;                   // >= 0: write d/d hyper[hidx] instead of K
     int batch = 1;

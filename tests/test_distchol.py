@@ -1,0 +1,141 @@
+"""The block-column distributed Cholesky schedule (pygp_b200/distchol.py) on
+CPU: world size 1 in-process and world size 2 over gloo, with a numpy stand-in
+for the per-rank device arithmetic (the schedule, ownership, lookahead and
+broadcast plumbing are under test; DeviceBackend itself is covered by
+tests/test_exact_gpu.py::test_distributed_update_single_rank and tools/dist_check.py)."""
+
+import os
+import socket
+
+import numpy as np
+import numpy.testing as nt
+import pytest
+import scipy.linalg as sla
+
+
+class NumpyBackend(object):
+    """TEST stand-in for distchol.DeviceBackend: same interface, numpy arithmetic."""
+
+    def __init__(self, K, r, nb):
+        self.K, self.r, self.n, self.nb = K, r, len(K), nb
+        self.F = np.full((self.n + 1, self.n), np.nan)
+        self._recv = {}
+
+    def build_panel(self, j0, w):
+        p = np.zeros((self.n - j0 + 1, self.nb))
+        p[:-1, :w] = self.K[j0:, j0:j0 + w]
+        p[-1, :w] = self.r[j0:j0 + w]
+        return p
+
+    def recv_buffer(self, rows, w, slot):
+        if slot not in self._recv:
+            self._recv[slot] = np.zeros((self.n + 1, self.nb))
+        return self._recv[slot][:rows]
+
+    def factor_panel(self, panel, w):
+        try:
+            L = np.linalg.cholesky(panel[:w, :w])
+        except np.linalg.LinAlgError:
+            return 1
+        panel[:w, :w] = L
+        panel[w:, :w] = sla.solve_triangular(L, panel[w:, :w].T, lower=True).T
+        return 0
+
+    def update_panel(self, pj, pk, off, wj):
+        pj[:, :wj] -= pk[off:] @ pk[off:off + wj].T
+
+    def store_panel(self, pk, j0, w):
+        self.F[j0:, j0:j0 + w] = pk[:, :w]
+
+    def sync(self):
+        pass
+
+
+def _problem(n, seed=0):
+    rng = np.random.RandomState(seed)
+    A = rng.randn(n, n + 8)
+    return A @ A.T/n + np.eye(n), rng.randn(n)
+
+
+@pytest.mark.parametrize('n,nb', [(64, 64), (100, 64), (257, 64), (400, 128)])
+def test_schedule_single_rank(n, nb):
+    from pygp_b200.distchol import distributed_factor, block_columns
+    assert sum(w for _, w in block_columns(n, nb)) == n
+    K, r = _problem(n)
+    be = NumpyBackend(K, r, nb)
+    assert distributed_factor(be, n, nb, 0, 1, None) == 0
+    L = np.linalg.cholesky(K)
+    low = np.tril_indices(n)
+    nt.assert_allclose(be.F[:n][low], L[low], rtol=1e-11, atol=1e-12)
+    nt.assert_allclose(be.F[n], sla.solve_triangular(L, r, lower=True), rtol=1e-10, atol=1e-12)
+
+
+def test_not_positive_definite_info():
+    from pygp_b200.distchol import distributed_factor
+    K, r = _problem(200)
+    K[150, 150] = -1.0
+    be = NumpyBackend(K, r, 64)
+    assert distributed_factor(be, 200, 64, 0, 1, None) > 128      # reported inside the third block column
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, size, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=size)
+    try:
+        from pygp_b200.distchol import distributed_factor
+
+        class H(object):
+            def __init__(self, work, t, buf):
+                self.work, self.t, self.buf = work, t, buf
+
+            def wait(self):
+                self.work.wait()
+                self.buf[...] = self.t.numpy()
+
+        def bcast(buf, src):
+            t = torch.from_numpy(np.ascontiguousarray(buf))
+            return H(dist.broadcast(t, src=src, async_op=True), t, buf)
+
+        for n, nb in [(300, 64), (257, 128), (64, 64)]:
+            K, r = _problem(n, seed=n)
+            be = NumpyBackend(K, r, nb)
+            info = distributed_factor(be, n, nb, rank, size, bcast)
+            assert info == 0
+            L = np.linalg.cholesky(K)
+            low = np.tril_indices(n)
+            # every rank ends with the complete factor (the broadcasts are the all-gather)
+            nt.assert_allclose(be.F[:n][low], L[low], rtol=1e-11, atol=1e-12)
+            nt.assert_allclose(be.F[n], sla.solve_triangular(L, r, lower=True), rtol=1e-10, atol=1e-12)
+        q.put((rank, 'ok'))
+    except Exception:      # pragma: no cover
+        import traceback
+        q.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_schedule_gloo_world_size_2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=150) for _ in procs]
+    for p in procs:
+        p.join(timeout=30)
+    for rank, msg in res:
+        assert msg == 'ok', 'rank %d: %s' % (rank, msg)

@@ -165,3 +165,34 @@ def test_loglikelihood_fd_basic():
     nt.assert_allclose(g1, g2, rtol=1e-5, atol=1e-5)
     for kern in ('se', 'matern1', 'matern3', 'matern5'):
         _ = pygp.BasicGP.from_gp(pygp.BasicGP(1, 1, 1, 0, 2, kern))
+
+
+@pytest.mark.parametrize('N,nb', [(700, 128), (513, 64), (256, 256)])
+def test_distributed_update_single_rank(N, nb):
+    """pygp_b200.distchol.DeviceBackend (panel Gram, panel potrf with extra rows,
+    DMMA panel updates, strided store into the model's factor, adopt) on one
+    GPU without a process group == pgp_exact_update.  The N > 1 schedule is
+    covered on CPU (tests/test_distchol.py) and on GPUs by tools/dist_check.py."""
+    import pygp_b200 as pygp
+    from pygp_b200.distchol import distributed_update
+    X, y, Xs = synthetic_problem(N, 4, 50)
+    spec = ('matern', 1.0, [0.7, 0.8, 0.9, 1.0], 5)
+    mk = lambda: pygp.inference.ExactGP(pygp.likelihoods.Gaussian(0.1), product_kernel(spec), 0.1)
+    ref = mk()
+    ref.add_data(X, y)
+    gp = mk()
+    gp.add_data(X, y)
+    h2 = gp.get_hyper() + 0.05
+    ref.set_hyper(h2)
+    # set the new hypers on the host objects only, then factor through the distributed path
+    a, b = gp._likelihood.nhyper, gp._kernel.nhyper
+    gp._likelihood.set_hyper(h2[:a]); gp._kernel.set_hyper(h2[a:a + b]); gp._mean = float(h2[-1])
+    distributed_update(gp, nb=nb)
+    lZ, dlZ = gp.loglikelihood(True)
+    lZ0, dlZ0 = ref.loglikelihood(True)
+    nt.assert_allclose(lZ, lZ0, rtol=1e-11)
+    assert_grad_close(dlZ, dlZ0, rtol=1e-9)
+    mu, s2 = gp.posterior(Xs)
+    mu0, s20 = ref.posterior(Xs)
+    nt.assert_allclose(mu, mu0, rtol=1e-10, atol=1e-11)
+    nt.assert_allclose(s2, s20, rtol=1e-9, atol=1e-12)

@@ -1,0 +1,105 @@
+"""Multi-GPU check + timing (run under torchrun on the GPU box, one rank per GPU):
+  torchrun --nnodes=1 --nproc-per-node G --master-addr 127.0.0.1 --master-port 29511 tools/dist_check.py [N] [nb]
+* block-column distributed Cholesky (pygp_b200.distchol) == single-GPU update, and its speed-up
+* sharded predict (test points) and sharded batched loglike / mixture posterior == single rank.
+Rank 0 prints JSON lines."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
+    nb = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
+    rank, world, local = int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), int(os.environ['LOCAL_RANK'])
+    torch.cuda.set_device(local)
+    os.environ['PYGP_B200_DEVICE'] = str(local)
+    dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    import pygp_b200 as pygp
+    from pygp_b200 import sharding, distchol, _lib
+    ctx = _lib.context(local)
+
+    def say(**kw):
+        if rank == 0:
+            print(json.dumps(kw), flush=True)
+
+    d = 8
+    rng = np.random.RandomState(0)
+    X = rng.rand(n, d)
+    y = np.sin(3*X.sum(1)) + 0.1*rng.randn(n)
+    Xs = np.random.RandomState(1).rand(4096, d)
+    mk = lambda: pygp.inference.ExactGP(pygp.likelihoods.Gaussian(0.1), pygp.kernels.SE(1.0, [0.5*np.sqrt(d)]*d), 0.0)
+    gp = mk()
+    gp.add_data(X, y)                      # single-GPU factorisation on every rank (reference)
+    ctx.sync()
+    t0 = time.perf_counter()
+    gp.set_hyper(gp.get_hyper())
+    ctx.sync()
+    t_single = time.perf_counter() - t0
+    lZ0 = gp.loglikelihood()
+    mu0, s20 = gp.posterior(Xs[:256])
+
+    g2 = mk()
+    g2.add_data(X, y)
+    for rep in range(2):
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        distchol.distributed_update(g2, nb=nb)
+        ctx.sync()
+        dist.barrier()
+        t_dist = time.perf_counter() - t0
+    lZ1 = g2.loglikelihood()
+    mu1, s21 = g2.posterior(Xs[:256])
+    say(check='distributed_cholesky', n=n, nb=nb, world=world, lZ_single=lZ0, lZ_dist=lZ1,
+        rel_err=abs(lZ1 - lZ0)/abs(lZ0), mu_err=float(np.abs(mu1 - mu0).max()), s2_err=float(np.abs(s21 - s20).max()),
+        t_single_s=t_single, t_dist_s=t_dist, speedup=t_single/t_dist,
+        tflops_single=n**3/3/t_single/1e12, tflops_dist_aggregate=n**3/3/t_dist/1e12)
+    assert abs(lZ1 - lZ0) <= 1e-10*abs(lZ0), (lZ0, lZ1)
+
+    # sharded predict
+    dist.barrier()
+    t0 = time.perf_counter()
+    mu_s, s2_s = sharding.sharded_posterior(gp, Xs)
+    dist.barrier()
+    t_sh = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    mu_f, s2_f = gp.posterior(Xs)
+    t_one = time.perf_counter() - t0
+    say(check='sharded_predict', points=len(Xs), max_err=float(max(np.abs(mu_s - mu_f).max(), np.abs(s2_s - s2_f).max())),
+        t_sharded_s=t_sh, t_single_rank_s=t_one)
+    assert np.array_equal(mu_s, mu_f) and np.array_equal(s2_s, s2_f)
+
+    # sharded batched hypers (C4 shape, scaled): N=2048, 64 samples
+    Xb, yb = X[:2048], y[:2048]
+    gb = mk()
+    gb.add_data(Xb, yb)
+    H = gb.get_hyper() + np.random.RandomState(2).uniform(-0.5, 0.5, size=(64*world, gb.nhyper))
+    dist.barrier()
+    t0 = time.perf_counter()
+    lz_sh = sharding.sharded_batched_loglike(gb, H)
+    dist.barrier()
+    t_sh = time.perf_counter() - t0
+    lz_one = sharding.sharded_batched_loglike(gb, H, group=None, local_fn=None) if world == 1 else None
+    ref = []
+    for h in H[:4]:
+        gb.set_hyper(h)
+        ref.append(gb.loglikelihood())
+    mu_m, s2_m = sharding.sharded_mixture_posterior(gb, H[:8*world], Xs[:64])
+    say(check='sharded_batched_loglike', B=len(H), t_s=t_sh, samples_per_s=len(H)/t_sh,
+        rel_err_first4=float(np.max(np.abs(lz_sh[:4] - np.array(ref))/np.abs(ref))),
+        mixture_finite=bool(np.all(np.isfinite(mu_m)) and np.all(s2_m > 0)))
+    assert np.allclose(lz_sh[:4], ref, rtol=1e-10)
+    dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -106,8 +106,38 @@ def gram_probe(ctx, L, kern, n, label):
     torch.cuda.empty_cache()
 
 
+def fitc_probe(ctx, L, n, p, d):
+    X, y = problem(n, d)
+    U = np.random.RandomState(3).rand(p, d)
+    gp = pygp.inference.FITC(pygp.likelihoods.Gaussian(0.1), pygp.kernels.SE(1.0, [0.6]*d), 0.0, U)
+    t0 = time.perf_counter()
+    gp.add_data(X, y)
+    t_first = time.perf_counter() - t0
+    h = gp.get_hyper()
+    gp.set_hyper(h + 0.01)
+    gp.loglikelihood(True)
+    ctx.profile(True)
+    t0 = time.perf_counter()
+    gp.set_hyper(h)
+    t_upd = time.perf_counter() - t0
+    lZ, dlZ = gp.loglikelihood(True)
+    t_all = time.perf_counter() - t0
+    pr = prof_dict(ctx)
+    ctx.profile(False)
+    Xs = np.random.RandomState(1).rand(65536, d)
+    gp.posterior(Xs[:1024])
+    t0 = time.perf_counter()
+    gp.posterior(Xs)
+    t_pred = time.perf_counter() - t0
+    flops = 8.0*p*p*n      # update: trsm p^2 n + syrk p^2 n; grad: 2 trsm + 3 tn-gemm + 1 nt-gemm (2 p^2 n) ~ 8 p^2 n
+    print(json.dumps({'probe': 'fitc', 'n': n, 'p': p, 'd': d, 'first_s': t_first, 'update_s': t_upd,
+                      'update+grad_s': t_all, 'eff_tflops_8p2n': flops/t_all/1e12, 'lZ': lZ,
+                      'predict_pts_per_s': len(Xs)/t_pred, 'prof': pr}), flush=True)
+    del gp
+
+
 def main():
-    what = sys.argv[1:] or ['predict', 'batched', 'gram']
+    what = sys.argv[1:] or ['predict', 'batched', 'gram', 'fitc']
     ctx, L = _lib.context(), _lib.lib()
     if 'predict' in what:
         predict_probe(ctx, L, 8192, 16, 16384)
@@ -115,6 +145,9 @@ def main():
     if 'batched' in what:
         batched_probe(ctx, L, 2048, 8, 256)
         batched_probe(ctx, L, 512, 8, 1024)
+    if 'fitc' in what:
+        fitc_probe(ctx, L, 65536, 512, 8)
+        fitc_probe(ctx, L, 262144, 2048, 8)
     if 'gram' in what:
         pk = pygp.kernels
         n = 32768
