@@ -145,6 +145,24 @@ struct DevBuf {
     template <class T> T* as() { return reinterpret_cast<T*>(p); }
 };
 
+// large scratch from the context pool (returned to it, not to the driver)
+struct PoolBuf {
+    pgp_ctx* ctx = nullptr;
+    double* p = nullptr;
+    size_t count = 0;
+    ~PoolBuf() {
+        if (p) {
+            cudaStreamSynchronize(ctx->stream);
+            pool_free(ctx, p, count);
+        }
+    }
+    int get(pgp_ctx* c, size_t n) {
+        ctx = c;
+        count = std::max<size_t>(n, 1);
+        return pool_alloc(c, &p, count);
+    }
+};
+
 template <class T>
 int alloc(pgp_ctx* ctx, DevBuf& b, size_t count) {
     T* p = nullptr;
@@ -714,21 +732,22 @@ static int batched_impl(pgp_ctx* ctx, const pgp_kernel_spec* spec, const double*
     size_t budget = std::min<size_t>((size_t)24 << 30, free_b / 2);
     int64_t chunk = std::max<int64_t>(1, std::min<int64_t>({(int64_t)(budget / per), B, (int64_t)32768}));
 
-    DevBuf dX, dy, dXs, dspec, dZ, dF, dres, dinfo, dZs, dB, dout;
+    DevBuf dX, dy, dXs, dspec, dZ, dres, dinfo, dZs, dout;
+    PoolBuf dF, dB;
     PGP_TRY(alloc<double>(ctx, dX, (size_t)n * d));
     PGP_TRY(alloc<double>(ctx, dy, (size_t)n));
     PGP_CUDA(ctx, cudaMemcpyAsync(dX.p, X, sizeof(double) * n * d, cudaMemcpyHostToDevice, ctx->stream));
     PGP_CUDA(ctx, cudaMemcpyAsync(dy.p, y, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
     PGP_TRY(alloc<DevSpec>(ctx, dspec, chunk));
     PGP_TRY(alloc<double>(ctx, dZ, (size_t)chunk * np * n * d));
-    PGP_TRY(alloc<double>(ctx, dF, (size_t)chunk * (n + 1) * ld));
+    PGP_TRY(dF.get(ctx, (size_t)chunk * (n + 1) * ld));
     PGP_TRY(alloc<double>(ctx, dres, (size_t)chunk));
     PGP_TRY(alloc<int>(ctx, dinfo, (size_t)chunk));
     if (pred) {
         PGP_TRY(alloc<double>(ctx, dXs, (size_t)ms * d));
         PGP_CUDA(ctx, cudaMemcpyAsync(dXs.p, Xs, sizeof(double) * ms * d, cudaMemcpyHostToDevice, ctx->stream));
         PGP_TRY(alloc<double>(ctx, dZs, (size_t)chunk * np * ms * d));
-        PGP_TRY(alloc<double>(ctx, dB, (size_t)chunk * ms * ld));
+        PGP_TRY(dB.get(ctx, (size_t)chunk * ms * ld));
         PGP_TRY(alloc<double>(ctx, dout, (size_t)chunk * 2 * ms));
     }
     std::vector<DevSpec> hspecs((size_t)chunk);
@@ -745,7 +764,7 @@ static int batched_impl(pgp_ctx* ctx, const pgp_kernel_spec* spec, const double*
         PGP_CUDA(ctx, cudaMemsetAsync(dinfo.p, 0, sizeof(int) * bc, ctx->stream));
         PGP_TRY(launch_scale(ctx, dspec.as<DevSpec>(), dX.as<double>(), n, d, np, dZ.as<double>(), bc));
         Mat F;
-        F.p = dF.as<double>();
+        F.p = dF.p;
         F.ld = ld;
         F.bstride = (n + 1) * ld;
         F.batch = bc;
@@ -778,14 +797,14 @@ static int batched_impl(pgp_ctx* ctx, const pgp_kernel_spec* spec, const double*
             c.n2 = n;
             c.ndim = d;
             c.n_parts = np;
-            c.out = dB.as<double>();
+            c.out = dB.p;
             c.ldo = ld;
             c.out_bstride = ms * ld;
             c.batch = bc;
             c.single_type = single_type(spec);
             PGP_TRY(launch_gram(ctx, c));
             Mat Bm;
-            Bm.p = dB.as<double>();
+            Bm.p = dB.p;
             Bm.ld = ld;
             Bm.bstride = ms * ld;
             Bm.batch = bc;
