@@ -49,6 +49,12 @@ class _DeviceModel(object):
 
 
 class ExactGP(GP):
+    # Opt-in multi-GPU factorisation: set to e.g. {'nb': 1024, 'min_n': 32768} in a
+    # one-process-per-GPU job whose ranks all hold the same model and call
+    # set_hyper in lockstep (replicated optimiser); `_update` then runs the 1-D
+    # block-column distributed Cholesky (pygp_b200/distchol.py) for ndata >= min_n.
+    distributed = None
+
     def __init__(self, likelihood, kernel, mean):
         if not isinstance(likelihood, Gaussian):
             raise ValueError('exact inference requires a Gaussian likelihood')
@@ -79,6 +85,12 @@ class ExactGP(GP):
             Xn, yn = _lib.as_f64(self._X[self._ndev:], 2), _lib.as_f64(self._y[self._ndev:], 1)
             _lib.check(self._dev.ctx, L.pgp_exact_append(self._dev.handle, _lib.ptr(Xn), _lib.ptr(yn), len(Xn)))
         self._ndev = n
+        cfg = self.distributed
+        if cfg and n >= cfg.get('min_n', 32768):
+            from .. import sharding, distchol
+            if sharding.world(cfg.get('group'))[1] > 1:
+                distchol.distributed_update(self, nb=cfg.get('nb', 1024), group=cfg.get('group'))
+                return
         hyp = _lib.as_f64(self.get_hyper())
         _lib.check(self._dev.ctx, L.pgp_exact_update(self._dev.handle, _lib.ptr(hyp)))
 
