@@ -196,3 +196,54 @@ def test_distributed_update_single_rank(N, nb):
     mu0, s20 = ref.posterior(Xs)
     nt.assert_allclose(mu, mu0, rtol=1e-10, atol=1e-11)
     nt.assert_allclose(s2, s20, rtol=1e-9, atol=1e-12)
+
+
+def test_full_size_properties_n32768():
+    """BASELINE configs[2] at full size (Matern-5/2 ARD d=16, N=32768), where the
+    oracle cannot run (> 72 GiB): size-independent properties of the same
+    device state instead.
+      (1) L L^T reproduces K + sn2 I on sampled rows (factor correctness);
+      (2) a = L^-1 r: |a|^2 and sum log diag L reproduce lZ (exact.py:119-121);
+      (3) posterior mean at training inputs equals y - sn2 alpha, with alpha taken
+          from dlZ's mean entry sum(alpha) (ties predict, solve and gradient paths);
+      (4) directional finite difference of lZ matches dlZ (tests/test_inference.py:105-112)."""
+    import pygp_b200 as pygp
+    n, d = 32768, 16
+    X, y, _ = synthetic_problem(n, d, 0)
+    ell = [0.5*np.sqrt(d)]*d
+    kern = pygp.kernels.Matern(1.0, ell, 5)
+    gp = pygp.inference.ExactGP(pygp.likelihoods.Gaussian(0.1), kern, 0.0)
+    gp.add_data(X, y)
+    lZ, dlZ = gp.loglikelihood(True)
+    assert np.isfinite(lZ) and np.all(np.isfinite(dlZ))
+    sn2 = 0.01
+    # (1) sampled rows of L L^T against the kernel, through the factor as the reference stores it
+    R, a = gp._R, gp._a                      # upper R = L^T (8 GiB on the host)
+    rows = [0, 1, 63, 64, 4097, 20000, n - 1]
+    Krows = kern.get(X[rows], X)
+    for r_i, krow in zip(rows, Krows):
+        rec = R[:r_i + 1, r_i] @ R[:r_i + 1, :]          # (L L^T)[r_i, :] = sum_k R[k, r_i] R[k, :]
+        ref = krow.copy()
+        ref[r_i] += sn2
+        nt.assert_allclose(rec[r_i:], ref[r_i:], rtol=1e-11, atol=1e-12)
+    # (2) lZ from its definition
+    lZ_def = -0.5*a @ a - np.sum(np.log(np.diag(R))) - 0.5*n*np.log(2*np.pi)
+    nt.assert_allclose(lZ, lZ_def, rtol=1e-12)
+    # (3) mu(X_i) = mean + k_i^T alpha = y_i - sn2 alpha_i ; alpha = R^-1 a on a slice via back substitution
+    import scipy.linalg as sla
+    tail = slice(n - 512, n)
+    alpha_tail = sla.solve_triangular(R[tail, tail], a[tail])      # last block of R^-1 a
+    mu, s2 = gp.posterior(X[tail])
+    nt.assert_allclose(mu, y[tail] - sn2*alpha_tail, rtol=1e-8, atol=1e-8)
+    assert np.all(s2 > 0) and np.all(s2 < 1.0 + 1e-12)
+    del R
+    # (4) directional derivative
+    h = gp.get_hyper()
+    v = np.random.RandomState(5).randn(len(h))
+    v /= np.linalg.norm(v)
+    eps = 1e-5
+    gp.set_hyper(h + eps*v)
+    lp = gp.loglikelihood()
+    gp.set_hyper(h - eps*v)
+    lm = gp.loglikelihood()
+    nt.assert_allclose((lp - lm)/(2*eps), dlZ @ v, rtol=2e-6)
