@@ -218,7 +218,7 @@ def test_full_size_properties_n32768():
     assert np.isfinite(lZ) and np.all(np.isfinite(dlZ))
     sn2 = 0.01
     # (1) sampled rows of L L^T against the kernel, through the factor as the reference stores it
-    R, a = gp._R, gp._a                      # upper R = L^T (8 GiB on the host)
+    R, a = gp._factor()                      # upper R = L^T (8 GiB on the host), a = R^-T r
     rows = [0, 1, 63, 64, 4097, 20000, n - 1]
     Krows = kern.get(X[rows], X)
     for r_i, krow in zip(rows, Krows):
