@@ -783,7 +783,14 @@ static int batched_impl(pgp_ctx* ctx, const pgp_kernel_spec* spec, const double*
         g.single_type = single_type(spec);
         PGP_TRY(launch_gram(ctx, g));
         PGP_TRY(launch_set_residual(ctx, F, n, dy.as<double>(), dspec.as<DevSpec>()));
-        PGP_TRY(potrf_lower(ctx, F, n, 1, dinfo.as<int>()));
+        if (trsv_lower_supported(n)) {
+            // a = L^-1 r by its own batched substitution: as an extra row of the
+            // factorisation it would cost a 128-row tile in every trailing update
+            PGP_TRY(potrf_lower(ctx, F, n, 0, dinfo.as<int>()));
+            PGP_TRY(launch_trsv_lower(ctx, F, n));
+        } else {
+            PGP_TRY(potrf_lower(ctx, F, n, 1, dinfo.as<int>()));
+        }
         PGP_TRY(launch_loglik(ctx, F, n, dres.as<double>()));
         PGP_CUDA(ctx, cudaMemcpyAsync(hres.data(), dres.p, sizeof(double) * bc, cudaMemcpyDeviceToHost, ctx->stream));
         PGP_CUDA(ctx, cudaMemcpyAsync(hinfo.data(), dinfo.p, sizeof(int) * bc, cudaMemcpyDeviceToHost, ctx->stream));

@@ -396,6 +396,76 @@ int syrk_upper_lower(pgp_ctx* ctx, const Mat& H, const Mat& G, int64_t n) {
 }
 
 // ---------------------------------------------------------------------------
+// batched forward substitution  x <- L^-1 x  for ONE right-hand side per problem
+// (row n of each factor buffer, a = L^-1 r of exact.py:55).  Used by the batched
+// small-N path instead of letting r ride along as row n of the factorisation:
+// there the extra row costs a whole 128-row tile in every trailing update
+// (+20 % tile work at N = 2048).  One CTA per problem, x in shared memory,
+// 64-wide blocks: warp 0 solves the diagonal block by shuffles, then all warps
+// subtract the block's contribution from the remaining entries (one warp per
+// row segment of 64 contiguous doubles).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) trsv_lower_kernel(double* F, int64_t ld, int64_t bstride, int n) {
+    extern __shared__ double xs[];                 // [n] then the staged diagonal block [64][65]
+    double* T = xs + ((n + 1) & ~1);
+    constexpr int TP = kNB + 1;
+    double* Fb = F + (int64_t)blockIdx.x * bstride;
+    double* xg = Fb + (int64_t)n * ld;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) xs[i] = xg[i];
+    for (int k0 = 0; k0 < n; k0 += kNB) {
+        const int nb = min(kNB, n - k0);
+        for (int idx = threadIdx.x; idx < kNB * kNB; idx += blockDim.x) {
+            int r = idx >> 6, c = idx & 63;
+            T[r * TP + c] = (r < nb && c <= r) ? Fb[(int64_t)(k0 + r) * ld + k0 + c] : (r == c ? 1.0 : 0.0);
+        }
+        __syncthreads();
+        if (warp == 0) {
+            // lanes own entries lane and 32 + lane of the block
+            double x0 = lane < nb ? xs[k0 + lane] : 0.0;
+            double x1 = lane + 32 < nb ? xs[k0 + 32 + lane] : 0.0;
+#pragma unroll 8
+            for (int k = 0; k < kNB; ++k) {
+                // x_k is final once all earlier columns are eliminated: broadcast it
+                double xk = __shfl_sync(0xffffffffu, k < 32 ? x0 : x1, k & 31) / T[k * TP + k];
+                if (k < 32) { if (lane == k) x0 = xk; } else { if (lane == k - 32) x1 = xk; }
+                if (lane > k) x0 -= T[lane * TP + k] * xk;
+                if (lane + 32 > k) x1 -= T[(lane + 32) * TP + k] * xk;
+            }
+            if (lane < nb) xs[k0 + lane] = x0;
+            if (lane + 32 < nb) xs[k0 + 32 + lane] = x1;
+        }
+        __syncthreads();
+        // x[j] -= L[j, k0:k0+nb] . x[k0:k0+nb]  for j >= k0 + nb
+        const double xa = lane < nb ? xs[k0 + lane] : 0.0;
+        const double xb = lane + 32 < nb ? xs[k0 + 32 + lane] : 0.0;
+        for (int j = k0 + nb + warp; j < n; j += nwarp) {
+            const double* Lj = Fb + (int64_t)j * ld + k0;
+            double s = (lane < nb ? Lj[lane] : 0.0) * xa + (lane + 32 < nb ? Lj[lane + 32] : 0.0) * xb;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) xs[j] -= s;
+        }
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) xg[i] = xs[i];
+}
+
+constexpr int64_t kTrsvMaxN = 20480;   // x (+ one 64 x 65 tile) must fit in shared memory
+
+int launch_trsv_lower(pgp_ctx* ctx, const Mat& F, int64_t n) {
+    if (n <= 0) return 0;
+    if (n > kTrsvMaxN) return ctx->fail(PGP_E_ARG, "trsv_lower: n too large for the shared-memory vector");
+    size_t smem = ((size_t)((n + 1) & ~1) + (size_t)kNB * (kNB + 1)) * sizeof(double);
+    PGP_CUDA(ctx, cudaFuncSetAttribute(trsv_lower_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    Launch L(ctx, PC_TRSM, (double)n * n * F.batch);
+    trsv_lower_kernel<<<F.batch, 1024, smem, ctx->stream>>>(F.p, F.ld, F.bstride, (int)n);
+    return check_launch(ctx, "trsv_lower_kernel");
+}
+
+bool trsv_lower_supported(int64_t n) { return n <= kTrsvMaxN; }
+
+// ---------------------------------------------------------------------------
 // small reductions
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ double block_sum_256(double v, double* red) {

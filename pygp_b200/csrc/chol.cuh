@@ -24,6 +24,11 @@ struct Mat {
 // style index of the first non-positive pivot (0 = ok).
 int potrf_lower(pgp_ctx* ctx, const Mat& F, int64_t n, int64_t extra, int* d_info);
 
+// row n of every batch member <- L^-1 (row n): a = L^-1 r as a separate batched
+// forward substitution (the batched small-N path; n <= 20480).
+int launch_trsv_lower(pgp_ctx* ctx, const Mat& F, int64_t n);
+bool trsv_lower_supported(int64_t n);
+
 // B[:, 0:n) <- B L^-T for `rows` rows of B (same column space as L).
 int trsm_right_lt(pgp_ctx* ctx, const Mat& B, int64_t rows, const Mat& L, int64_t n);
 
