@@ -108,6 +108,12 @@ int pgp_dget(pgp_ctx* ctx, const pgp_kernel_spec* spec, const double* hyp,
 /* Kernel.dgrad(X) (se.py:71 ...): out (nhyper, n). */
 int pgp_dgrad(pgp_ctx* ctx, const pgp_kernel_spec* spec, const double* hyp,
               const double* X, int64_t n, double* out);
+/* Kernel.gradx / grady (se.py:76-86, matern.py:100-114, periodic.py:84-97,
+ * rq.py:95-111, _real.py:96-127): derivatives w.r.t. the inputs X1 (wrt_y = 0)
+ * or X2 (wrt_y = 1).  out: (n1, n2, ndim). */
+int pgp_gram_gradx(pgp_ctx* ctx, const pgp_kernel_spec* spec, const double* hyp,
+                   const double* X1, int64_t n1, const double* X2, int64_t n2,
+                   int32_t wrt_y, double* out);
 /* same as pgp_gram with operands and result resident in HBM (bench.py `value`) */
 int pgp_gram_dev(pgp_ctx* ctx, const pgp_kernel_spec* spec, const double* hyp,
                  const double* d_X1, int64_t n1, const double* d_X2, int64_t n2,
@@ -134,6 +140,10 @@ int pgp_exact_loglike(pgp_model* m, int want_grad, double* lZ, double* dlZ);
 /* ExactGP._marg_posterior(X, grad=False) (exact.py:81-97): mu (ms), s2 (ms). */
 int pgp_exact_predict(pgp_model* m, const double* Xs, int64_t ms,
                       double* mu, double* s2);
+/* ExactGP._marg_posterior(X, grad=True) (exact.py:81-116): additionally the
+ * input-gradients dmu, ds2 (ms, ndim). */
+int pgp_exact_predict_grad(pgp_model* m, const double* Xs, int64_t ms,
+                           double* mu, double* s2, double* dmu, double* ds2);
 /* device-resident test points / outputs (bench.py `value`, sharded predict) */
 int pgp_exact_predict_dev(pgp_model* m, const double* d_Xs, int64_t ms,
                           double* d_mu, double* d_s2);
@@ -176,6 +186,9 @@ int pgp_fitc_loglike(pgp_fitc* f, int want_grad, double* lZ, double* dlZ);
 /* FITC._marg_posterior(X, grad=False) (fitc.py:122-142) */
 int pgp_fitc_predict(pgp_fitc* f, const double* Xs, int64_t ms,
                      double* mu, double* s2);
+/* FITC._marg_posterior(X, grad=True) (fitc.py:122-165): dmu, ds2 (ms, ndim) */
+int pgp_fitc_predict_grad(pgp_fitc* f, const double* Xs, int64_t ms,
+                          double* mu, double* s2, double* dmu, double* ds2);
 
 /* ---- building blocks exported for tests and profiling ---------------------- */
 /* C (m, n) = beta C + alpha A (m, k) B (n, k)^T on device buffers, row-major,

@@ -45,7 +45,13 @@ def kernel_golden(pygp):
             'grad11': np.array(list(rk.grad(x1))),
             'dget': rk.dget(x1),
             'dgrad': np.array(list(rk.dgrad(x1))),
+            'gradx12': rk.gradx(x1, x2),
+            'grady12': rk.grady(x1, x2),
+            'gradx11': rk.gradx(x1),
         }
+        _close(ok.gradx(x1, x2), rec['gradx12'], name + '.gradx12')
+        _close(ok.grady(x1, x2), rec['grady12'], name + '.grady12')
+        _close(ok.gradx(x1), rec['gradx11'], name + '.gradx11')
         _close(ok.get(x1, x2), rec['get12'], name + '.get12')
         _close(ok.get(x1), rec['get11'], name + '.get11')
         _close(np.array(ok.grad(x1, x2)), rec['grad12'], name + '.grad12')
@@ -81,14 +87,16 @@ def gp_golden(pygp):
         rgp.add_data(X, y)
         ogp.add_data(X, y)
         lZ, dlZ = rgp.loglikelihood(True)
-        mu, s2 = rgp.posterior(Xs)
+        mu, s2, dmu, ds2 = rgp.posterior(Xs, grad=True)
         olZ, odlZ = ogp.loglikelihood(True)
-        omu, os2 = ogp.posterior(Xs)
+        omu, os2, odmu, ods2 = ogp.posterior(Xs, grad=True)
+        _close(odmu, dmu, name + '.dmu', 1e-10, 1e-12)
+        _close(ods2, ds2, name + '.ds2', 1e-10, 1e-12)
         _close(olZ, lZ, name + '.lZ')
         _close(odlZ, dlZ, name + '.dlZ', 1e-10, 1e-11)
         _close(omu, mu, name + '.mu')
         _close(os2, s2, name + '.s2', 1e-11, 1e-13)
-        rec = {'hyper': rgp.get_hyper(), 'lZ': lZ, 'dlZ': dlZ, 'mu': mu, 's2': s2}
+        rec = {'hyper': rgp.get_hyper(), 'lZ': lZ, 'dlZ': dlZ, 'mu': mu, 's2': s2, 'dmu': dmu, 'ds2': ds2}
         if not fitc:
             rec['R'] = rgp._R if N <= 64 else rgp._R[:8, :8]
             rec['a'] = rgp._a

@@ -43,6 +43,12 @@ def _sqdist(X1, X2=None):
     return ssd.cdist(X1, X2, 'sqeuclidean')
 
 
+def _diff(X1, X2=None):
+    # _distances.py:26-32 -- pairwise differences X1[:, None, :] - X2[None, :, :]
+    X2 = X1 if (X2 is None) else X2
+    return X1[:, None, :] - X2[None, :, :]
+
+
 def _sqdist_foreach(X1, X2=None):
     # _distances.py:44-52 -- one squared-difference matrix per input dimension.
     X2 = X1 if (X2 is None) else X2
@@ -100,6 +106,17 @@ class OSE(_OKernel):
             for D in _sqdist_foreach(X1, X2):
                 out.append(K*D)
         return out
+
+    def gradx(self, X1, X2=None):
+        # se.py:76-83
+        ell = np.exp(self._logell)
+        X1, X2 = _rescale(ell, X1, X2)
+        D = _diff(X1, X2)
+        K = np.exp(self._logsf*2 - np.sum(D**2, axis=-1)/2)
+        return -K[:, :, None] * D / ell
+
+    def grady(self, X1, X2=None):
+        return -self.gradx(X1, X2)      # se.py:85-86
 
     def dget(self, X1):
         return np.exp(self._logsf*2) * np.ones(len(X1))  # se.py:68-69
@@ -173,6 +190,20 @@ class OMatern(_OKernel):
                     out.append(np.where(D < 1e-12, 0, M*D_/D))
         return out
 
+    def gradx(self, X1, X2=None):
+        # matern.py:100-111
+        ell = np.exp(self._logell) / np.sqrt(self._d)
+        X1, X2 = _rescale(ell, X1, X2)
+        D1 = _diff(X1, X2)
+        D = np.sqrt(np.sum(D1**2, axis=-1))
+        S = np.exp(self._logsf*2 - D)
+        with np.errstate(invalid='ignore', divide='ignore'):
+            M = np.where(D < 1e-12, 0, S * self._df(D) / D)
+        return -M[:, :, None] * D1 / ell
+
+    def grady(self, X1, X2=None):
+        return -self.gradx(X1, X2)      # matern.py:113-114
+
     def dget(self, X1):
         return np.exp(self._logsf*2) * np.ones(len(X1))  # matern.py:92-93
 
@@ -216,6 +247,18 @@ class OPeriodic(_OKernel):
         S = R**2
         E = 2 * sf2 * np.exp(-2*S)
         return [E, 2*E*S, 2*E*R*D * np.cos(D) / ell]
+
+    def gradx(self, X1, X2=None):
+        # periodic.py:84-94
+        sf2 = np.exp(self._logsf*2)
+        ell = np.exp(self._logell)
+        p = np.exp(self._logp)
+        D = _diff(X1, X2) * np.pi / p
+        K = sf2 * np.exp(-2*(np.sin(D) / ell)**2)
+        return -2 * np.pi / ell**2 / p * K * np.sin(2*D)
+
+    def grady(self, X1, X2=None):
+        return -self.gradx(X1, X2)      # periodic.py:96-97
 
     def dget(self, X1):
         return np.exp(self._logsf*2) * np.ones(len(X1))  # periodic.py:76-77
@@ -278,6 +321,20 @@ class ORQ(_OKernel):
         out.append(0.5*M - alpha*K*np.log(E))
         return out
 
+    def gradx(self, X1, X2=None):
+        # rq.py:95-108
+        sf2 = np.exp(self._logsf*2)
+        ell = np.exp(self._logell)
+        alpha = np.exp(self._logalpha)
+        X1, X2 = _rescale(ell, X1, X2)
+        D = _diff(X1, X2)
+        E = 1 + np.sum(D**2, axis=-1) / 2 / alpha
+        K = sf2 * E**(-alpha)
+        return -(K/E)[:, :, None] * D / ell
+
+    def grady(self, X1, X2=None):
+        return -self.gradx(X1, X2)      # rq.py:110-111
+
     def dget(self, X1):
         return np.exp(self._logsf*2) * np.ones(len(X1))  # rq.py:86-87
 
@@ -330,6 +387,12 @@ class OSum(_OCombo):
     def get(self, X1, X2=None):
         return sum(p.get(X1, X2) for p in self._parts)
 
+    def gradx(self, X1, X2=None):
+        return sum(p.gradx(X1, X2) for p in self._parts)        # _real.py:96-97
+
+    def grady(self, X1, X2=None):
+        return sum(p.grady(X1, X2) for p in self._parts)        # _real.py:99-100
+
     def dget(self, X):
         return sum(p.dget(X) for p in self._parts)
 
@@ -347,6 +410,16 @@ class OProduct(_OCombo):
         for p in self._parts:
             out = out * p.get(X1, X2)
         return out
+
+    def gradx(self, X1, X2=None):
+        # _real.py:119-122
+        F = _product_but([p.get(X1, X2)[:, :, None] for p in self._parts])
+        return sum(f*p.gradx(X1, X2) for f, p in zip(F, self._parts))
+
+    def grady(self, X1, X2=None):
+        # _real.py:124-127
+        F = _product_but([p.get(X1, X2)[:, :, None] for p in self._parts])
+        return sum(f*p.grady(X1, X2) for f, p in zip(F, self._parts))
 
     def dget(self, X):
         out = 1
@@ -456,8 +529,8 @@ class OExactGP(object):
             np.sum(alpha)]
         return lZ, dlZ
 
-    def posterior(self, X):
-        # exact.py:81-97 (grad=False branch), via _base.py:179-186
+    def posterior(self, X, grad=False):
+        # exact.py:81-116, via _base.py:179-186
         X = np.array(X, ndmin=2, dtype=float)
         mu = np.full(X.shape[0], self._mean)
         s2 = self._kernel.dget(X)
@@ -466,7 +539,18 @@ class OExactGP(object):
             RK = sla.solve_triangular(self._R, K, trans=True)
             mu += np.dot(RK.T, self._a)
             s2 -= np.sum(RK**2, axis=0)
-        return mu, s2
+        if not grad:
+            return mu, s2
+        dmu = np.zeros_like(X)
+        ds2 = np.zeros_like(X)
+        if self._X is not None:
+            dK = self._kernel.grady(self._X, X)
+            dK = dK.reshape(self.ndata, -1)
+            RdK = sla.solve_triangular(self._R, dK, trans=True)
+            dmu += np.dot(RdK.T, self._a).reshape(X.shape)
+            RdK = np.rollaxis(np.reshape(RdK, (-1,) + X.shape), 2)
+            ds2 -= 2 * np.sum(RdK * RK, axis=1).T
+        return mu, s2, dmu, ds2
 
 
 # -- FITC: pygp/inference/fitc.py:19-232 --------------------------------------
@@ -530,8 +614,8 @@ class OFITC(object):
         self._R = np.dot(sla.cholesky(self._A), self._L)
         self._b = sla.solve_triangular(self._R, self._a, trans=True)
 
-    def posterior(self, X):
-        # fitc.py:122-142 (grad=False branch)
+    def posterior(self, X, grad=False):
+        # fitc.py:122-165
         X = np.array(X, ndmin=2, dtype=float)
         mu = np.full(X.shape[0], self._mean)
         s2 = self._kernel.dget(X)
@@ -541,7 +625,22 @@ class OFITC(object):
             RK = sla.solve_triangular(self._R, K, trans=True)
             mu += np.dot(RK.T, self._b)
             s2 += np.sum(RK**2, axis=0) - np.sum(LK**2, axis=0)
-        return mu, s2
+        if not grad:
+            return mu, s2
+        dmu = np.zeros_like(X)
+        ds2 = np.zeros_like(X)
+        if self._X is not None:
+            p = self._U.shape[0]
+            dK = self._kernel.grady(self._U, X)
+            dK = dK.reshape(p, -1)
+            LdK = sla.solve_triangular(self._L, dK, trans=True)
+            RdK = sla.solve_triangular(self._R, dK, trans=True)
+            dmu += np.dot(RdK.T, self._b).reshape(X.shape)
+            LdK = np.rollaxis(np.reshape(LdK, (p,) + X.shape), 2)
+            RdK = np.rollaxis(np.reshape(RdK, (p,) + X.shape), 2)
+            ds2 += 2 * np.sum(RdK * RK, axis=1).T
+            ds2 -= 2 * np.sum(LdK * LK, axis=1).T
+        return mu, s2, dmu, ds2
 
     def loglikelihood(self, grad=False):
         # fitc.py:167-232

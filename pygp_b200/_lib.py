@@ -63,6 +63,7 @@ SIGNATURES = {
     'pgp_gram_grad': (C.c_int, [_vp, _sp, _dp, _dp, _i64, _dp, _i64, C.c_int32, _dp]),
     'pgp_dget': (C.c_int, [_vp, _sp, _dp, _dp, _i64, _dp]),
     'pgp_dgrad': (C.c_int, [_vp, _sp, _dp, _dp, _i64, _dp]),
+    'pgp_gram_gradx': (C.c_int, [_vp, _sp, _dp, _dp, _i64, _dp, _i64, C.c_int32, _dp]),
     'pgp_gram_dev': (C.c_int, [_vp, _sp, _dp, _vp, _i64, _vp, _i64, _vp]),
     'pgp_exact_create': (C.c_int, [_vp, _sp, _dp, _dp, _i64, C.POINTER(_vp)]),
     'pgp_exact_append': (C.c_int, [_vp, _dp, _dp, _i64]),
@@ -72,6 +73,7 @@ SIGNATURES = {
     'pgp_exact_update': (C.c_int, [_vp, _dp]),
     'pgp_exact_loglike': (C.c_int, [_vp, C.c_int, _dp, _dp]),
     'pgp_exact_predict': (C.c_int, [_vp, _dp, _i64, _dp, _dp]),
+    'pgp_exact_predict_grad': (C.c_int, [_vp, _dp, _i64, _dp, _dp, _dp, _dp]),
     'pgp_exact_predict_dev': (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     'pgp_exact_get_factor': (C.c_int, [_vp, _dp, _dp]),
     'pgp_exact_factor_buffer': (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_i64)]),
@@ -83,6 +85,7 @@ SIGNATURES = {
     'pgp_fitc_update': (C.c_int, [_vp, _dp]),
     'pgp_fitc_loglike': (C.c_int, [_vp, C.c_int, _dp, _dp]),
     'pgp_fitc_predict': (C.c_int, [_vp, _dp, _i64, _dp, _dp]),
+    'pgp_fitc_predict_grad': (C.c_int, [_vp, _dp, _i64, _dp, _dp, _dp, _dp]),
     'pgp_dev_gemm_nt': (C.c_int, [_vp, _i64, _i64, _i64, C.c_double, _vp, _i64, _vp, _i64,
                                   C.c_double, _vp, _i64, C.c_int]),
     'pgp_dev_gemm': (C.c_int, [_vp, C.c_int, C.c_int, _i64, _i64, _i64, C.c_double, _vp, _i64, _vp, _i64,

@@ -276,6 +276,57 @@ extern "C" int pgp_gram_dev(pgp_ctx* ctx, const pgp_kernel_spec* spec, const dou
     return gram_device(ctx, spec, hyp, d_X1, n1, d_X2, n2, -1, d_out, n2);
 }
 
+// Kernel.gradx / grady (se.py:76-86, matern.py:100-114, periodic.py:84-97, rq.py:95-111,
+// _real.py:96-127): out (n1, n2, ndim); grady = -gradx for these stationary kernels.
+extern "C" int pgp_gram_gradx(pgp_ctx* ctx, const pgp_kernel_spec* spec, const double* hyp, const double* X1,
+                              int64_t n1, const double* X2, int64_t n2, int32_t wrt_y, double* out) {
+    if (!ctx) return PGP_E_ARG;
+    if (!spec || !hyp || !X1 || !out || n1 < 0 || n2 < 0) return ctx->fail(PGP_E_ARG, "null or negative argument");
+    PGP_TRY(set_device(ctx));
+    if (!X2) n2 = n1;
+    if (n1 == 0 || n2 == 0) return 0;
+    const int d = spec->ndim, np = spec->n_parts;
+    DevSpec hs;
+    PGP_TRY(compile_spec(spec, hyp, 0.0, 0.0, &hs, &ctx->err));
+    DevBuf dspec, x1, x2, z1, z2, o;
+    PGP_TRY(alloc<DevSpec>(ctx, dspec, 1));
+    PGP_TRY(upload_spec(ctx, hs, dspec.as<DevSpec>()));
+    PGP_TRY(alloc<double>(ctx, x1, (size_t)n1 * d));
+    PGP_CUDA(ctx, cudaMemcpyAsync(x1.p, X1, sizeof(double) * n1 * d, cudaMemcpyHostToDevice, ctx->stream));
+    PGP_TRY(alloc<double>(ctx, z1, (size_t)np * n1 * d));
+    PGP_TRY(launch_scale(ctx, dspec.as<DevSpec>(), x1.as<double>(), n1, d, np, z1.as<double>(), 1));
+    const double* Z2 = z1.as<double>();
+    if (X2) {
+        PGP_TRY(alloc<double>(ctx, x2, (size_t)n2 * d));
+        PGP_CUDA(ctx, cudaMemcpyAsync(x2.p, X2, sizeof(double) * n2 * d, cudaMemcpyHostToDevice, ctx->stream));
+        PGP_TRY(alloc<double>(ctx, z2, (size_t)np * n2 * d));
+        PGP_TRY(launch_scale(ctx, dspec.as<DevSpec>(), x2.as<double>(), n2, d, np, z2.as<double>(), 1));
+        Z2 = z2.as<double>();
+    }
+    PGP_TRY(alloc<double>(ctx, o, (size_t)n1 * n2 * d));
+    for (int k = 0; k < d; ++k) {
+        GramArgs g;
+        g.spec = dspec.as<DevSpec>();
+        g.Z1 = z1.as<double>();
+        g.Z2 = Z2;
+        g.n1 = n1;
+        g.n2 = n2;
+        g.ndim = d;
+        g.n_parts = np;
+        g.out = o.as<double>() + k;
+        g.ldo = n2 * d;
+        g.ostride = d;
+        g.xdim = k;
+        g.single_type = single_type(spec);
+        PGP_TRY(launch_gram(ctx, g));
+    }
+    PGP_CUDA(ctx, cudaMemcpyAsync(out, o.p, sizeof(double) * n1 * n2 * d, cudaMemcpyDeviceToHost, ctx->stream));
+    PGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (wrt_y)
+        for (int64_t i = 0; i < n1 * n2 * d; ++i) out[i] = -out[i];
+    return 0;
+}
+
 static int diag_host(pgp_ctx* ctx, const pgp_kernel_spec* spec, const double* hyp, int64_t n, int hmode,
                      double* out) {
     if (!ctx) return PGP_E_ARG;
@@ -616,7 +667,7 @@ extern "C" int pgp_exact_loglike(pgp_model* m, int want_grad, double* lZ, double
 namespace {
 
 int predict_chunked(pgp_model* m, const double* Xs, bool xs_on_device, int64_t ms, double* mu, double* s2,
-                    bool out_on_device) {
+                    bool out_on_device, double* dmu_out = nullptr, double* ds2_out = nullptr) {
     pgp_ctx* ctx = m->ctx;
     if (!m->factored) return ctx->fail(PGP_E_STATE, "predict before a successful update");
     if (ms == 0) return 0;
@@ -625,17 +676,22 @@ int predict_chunked(pgp_model* m, const double* Xs, bool xs_on_device, int64_t m
     // chunk of test points: B (chunk, ld) capped at 4 GiB
     int64_t chunk = std::max<int64_t>(256, (int64_t)(4ll << 30) / (ld * 8));
     chunk = std::min(chunk, ms);
-    if (m->bc_rows < chunk) {
+    // with input-gradients every test point brings ndim more rows (d k / d x*_k) through the same solve
+    const bool want_grad = dmu_out != nullptr;
+    const int64_t rpp = want_grad ? d + 1 : 1;
+    if (want_grad) chunk = std::max<int64_t>(1, std::min(chunk, std::max<int64_t>(64, chunk / rpp)));
+    const int64_t need_rows = chunk * rpp;
+    if (m->bc_rows < need_rows) {
         PGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         pool_free(ctx, m->d_Bc, (size_t)m->bc_rows * ld);
         m->bc_rows = 0;
-        PGP_TRY(pool_alloc(ctx, &m->d_Bc, (size_t)chunk * ld));
-        m->bc_rows = chunk;
+        PGP_TRY(pool_alloc(ctx, &m->d_Bc, (size_t)need_rows * ld));
+        m->bc_rows = need_rows;
     }
     DevBuf xs, zs, o;
     if (!xs_on_device) PGP_TRY(alloc<double>(ctx, xs, (size_t)chunk * d));
     PGP_TRY(alloc<double>(ctx, zs, (size_t)np * chunk * d));
-    if (!out_on_device) PGP_TRY(alloc<double>(ctx, o, (size_t)2 * chunk));
+    if (!out_on_device) PGP_TRY(alloc<double>(ctx, o, (size_t)2 * chunk * rpp));
     Mat B, F;
     B.p = m->d_Bc; B.ld = ld;
     F.p = m->d_F; F.ld = ld;
@@ -661,10 +717,22 @@ int predict_chunked(pgp_model* m, const double* Xs, bool xs_on_device, int64_t m
         g.ldo = ld;
         g.single_type = single_type(&m->spec);
         PGP_TRY(launch_gram(ctx, g));
-        PGP_TRY(trsm_right_lt(ctx, B, mc, F, n));  // rows become (R^-T k*)^T
+        for (int k = 0; want_grad && k < d; ++k) {   // rows mc + k mc + j: d k(x*_j, X) / d x*_jk
+            GramArgs gk = g;
+            gk.out = m->d_Bc + (size_t)(mc + k * mc) * ld;
+            gk.xdim = k;
+            PGP_TRY(launch_gram(ctx, gk));
+        }
+        PGP_TRY(trsm_right_lt(ctx, B, mc * rpp, F, n));  // rows become (R^-T k*)^T
         double* dmu = out_on_device ? mu + s0 : o.as<double>();
         double* ds2 = out_on_device ? s2 + s0 : o.as<double>() + chunk;
         PGP_TRY(launch_predict_reduce(ctx, m->d_Bc, ld, mc, n, m->d_F + n * ld, m->d_spec, dmu, ds2, 1, 0, 0, 0));
+        if (want_grad) {
+            double* dg = o.as<double>() + 2 * chunk;          // (mc, d) dmu then (mc, d) ds2
+            PGP_TRY(launch_predict_grad_reduce(ctx, m->d_Bc, ld, mc, d, n, m->d_F + n * ld, dg, dg + chunk * d));
+            PGP_CUDA(ctx, cudaMemcpyAsync(dmu_out + s0 * d, dg, sizeof(double) * mc * d, cudaMemcpyDeviceToHost, ctx->stream));
+            PGP_CUDA(ctx, cudaMemcpyAsync(ds2_out + s0 * d, dg + chunk * d, sizeof(double) * mc * d, cudaMemcpyDeviceToHost, ctx->stream));
+        }
         if (!out_on_device) {
             PGP_CUDA(ctx, cudaMemcpyAsync(mu + s0, dmu, sizeof(double) * mc, cudaMemcpyDeviceToHost, ctx->stream));
             PGP_CUDA(ctx, cudaMemcpyAsync(s2 + s0, ds2, sizeof(double) * mc, cudaMemcpyDeviceToHost, ctx->stream));
@@ -681,6 +749,14 @@ extern "C" int pgp_exact_predict(pgp_model* m, const double* Xs, int64_t ms, dou
     if (!Xs || !mu || !s2 || ms < 0) return m->ctx->fail(PGP_E_ARG, "null or negative argument");
     PGP_TRY(set_device(m->ctx));
     return predict_chunked(m, Xs, false, ms, mu, s2, false);
+}
+
+extern "C" int pgp_exact_predict_grad(pgp_model* m, const double* Xs, int64_t ms, double* mu, double* s2,
+                                      double* dmu, double* ds2) {
+    if (!m) return PGP_E_ARG;
+    if (!Xs || !mu || !s2 || !dmu || !ds2 || ms < 0) return m->ctx->fail(PGP_E_ARG, "null or negative argument");
+    PGP_TRY(set_device(m->ctx));
+    return predict_chunked(m, Xs, false, ms, mu, s2, false, dmu, ds2);
 }
 
 extern "C" int pgp_exact_predict_dev(pgp_model* m, const double* d_Xs, int64_t ms, double* d_mu, double* d_s2) {

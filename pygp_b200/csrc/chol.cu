@@ -579,6 +579,41 @@ int launch_predict_reduce(pgp_ctx* ctx, const double* B, int64_t ld, int64_t row
     return check_launch(ctx, "predict_reduce_kernel");
 }
 
+// one warp per (dimension k, test point j): rows [mc + k mc + j] of B hold
+// (R^-T d k(X, x*_j)/d x*_jk)^T; dmu = <row, a>, ds2 = -2 <row, B_j>   (exact.py:107-114)
+__global__ void predict_grad_reduce_kernel(const double* B, int64_t ld, int64_t mc, int d, int64_t n,
+                                           const double* a, double* dmu, double* ds2) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= mc * d) return;
+    const int64_t k = w / mc, j = w - k * mc;
+    const double* g = B + (mc + w) * ld;
+    const double* v = B + j * ld;
+    double sm = 0.0, sv = 0.0;
+    for (int64_t i = lane; i < n; i += 32) {
+        double x = g[i];
+        sm += x * a[i];
+        sv += x * v[i];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sm += __shfl_xor_sync(0xffffffffu, sm, o);
+        sv += __shfl_xor_sync(0xffffffffu, sv, o);
+    }
+    if (lane == 0) {
+        dmu[j * d + k] = sm;
+        ds2[j * d + k] = -2.0 * sv;
+    }
+}
+
+int launch_predict_grad_reduce(pgp_ctx* ctx, const double* B, int64_t ld, int64_t mc, int d, int64_t n,
+                               const double* a, double* dmu, double* ds2) {
+    if (mc <= 0) return 0;
+    Launch L(ctx, PC_OTHER, 16.0 * mc * d * n);
+    predict_grad_reduce_kernel<<<(unsigned)ceil_div(mc * d, 8), 256, 0, ctx->stream>>>(B, ld, mc, d, n, a, dmu, ds2);
+    return check_launch(ctx, "predict_grad_reduce_kernel");
+}
+
 __global__ void extract_upper_kernel(const double* F, int64_t ld, int64_t n, double* R) {
     // R[i][j] = L[j][i] for j >= i else 0 ; tile transpose through shared memory
     __shared__ double tile[32][33];

@@ -57,6 +57,11 @@ int launch_predict_reduce(pgp_ctx* ctx, const double* B, int64_t ld, int64_t row
                           const double* a, const DevSpec* d_spec, double* mu, double* s2,
                           int batch, int64_t bstrideB, int64_t bstrideA, int64_t bstrideOut);
 
+// posterior input-gradients (exact.py:99-116): B rows [0, mc) = solved k(x*_j, X),
+// rows [mc + k mc + j] = solved d k / d x*_jk; dmu, ds2 are (mc, d)
+int launch_predict_grad_reduce(pgp_ctx* ctx, const double* B, int64_t ld, int64_t mc, int d, int64_t n,
+                               const double* a, double* dmu, double* ds2);
+
 // R_out (n, n) dense upper = L^T  (the reference's self._R)
 int launch_extract_upper(pgp_ctx* ctx, const double* F, int64_t ld, int64_t n, double* R);
 

@@ -300,6 +300,32 @@ __global__ void fitc_predict_reduce_kernel(const double* LK, const double* RK, i
     }
 }
 
+// one warp per (dimension k, test point j): dmu = <RdK, b>, ds2 = 2 <RdK, RK_j> - 2 <LdK, LK_j>  (fitc.py:144-165)
+__global__ void fitc_predict_grad_reduce_kernel(const double* LK, const double* RK, int64_t ld, int64_t mc, int d,
+                                                int64_t p, const double* b, double* dmu, double* ds2) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= mc * d) return;
+    const int64_t k = w / mc, j = w - k * mc;
+    const double* lg = LK + (mc + w) * ld;
+    const double* rg = RK + (mc + w) * ld;
+    const double* lv = LK + j * ld;
+    const double* rv = RK + j * ld;
+    double sm = 0.0, sr = 0.0, sl = 0.0;
+    for (int64_t i = lane; i < p; i += 32) {
+        sm += rg[i] * b[i];
+        sr += rg[i] * rv[i];
+        sl += lg[i] * lv[i];
+    }
+    sm = warp_sum(sm);
+    sr = warp_sum(sr);
+    sl = warp_sum(sl);
+    if (lane == 0) {
+        dmu[j * d + k] = sm;
+        ds2[j * d + k] = 2.0 * sr - 2.0 * sl;
+    }
+}
+
 // ---- launch helpers ------------------------------------------------------------
 inline unsigned warp_rows_grid(int64_t n) { return (unsigned)ceil_div(n, 8); }
 inline int flat_grid(int64_t total) { return (int)std::min<int64_t>(ceil_div(total, 256), 148 * 8); }
@@ -634,10 +660,9 @@ extern "C" int pgp_fitc_loglike(pgp_fitc* f, int want_grad, double* lZ, double* 
     return 0;
 }
 
-extern "C" int pgp_fitc_predict(pgp_fitc* f, const double* Xs, int64_t ms, double* mu, double* s2) {
-    if (!f) return PGP_E_ARG;
+static int fitc_predict_impl(pgp_fitc* f, const double* Xs, int64_t ms, double* mu, double* s2, double* dmu_out,
+                             double* ds2_out) {
     pgp_ctx* ctx = f->ctx;
-    if (!Xs || !mu || !s2 || ms < 0) return ctx->fail(PGP_E_ARG, "null or negative argument");
     if (!f->factored) return ctx->fail(PGP_E_STATE, "predict before a successful update");
     if (ms == 0) return 0;
     PGP_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -645,17 +670,20 @@ extern "C" int pgp_fitc_predict(pgp_fitc* f, const double* Xs, int64_t ms, doubl
     const int64_t p = f->p, ldp = f->ldp;
     cudaStream_t s = ctx->stream;
     int64_t chunk = std::min<int64_t>(ms, std::max<int64_t>(1024, ((int64_t)1 << 30) / (ldp * 8)));
-    if (f->pc_rows < chunk) {
+    const bool want_grad = dmu_out != nullptr;
+    const int64_t rpp = want_grad ? d + 1 : 1;      // rows per test point: k(x*, U) and its ndim input-derivatives
+    if (want_grad) chunk = std::max<int64_t>(1, std::min(chunk, std::max<int64_t>(64, chunk / rpp)));
+    if (f->pc_rows < chunk * rpp) {
         PGP_CUDA(ctx, cudaStreamSynchronize(s));
         pool_free(ctx, f->d_pred, (size_t)2 * f->pc_rows * ldp);
         f->pc_rows = 0;
-        PGP_TRY(pool_alloc(ctx, &f->d_pred, (size_t)2 * chunk * ldp));
-        f->pc_rows = chunk;
+        PGP_TRY(pool_alloc(ctx, &f->d_pred, (size_t)2 * chunk * rpp * ldp));
+        f->pc_rows = chunk * rpp;
     }
     double *dxs = nullptr, *dzs = nullptr, *dout = nullptr;
     int rc = dev_alloc(ctx, &dxs, (size_t)chunk * d);
     if (!rc) rc = dev_alloc(ctx, &dzs, (size_t)np * chunk * d);
-    if (!rc) rc = dev_alloc(ctx, &dout, (size_t)2 * chunk);
+    if (!rc) rc = dev_alloc(ctx, &dout, (size_t)2 * chunk * rpp);
     Mat L; L.p = f->d_L; L.ld = ldp;
     Mat R; R.p = f->d_R; R.ld = ldp;
     for (int64_t s0 = 0; !rc && s0 < ms; s0 += chunk) {
@@ -673,16 +701,32 @@ extern "C" int pgp_fitc_predict(pgp_fitc* f, const double* Xs, int64_t ms, doubl
             g.out = LK; g.ldo = ldp;
             g.single_type = single_type(&f->spec);
             PGP_TRY(launch_gram(ctx, g));
-            PGP_CUDA(ctx, cudaMemcpyAsync(RK, LK, sizeof(double) * mc * ldp, cudaMemcpyDeviceToDevice, s));
+            for (int k = 0; want_grad && k < d; ++k) {    // d k(x*_j, U) / d x*_jk      fitc.py:151
+                GramArgs gk = g;
+                gk.out = LK + (size_t)(mc + k * mc) * ldp;
+                gk.xdim = k;
+                PGP_TRY(launch_gram(ctx, gk));
+            }
+            PGP_CUDA(ctx, cudaMemcpyAsync(RK, LK, sizeof(double) * mc * rpp * ldp, cudaMemcpyDeviceToDevice, s));
             Mat Lk; Lk.p = LK; Lk.ld = ldp;
             Mat Rk; Rk.p = RK; Rk.ld = ldp;
-            PGP_TRY(trsm_right_lt(ctx, Lk, mc, L, p));    // (L^-T K)^T   fitc.py:131
-            PGP_TRY(trsm_right_lt(ctx, Rk, mc, R, p));    // (R^-T K)^T   fitc.py:132
+            PGP_TRY(trsm_right_lt(ctx, Lk, mc * rpp, L, p));    // (L^-T K)^T   fitc.py:131,154
+            PGP_TRY(trsm_right_lt(ctx, Rk, mc * rpp, R, p));    // (R^-T K)^T   fitc.py:132,155
             {
                 Launch Lc(ctx, PC_OTHER, 16.0 * mc * p);
                 fitc_predict_reduce_kernel<<<warp_rows_grid(mc), 256, 0, s>>>(LK, RK, ldp, mc, p, f->d_b, f->d_spec,
                                                                              dout, dout + chunk);
                 PGP_TRY(check_launch(ctx, "fitc_predict_reduce_kernel"));
+            }
+            if (want_grad) {
+                double* dg = dout + 2 * chunk;
+                Launch Lc(ctx, PC_OTHER, 24.0 * mc * d * p);
+                fitc_predict_grad_reduce_kernel<<<warp_rows_grid(mc * d), 256, 0, s>>>(LK, RK, ldp, mc, d, p, f->d_b, dg,
+                                                                                      dg + chunk * d);
+                PGP_TRY(check_launch(ctx, "fitc_predict_grad_reduce_kernel"));
+                PGP_CUDA(ctx, cudaMemcpyAsync(dmu_out + s0 * d, dg, sizeof(double) * mc * d, cudaMemcpyDeviceToHost, s));
+                PGP_CUDA(ctx, cudaMemcpyAsync(ds2_out + s0 * d, dg + chunk * d, sizeof(double) * mc * d,
+                                              cudaMemcpyDeviceToHost, s));
             }
             PGP_CUDA(ctx, cudaMemcpyAsync(mu + s0, dout, sizeof(double) * mc, cudaMemcpyDeviceToHost, s));
             PGP_CUDA(ctx, cudaMemcpyAsync(s2 + s0, dout + chunk, sizeof(double) * mc, cudaMemcpyDeviceToHost, s));
@@ -695,4 +739,17 @@ extern "C" int pgp_fitc_predict(pgp_fitc* f, const double* Xs, int64_t ms, doubl
     cudaFree(dzs);
     cudaFree(dout);
     return rc;
+}
+
+extern "C" int pgp_fitc_predict(pgp_fitc* f, const double* Xs, int64_t ms, double* mu, double* s2) {
+    if (!f) return PGP_E_ARG;
+    if (!Xs || !mu || !s2 || ms < 0) return f->ctx->fail(PGP_E_ARG, "null or negative argument");
+    return fitc_predict_impl(f, Xs, ms, mu, s2, nullptr, nullptr);
+}
+
+extern "C" int pgp_fitc_predict_grad(pgp_fitc* f, const double* Xs, int64_t ms, double* mu, double* s2, double* dmu,
+                                     double* ds2) {
+    if (!f) return PGP_E_ARG;
+    if (!Xs || !mu || !s2 || !dmu || !ds2 || ms < 0) return f->ctx->fail(PGP_E_ARG, "null or negative argument");
+    return fitc_predict_impl(f, Xs, ms, mu, s2, dmu, ds2);
 }

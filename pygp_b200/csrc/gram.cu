@@ -102,6 +102,14 @@ __device__ __forceinline__ double slot_value(const PartVal& v, int kind, double 
     return kind == SLOT_SF ? v.g_sf : kind == SLOT_ISO ? v.g_iso : kind == SLOT_E0 ? v.e0 : v.ardw * dk2;
 }
 
+// d k_leaf / d x1_k  (se.py:76-83, matern.py:100-111, periodic.py:84-94, rq.py:95-108):
+// -w (z1k - z2k) / ell_k with the same weight w as the ARD hyper-gradient;
+// Periodic: -2 pi / (ell^2 p) K sin(2 pi (x1 - x2) / p)
+__device__ __forceinline__ double leaf_gradx(const DevPart& p, const PartVal& v, double sdiff, double ellk) {
+    if (p.type == PGP_PERIODIC) return -2.0 * kPi / (p.p0 * p.p0) / p.p1 * v.K * sin(2.0 * sdiff * kPi / p.p1);
+    return -v.ardw * sdiff / ellk;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------
@@ -138,8 +146,10 @@ int launch_scale(pgp_ctx* ctx, const DevSpec* d_spec, const double* d_X, int64_t
 //   PTYPE >= 0: single leaf of that type (register micro-tile fast path)
 //   PTYPE <  0: composite, one entry at a time through the tree
 // ---------------------------------------------------------------------------
-template <int PTYPE, bool GRAD1>
+template <int PTYPE, int MODE>
 __global__ void __launch_bounds__(kThreads) gram_kernel(GramArgs a) {
+    constexpr bool GRAD1 = MODE == 1;
+    constexpr bool GRADX = MODE == 2;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     DevSpecHdr* S = reinterpret_cast<DevSpecHdr*>(smem_raw);
     double* Zs1 = reinterpret_cast<double*>(smem_raw + ((sizeof(DevSpecHdr) + 15) / 16) * 16);
@@ -164,6 +174,7 @@ __global__ void __launch_bounds__(kThreads) gram_kernel(GramArgs a) {
     int gpart = 0, gkind = 0, gdim = 0;
     if (GRAD1) classify_hyper(*S, a.hidx, &gpart, &gkind, &gdim);
     const double noise = a.add_noise ? S->sn2 : 0.0;
+    const int xdim = a.xdim;
 
     double res[4][4];
     if (PTYPE >= 0) {
@@ -194,8 +205,11 @@ __global__ void __launch_bounds__(kThreads) gram_kernel(GramArgs a) {
 #pragma unroll
             for (int y = 0; y < 4; ++y) {
                 PartVal v;
-                part_eval<GRAD1>(part, D[x][y], v);
-                if (GRAD1) {
+                part_eval<GRAD1 || GRADX>(part, D[x][y], v);
+                if (GRADX) {
+                    double sd = Zs1[xdim * kTile + t.row(x)] - Zs2[xdim * kTile + t.col(y)];
+                    res[x][y] = leaf_gradx(part, v, sd, a.spec[b].ell[0][xdim]);
+                } else if (GRAD1) {
                     double dk2 = 0.0;
                     if (gkind == SLOT_ARD) {
                         double df = Zs1[gdim * kTile + t.row(x)] - Zs2[gdim * kTile + t.col(y)];
@@ -213,7 +227,19 @@ __global__ void __launch_bounds__(kThreads) gram_kernel(GramArgs a) {
             for (int y = 0; y < 4; ++y) {
                 const double* z1 = Zs1 + t.row(x);
                 const double* z2 = Zs2 + t.col(y);
-                if (GRAD1) {
+                if (GRADX) {
+                    PartVal pv[kMaxParts];
+                    double val[kMaxNodes], adj[kMaxNodes];
+                    eval_parts<true>(*S, z1, z2, pv);
+                    tree_forward(*S, pv, val);
+                    tree_backward(*S, val, adj);
+                    double g = 0.0;
+                    for (int p = 0; p < n_parts; ++p) {
+                        double sd = z1[(p * ndim + xdim) * kTile] - z2[(p * ndim + xdim) * kTile];
+                        g += adj[S->leaf_node[p]] * leaf_gradx(S->parts[p], pv[p], sd, a.spec[b].ell[p][xdim]);
+                    }
+                    res[x][y] = g;
+                } else if (GRAD1) {
                     res[x][y] = composite_grad1(*S, z1, z2, gpart, gkind, gdim);
                 } else {
                     PartVal pv[kMaxParts];
@@ -224,7 +250,8 @@ __global__ void __launch_bounds__(kThreads) gram_kernel(GramArgs a) {
             }
     }
 
-    const bool vec_ok = ((a.ldo & 1) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    const int64_t os = a.ostride;
+    const bool vec_ok = os == 1 && ((a.ldo & 1) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
 #pragma unroll
     for (int x = 0; x < 4; ++x) {
         int64_t gi = i0 + t.row(x);
@@ -235,12 +262,12 @@ __global__ void __launch_bounds__(kThreads) gram_kernel(GramArgs a) {
             double v0 = res[x][2 * h], v1 = res[x][2 * h + 1];
             if (gi == gj) v0 += noise;
             if (gi == gj + 1) v1 += noise;
-            double* dst = out + gi * a.ldo + gj;
+            double* dst = out + gi * a.ldo + gj * os;
             if (vec_ok && gj + 1 < a.n2) {
                 *reinterpret_cast<double2*>(dst) = make_double2(v0, v1);
             } else {
                 if (gj < a.n2) dst[0] = v0;
-                if (gj + 1 < a.n2) dst[1] = v1;
+                if (gj + 1 < a.n2) dst[os] = v1;
             }
         }
     }
@@ -278,9 +305,9 @@ __global__ void __launch_bounds__(kThreads) gram_kernel(GramArgs a) {
     }
 }
 
-template <int PTYPE, bool GRAD1>
+template <int PTYPE, int MODE>
 static int launch_gram_t(pgp_ctx* ctx, const GramArgs& a, size_t smem) {
-    auto kern = gram_kernel<PTYPE, GRAD1>;
+    auto kern = gram_kernel<PTYPE, MODE>;
     PGP_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int64_t t1 = ceil_div(a.n1, kTile), t2 = ceil_div(a.n2, kTile);
     dim3 grid;
@@ -306,11 +333,15 @@ int launch_gram(pgp_ctx* ctx, const GramArgs& a) {
         return ctx->fail(PGP_E_ARG, "gram: n_parts * ndim > 192 exceeds the shared-memory tile");
     size_t smem = ((sizeof(DevSpecHdr) + 15) / 16) * 16 + 2ull * a.n_parts * a.ndim * kTile * sizeof(double);
     if (a.symmetric) smem += (size_t)kTile * (kTile + 1) * sizeof(double);
-    const bool g = a.hidx >= 0;
+    const int mode = a.xdim >= 0 ? 2 : (a.hidx >= 0 ? 1 : 0);
+    if (mode == 2 && (a.xdim >= a.ndim || a.symmetric || a.lower_only))
+        return ctx->fail(PGP_E_ARG, "gram: bad input-gradient request");
+    if (a.ostride != 1 && a.symmetric) return ctx->fail(PGP_E_ARG, "gram: strided output cannot be mirrored");
     int st = a.n_parts == 1 ? a.single_type : -1;
-#define PGP_GRAM_CASE(T)                                             \
-    case T:                                                          \
-        return g ? launch_gram_t<T, true>(ctx, a, smem) : launch_gram_t<T, false>(ctx, a, smem);
+#define PGP_GRAM_CASE(T)                                                                  \
+    case T:                                                                               \
+        return mode == 2 ? launch_gram_t<T, 2>(ctx, a, smem)                              \
+                         : (mode == 1 ? launch_gram_t<T, 1>(ctx, a, smem) : launch_gram_t<T, 0>(ctx, a, smem));
     switch (st) {
         PGP_GRAM_CASE(PGP_SE)
         PGP_GRAM_CASE(PGP_MATERN1)
@@ -319,7 +350,8 @@ int launch_gram(pgp_ctx* ctx, const GramArgs& a) {
         PGP_GRAM_CASE(PGP_PERIODIC)
         PGP_GRAM_CASE(PGP_RQ)
         default:
-            return g ? launch_gram_t<-1, true>(ctx, a, smem) : launch_gram_t<-1, false>(ctx, a, smem);
+            return mode == 2 ? launch_gram_t<-1, 2>(ctx, a, smem)
+                             : (mode == 1 ? launch_gram_t<-1, 1>(ctx, a, smem) : launch_gram_t<-1, 0>(ctx, a, smem));
     }
 #undef PGP_GRAM_CASE
 }

@@ -118,15 +118,19 @@ class ExactGP(GP):
         return (lZ.value, dlZ) if grad else lZ.value
 
     def _marg_posterior(self, X, grad=False):
-        if grad:
-            raise NotImplementedError('posterior input-gradients are outside the B200 hot path (next: N1)')
         X = _lib.as_f64(X, 2)
         if self._X is None:
-            # prior: mean and k(x, x)   (exact.py:83-86)
-            return np.full(X.shape[0], self._mean), self._kernel.dget(X)
+            # prior: mean and k(x, x); constant mean and stationary kernel -> zero gradients (exact.py:83-104)
+            out = (np.full(X.shape[0], self._mean), self._kernel.dget(X))
+            return out + (np.zeros_like(X), np.zeros_like(X)) if grad else out
         if X.shape[1] != self._kernel.ndim:
             raise ValueError('test inputs have the wrong number of columns')
         mu, s2 = np.empty(len(X)), np.empty(len(X))
-        _lib.check(self._dev.ctx, _lib.lib().pgp_exact_predict(
-            self._dev.handle, _lib.ptr(X), len(X), _lib.ptr(mu), _lib.ptr(s2)))
-        return mu, s2
+        if not grad:
+            _lib.check(self._dev.ctx, _lib.lib().pgp_exact_predict(
+                self._dev.handle, _lib.ptr(X), len(X), _lib.ptr(mu), _lib.ptr(s2)))
+            return mu, s2
+        dmu, ds2 = np.empty(X.shape), np.empty(X.shape)
+        _lib.check(self._dev.ctx, _lib.lib().pgp_exact_predict_grad(
+            self._dev.handle, _lib.ptr(X), len(X), _lib.ptr(mu), _lib.ptr(s2), _lib.ptr(dmu), _lib.ptr(ds2)))
+        return mu, s2, dmu, ds2

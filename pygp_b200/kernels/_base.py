@@ -114,16 +114,26 @@ class RealKernel(Kernel):
     def transform(self, X):
         return np.array(X, ndmin=2, dtype=float)
 
-    # Input-gradients and spectral sampling are outside the accelerated path
-    # (SURVEY.md section 8f, row N1): not provided in this round.
+    # Input-gradients: on the device as well.
+    def _gradx(self, X1, X2, wrt_y):
+        X1, X2 = self._inputs(X1, X2)
+        n1, n2 = len(X1), (len(X1) if X2 is None else len(X2))
+        out = np.empty((n1, n2, self.ndim))
+        ctx, L, hyp, spec = _lib.context(), _lib.lib(), self._hyp(), self._spec()
+        _lib.check(ctx, L.pgp_gram_gradx(ctx.handle, spec, _lib.ptr(hyp), _lib.ptr(X1), n1,
+                                         None if X2 is None else _lib.ptr(X2), n2, wrt_y, _lib.ptr(out)))
+        return out
+
     def gradx(self, X1, X2=None):
-        raise NotImplementedError('gradx is outside the B200 hot path (next: N1)')
+        """d k(x1, x2) / d x1: (n1, n2, ndim)."""
+        return self._gradx(X1, X2, 0)
 
     def grady(self, X1, X2=None):
-        raise NotImplementedError('grady is outside the B200 hot path (next: N1)')
+        """d k(x1, x2) / d x2: (n1, n2, ndim)."""
+        return self._gradx(X1, X2, 1)
 
     def gradxy(self, X1, X2=None):
-        raise NotImplementedError('gradxy is outside the B200 hot path (next: N1)')
+        raise NotImplementedError('gradxy is outside the B200 hot path (SE-only in the reference; next: N1)')
 
     def sample_spectrum(self, N, rng=None):
         raise NotImplementedError('sample_spectrum is outside the B200 hot path')

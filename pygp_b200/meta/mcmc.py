@@ -86,7 +86,14 @@ class MCMC(object):
     def posterior(self, X, grad=False):
         """Moment-matched mixture over the sampled models (mcmc.py:75-93)."""
         if grad:
-            raise NotImplementedError('posterior input-gradients are outside the B200 hot path (next: N1)')
+            parts = [m.posterior(X, True) for m in self._samples]
+            mu_, s2_, dmu_, ds2_ = (np.array([p[i] for p in parts]) for i in range(4))
+            mu = np.mean(mu_, axis=0)
+            s2 = np.mean(s2_ + (mu_ - mu)**2, axis=0)
+            dmu = np.mean(dmu_, axis=0)
+            Dmu = dmu_ - dmu
+            ds2 = np.mean(ds2_ + 2*mu_[:, :, None]*Dmu - 2*mu[None, :, None]*Dmu, axis=0)
+            return mu, s2, dmu, ds2
         from .. import sharding
         model = self._model
         if (sharding.world()[1] > 1 and isinstance(model, ExactGP) and model.ndata > 0

@@ -247,3 +247,30 @@ def test_full_size_properties_n32768():
     gp.set_hyper(h - eps*v)
     lm = gp.loglikelihood()
     nt.assert_allclose((lp - lm)/(2*eps), dlZ @ v, rtol=2e-6)
+
+
+@pytest.mark.parametrize('name', EXACT)
+def test_posterior_input_gradients(name, golden):
+    """posterior(X, grad=True) (exact.py:99-116, reference tests/test_inference.py:159-169)
+    against the reference's outputs, and a second test-point set against the oracle."""
+    g = golden['gp']
+    gp, Xs = build(name)
+    mu, s2, dmu, ds2 = gp.posterior(Xs, grad=True)
+    assert_pred_close(mu, s2, g[name + '/mu'], g[name + '/s2'])
+    sc = max(1.0, np.abs(g[name + '/dmu']).max())
+    nt.assert_allclose(dmu, g[name + '/dmu'], rtol=1e-9, atol=1e-10*sc)
+    sc = max(1.0, np.abs(g[name + '/ds2']).max())
+    nt.assert_allclose(ds2, g[name + '/ds2'], rtol=1e-8, atol=1e-10*sc)
+    spec, N, d, _ = GP_CASES[name]
+    X, y, _, _ = gp_inputs(N, d)
+    ogp = OExactGP(GP_SN, make_kernel(spec), GP_MEAN)
+    ogp.add_data(X, y)
+    Xt = np.random.RandomState(8).rand(77, d)             # crosses the 64-row tile; d + 1 rows per point
+    out = gp.posterior(Xt, grad=True)
+    ref = ogp.posterior(Xt, grad=True)
+    for a, b, tol in zip(out, ref, (1e-10, 1e-10, 1e-9, 1e-8)):
+        nt.assert_allclose(a, b, rtol=tol, atol=tol*max(1.0, np.abs(b).max()))
+    # before any data: zero gradients (exact.py:100-104)
+    gp.reset()
+    out = gp.posterior(Xt[:5], grad=True)
+    assert np.all(out[2] == 0) and np.all(out[3] == 0)

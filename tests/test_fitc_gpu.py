@@ -152,3 +152,14 @@ def test_not_positive_definite_raises():
     gp = pygp.inference.FITC(pygp.likelihoods.Gaussian(1e-9), pygp.kernels.SE(1.0, 5.0, ndim=1), 0.0, U)
     with pytest.raises(np.linalg.LinAlgError):
         gp.add_data(X, y)
+
+
+@pytest.mark.parametrize('name', FITC_CASES)
+def test_posterior_input_gradients(name, golden):
+    """FITC.posterior(X, grad=True) (fitc.py:144-165) against the reference's outputs."""
+    g = golden['gp']
+    gp, Xs = build(name)
+    mu, s2, dmu, ds2 = gp.posterior(Xs, grad=True)
+    assert_pred_close(mu, s2, g[name + '/mu'], g[name + '/s2'])
+    nt.assert_allclose(dmu, g[name + '/dmu'], rtol=1e-8, atol=1e-9*max(1.0, np.abs(g[name + '/dmu']).max()))
+    nt.assert_allclose(ds2, g[name + '/ds2'], rtol=1e-7, atol=1e-9*max(1.0, np.abs(g[name + '/ds2']).max()))

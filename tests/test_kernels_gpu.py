@@ -71,3 +71,33 @@ def test_empty_and_errors():
     assert k.dget(np.zeros((0, 2))).shape == (0,)
     with pytest.raises(ValueError):
         k.get(np.zeros((3, 3)))
+
+
+@pytest.mark.parametrize('name', sorted(KERNEL_CASES))
+def test_input_gradients_vs_golden(name, golden):
+    """Kernel.gradx / grady (reference tests/test_kernels.py:97-128) against the
+    reference's own outputs; grady == -gradx, and gradx(X) == gradx(X, X)."""
+    g = golden['kernels']
+    k = product_kernel(KERNEL_CASES[name])
+    x1, x2 = kernel_inputs(k.ndim)
+    nt.assert_allclose(k.gradx(x1, x2), g[name + '/gradx12'], rtol=1e-12, atol=1e-13)
+    nt.assert_allclose(k.grady(x1, x2), g[name + '/grady12'], rtol=1e-12, atol=1e-13)
+    nt.assert_allclose(k.gradx(x1), g[name + '/gradx11'], rtol=1e-12, atol=1e-13)
+    with pytest.raises(NotImplementedError):
+        k.gradxy(x1, x2)
+
+
+@pytest.mark.parametrize('name', ['matern3_ard', 'maunaloa', 'prod_mixed', 'periodic'])
+def test_input_gradients_tiles_vs_oracle(name):
+    """ragged sizes crossing the 64 x 64 tile, and the finite-difference check
+    of the reference's test_gradx."""
+    import scipy.optimize as spop
+    spec = KERNEL_CASES[name]
+    k, ok = product_kernel(spec), make_kernel(spec)
+    rng = np.random.RandomState(4)
+    x1, x2 = rng.rand(70, k.ndim), rng.rand(131, k.ndim)
+    G = k.gradx(x1, x2)
+    nt.assert_allclose(G, ok.gradx(x1, x2), rtol=1e-12, atol=1e-13)
+    f = lambda a, b: ok.get(a[None], b[None])[0, 0]
+    G2 = np.array([spop.approx_fprime(a, f, 1e-8, b) for a in x1[:3] for b in x2[:4]]).reshape(3, 4, -1)
+    nt.assert_allclose(G[:3, :4], G2, rtol=1e-5, atol=1e-5)

@@ -173,3 +173,24 @@ def test_sharding_single_rank_uses_device_path():
     m0, v0 = gp.posterior(Xs)
     nt.assert_array_equal(m2, m0)
     nt.assert_array_equal(v2, v0)
+
+
+def test_mcmc_posterior_input_gradients():
+    """meta.MCMC.posterior(X, grad=True) (mcmc.py:84-93; reference tests/test_meta.py:44-54):
+    finite differences of the mixture mean and variance."""
+    import scipy.optimize as spop
+    import pygp_b200 as pygp
+    rng = np.random.RandomState(1)
+    X = rng.rand(10, 2)
+    y = rng.rand(10)
+    gp = pygp.BasicGP(0.5, 1, [1, 1])
+    gp.add_data(X, y)
+    priors = {'sn': pygp.priors.Uniform(0.01, 1.0), 'sf': pygp.priors.Uniform(0.01, 5.0),
+              'ell': pygp.priors.Uniform([0.01, 0.01], [1.0, 1.0]), 'mu': pygp.priors.Uniform(-2, 2)}
+    model = pygp.meta.MCMC(gp, priors, n=6, burn=0, rng=0)
+    Xq = rng.rand(4, 2)
+    mu, s2, dmu, ds2 = model.posterior(Xq, grad=True)
+    f_mu = lambda x: model.posterior(x[None])[0][0]
+    f_s2 = lambda x: model.posterior(x[None])[1][0]
+    nt.assert_allclose(dmu, [spop.approx_fprime(x, f_mu, 1e-7) for x in Xq], rtol=1e-5, atol=1e-5)
+    nt.assert_allclose(ds2, [spop.approx_fprime(x, f_s2, 1e-7) for x in Xq], rtol=1e-4, atol=1e-5)

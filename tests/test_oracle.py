@@ -24,6 +24,9 @@ def test_kernel_vs_golden(name, golden):
     nt.assert_allclose(k.get(x1), g[name + '/get11'], rtol=1e-13, atol=1e-15)
     nt.assert_allclose(np.array(k.grad(x1, x2)), g[name + '/grad12'], rtol=1e-12, atol=1e-14)
     nt.assert_allclose(np.array(k.grad(x1)), g[name + '/grad11'], rtol=1e-12, atol=1e-14)
+    nt.assert_allclose(k.gradx(x1, x2), g[name + '/gradx12'], rtol=1e-12, atol=1e-14)
+    nt.assert_allclose(k.grady(x1, x2), g[name + '/grady12'], rtol=1e-12, atol=1e-14)
+    nt.assert_allclose(k.gradx(x1), g[name + '/gradx11'], rtol=1e-12, atol=1e-14)
     nt.assert_allclose(k.dget(x1), g[name + '/dget'], rtol=1e-15)
     nt.assert_allclose(np.array(k.dgrad(x1)), g[name + '/dgrad'], rtol=1e-15)
     k2 = k.copy_with(g[name + '/hyper2'])
@@ -61,7 +64,9 @@ def test_gp_vs_golden(name, golden):
     g = golden['gp']
     gp, Xs = _build(name)
     lZ, dlZ = gp.loglikelihood(True)
-    mu, s2 = gp.posterior(Xs)
+    mu, s2, dmu, ds2 = gp.posterior(Xs, grad=True)
+    nt.assert_allclose(dmu, g[name + '/dmu'], rtol=1e-10, atol=1e-12)
+    nt.assert_allclose(ds2, g[name + '/ds2'], rtol=1e-10, atol=1e-12)
     nt.assert_allclose(lZ, g[name + '/lZ'], rtol=1e-12)
     nt.assert_allclose(dlZ, g[name + '/dlZ'], rtol=1e-10, atol=1e-10)
     nt.assert_allclose(mu, g[name + '/mu'], rtol=1e-12)
