@@ -127,6 +127,11 @@ int pgp_exact_create(pgp_ctx* ctx, const pgp_kernel_spec* spec,
 /* GP.add_data later calls (_base.py:132-141, full-update branch): append rows;
  * the caller follows with pgp_exact_update. */
 int pgp_exact_append(pgp_model* m, const double* X, const double* y, int64_t n_new);
+/* ExactGP._updateinc (exact.py:57-62, mwhutils.linalg.chol_update): append rows
+ * AND grow the existing factor by them (O(n^2 m) instead of O(n^3)); needs a
+ * factored model; hypers unchanged.  Returns info > 0 if the grown matrix is not
+ * positive definite. */
+int pgp_exact_append_inc(pgp_model* m, const double* X, const double* y, int64_t n_new);
 /* Parameterized.copy (utils/models.py:47-55): deep copy of the device state. */
 int pgp_model_clone(const pgp_model* m, pgp_model** out);
 void pgp_model_destroy(pgp_model* m);

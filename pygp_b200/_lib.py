@@ -67,6 +67,7 @@ SIGNATURES = {
     'pgp_gram_dev': (C.c_int, [_vp, _sp, _dp, _vp, _i64, _vp, _i64, _vp]),
     'pgp_exact_create': (C.c_int, [_vp, _sp, _dp, _dp, _i64, C.POINTER(_vp)]),
     'pgp_exact_append': (C.c_int, [_vp, _dp, _dp, _i64]),
+    'pgp_exact_append_inc': (C.c_int, [_vp, _dp, _dp, _i64]),
     'pgp_model_clone': (C.c_int, [_vp, C.POINTER(_vp)]),
     'pgp_model_destroy': (None, [_vp]),
     'pgp_model_ndata': (_i64, [_vp]),

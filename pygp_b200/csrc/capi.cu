@@ -478,6 +478,119 @@ extern "C" int pgp_exact_append(pgp_model* m, const double* X, const double* y, 
     return model_alloc_work(m);
 }
 
+// ExactGP._updateinc (exact.py:57-62; the un-vendored mwhutils.linalg.chol_update):
+// grow the factor by the new rows instead of refactoring,
+//     L' = [L 0; S^T L22],  S^T = k(Xnew, X) L^-T,  L22 = chol(Kss + sn2 I - S^T S),
+//     a' = [a; L22^-1 (r_new - S^T a)]
+// i.e. one right-solve of the m new rows (O(n^2 m)), one GEMM and an m x m
+// factorisation (done in an aligned scratch block with the residual riding along).
+extern "C" int pgp_exact_append_inc(pgp_model* m, const double* X, const double* y, int64_t n_new) {
+    if (!m) return PGP_E_ARG;
+    pgp_ctx* ctx = m->ctx;
+    if (!X || !y || n_new <= 0) return ctx->fail(PGP_E_ARG, "null argument or n_new <= 0");
+    if (!m->factored) return ctx->fail(PGP_E_STATE, "incremental update before a successful update");
+    PGP_TRY(set_device(ctx));
+    const int d = m->ndim, np = m->spec.n_parts;
+    const int64_t n_old = m->n, n = n_old + n_new, ld_old = m->ld, ld = lead_dim(n);
+    cudaStream_t s = ctx->stream;
+    // new buffers first; the model is only touched once everything is in place
+    double *nF = nullptr, *nZ = nullptr, *nAlpha = nullptr;
+    PoolBuf T;                                   // (n_new + 1, ldt) scratch block
+    const int64_t ldt = lead_dim(n_new);
+    PGP_TRY(T.get(ctx, (size_t)(n_new + 1) * ldt));
+    PGP_TRY(pool_alloc(ctx, &nF, (size_t)(n + 1) * ld));
+    int rc = pool_alloc(ctx, &nZ, (size_t)np * n * d);
+    if (!rc) rc = dev_alloc(ctx, &nAlpha, (size_t)n);
+    auto bail = [&](int code) {
+        cudaStreamSynchronize(s);
+        pool_free(ctx, nF, (size_t)(n + 1) * ld);
+        pool_free(ctx, nZ, (size_t)np * n * d);
+        cudaFree(nAlpha);
+        return code;
+    };
+    if (rc) return bail(rc);
+    // old factor and a into the wider buffer
+    cudaError_t e = cudaMemcpy2DAsync(nF, ld * 8, m->d_F, ld_old * 8, n_old * 8, n_old, cudaMemcpyDeviceToDevice, s);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(nF + n * ld, m->d_F + n_old * ld_old, n_old * 8, cudaMemcpyDeviceToDevice, s);
+    if (e != cudaSuccess) return bail(ctx->cuda_fail(e, "factor copy", __FILE__, __LINE__));
+    if ((rc = model_upload(m, X, y, n_old, n_new))) return bail(rc);           // X, y grow (m->n = n now)
+    // from here on a failure must leave the model consistent for n rows (unfactored): the caller
+    // falls back to a full pgp_exact_update
+    auto bail_grown = [&](int code) {
+        bail(code);
+        m->n = n_old;
+        model_free_work(m);
+        m->n = n;
+        int rc2 = model_alloc_work(m);
+        return rc2 ? rc2 : code;
+    };
+    if ((rc = launch_scale(ctx, m->d_spec, m->d_X, n, d, np, nZ, 1))) return bail_grown(rc);
+    const int st = single_type(&m->spec);
+    GramArgs g;                                   // new rows: k(Xnew, Xold)
+    g.spec = m->d_spec;
+    g.Z1 = nZ + n_old * d; g.zs1 = n * d; g.n1 = n_new;
+    g.Z2 = nZ; g.zs2 = n * d; g.n2 = n_old;
+    g.ndim = d; g.n_parts = np;
+    g.out = nF + n_old * ld; g.ldo = ld;
+    g.single_type = st;
+    if ((rc = launch_gram(ctx, g))) return bail_grown(rc);
+    Mat F, Bn, Tm;
+    F.p = nF; F.ld = ld;
+    Bn.p = nF + n_old * ld; Bn.ld = ld;
+    Tm.p = T.p; Tm.ld = ldt;
+    if ((rc = trsm_right_lt(ctx, Bn, n_new, F, n_old))) return bail_grown(rc);      // S^T = k(Xnew, X) L^-T
+    GramArgs gs;                                  // T = Kss + sn2 I (lower), row n_new = r_new
+    gs.spec = m->d_spec;
+    gs.Z1 = gs.Z2 = nZ + n_old * d; gs.zs1 = gs.zs2 = n * d; gs.n1 = gs.n2 = n_new;
+    gs.ndim = d; gs.n_parts = np;
+    gs.out = T.p; gs.ldo = ldt;
+    gs.lower_only = 1; gs.add_noise = 1;
+    gs.single_type = st;
+    if ((rc = launch_gram(ctx, gs))) return bail_grown(rc);
+    if ((rc = launch_set_residual_at(ctx, Tm, n_new, n_new, m->d_y, n_old, m->d_spec))) return bail_grown(rc);
+    {   // T -= [S^T; a] S   (rows: the new rows and the residual row; contraction over the old columns)
+        GemmArgs ga;
+        ga.A = nF + n_old * ld; ga.lda = ld;
+        ga.B = nF + n_old * ld; ga.ldb = ld;
+        ga.C = T.p; ga.ldc = ldt;
+        ga.M = n_new + 1; ga.N = n_new; ga.K = n_old;
+        ga.alpha = -1.0; ga.beta = 1.0;
+        ga.tri = 1;
+        ga.splitk = 0;
+        if ((rc = launch_gemm(ctx, ga))) return bail_grown(rc);
+    }
+    if ((rc = cudaMemsetAsync(m->d_info, 0, sizeof(int), s) == cudaSuccess ? 0 : PGP_E_CUDA)) return bail_grown(rc);
+    if ((rc = potrf_lower(ctx, Tm, n_new, 1, m->d_info))) return bail_grown(rc);
+    e = cudaMemcpy2DAsync(nF + n_old * ld + n_old, ld * 8, T.p, ldt * 8, n_new * 8, n_new + 1, cudaMemcpyDeviceToDevice, s);
+    if (e != cudaSuccess) return bail_grown(ctx->cuda_fail(e, "tail copy", __FILE__, __LINE__));
+    if ((rc = launch_loglik(ctx, F, n, m->d_res))) return bail_grown(rc);
+    double* hp = ctx->h_pin;
+    e = cudaMemcpyAsync(hp, m->d_res, sizeof(double), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(hp + 1, m->d_info, sizeof(int), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) return bail_grown(ctx->cuda_fail(e, "incremental update", __FILE__, __LINE__));
+    // swap the work buffers in (model_free_work reads m->n and m->ld for the pool sizes)
+    const int info = *reinterpret_cast<int*>(hp + 1);
+    m->n = n_old;
+    model_free_work(m);
+    m->n = n;
+    m->ld = ld;
+    m->d_F = nF;
+    m->d_Z = nZ;
+    m->d_alpha = nAlpha;
+    m->lZ = hp[0];
+    m->info = info ? (int)n_old + info : 0;
+    if (info) {
+        char buf[160];
+        snprintf(buf, sizeof buf, "%d-th leading minor of the array is not positive definite", m->info);
+        ctx->err = buf;
+        return m->info;
+    }
+    m->factored = true;
+    return 0;
+}
+
 extern "C" void pgp_model_destroy(pgp_model* m) {
     if (!m) return;
     cudaSetDevice(m->ctx->device);

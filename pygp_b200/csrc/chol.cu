@@ -519,17 +519,27 @@ int launch_gemv_upper(pgp_ctx* ctx, const double* G, int64_t ld, const double* a
 }
 
 __global__ void set_residual_kernel(double* F, int64_t ld, int64_t bstride, int64_t n, const double* y,
-                                    const DevSpec* spec) {
+                                    const DevSpec* spec, int64_t row_index, int64_t c0) {
     const double mean = spec[blockIdx.y].h.mean;
-    double* row = F + (int64_t)blockIdx.y * bstride + n * ld;
+    double* row = F + (int64_t)blockIdx.y * bstride + row_index * ld;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        row[i] = y[i] - mean;
+        row[i] = y[c0 + i] - mean;
 }
 
 int launch_set_residual(pgp_ctx* ctx, const Mat& F, int64_t n, const double* d_y, const DevSpec* d_spec) {
     int blocks = (int)std::min<int64_t>(ceil_div(n, 256), 148);
     Launch L(ctx, PC_OTHER, 16.0 * n * F.batch);
-    set_residual_kernel<<<dim3(blocks, F.batch), 256, 0, ctx->stream>>>(F.p, F.ld, F.bstride, n, d_y, d_spec);
+    set_residual_kernel<<<dim3(blocks, F.batch), 256, 0, ctx->stream>>>(F.p, F.ld, F.bstride, n, d_y, d_spec, n, 0);
+    return check_launch(ctx, "set_residual_kernel");
+}
+
+// row `row_index` of T, columns [0, cnt) <- y[c0 + i] - mean   (the new data's residual, exact.py:61)
+int launch_set_residual_at(pgp_ctx* ctx, const Mat& T, int64_t row_index, int64_t cnt, const double* d_y, int64_t c0,
+                           const DevSpec* d_spec) {
+    if (cnt <= 0) return 0;
+    int blocks = (int)std::min<int64_t>(ceil_div(cnt, 256), 148);
+    Launch L(ctx, PC_OTHER, 16.0 * cnt);
+    set_residual_kernel<<<dim3(blocks, 1), 256, 0, ctx->stream>>>(T.p, T.ld, 0, cnt, d_y, d_spec, row_index, c0);
     return check_launch(ctx, "set_residual_kernel");
 }
 

@@ -51,6 +51,8 @@ int launch_gemv_upper(pgp_ctx* ctx, const double* G, int64_t ld, const double* a
 // F[n][j] = y[j] - mean(spec[b])   (exact.py:53)
 struct DevSpec;
 int launch_set_residual(pgp_ctx* ctx, const Mat& F, int64_t n, const double* d_y, const DevSpec* d_spec);
+int launch_set_residual_at(pgp_ctx* ctx, const Mat& T, int64_t row_index, int64_t cnt, const double* d_y, int64_t c0,
+                           const DevSpec* d_spec);
 
 // mu[i] = mean + <B[i], a>, s2[i] = kdiag - |B[i]|^2 (exact.py:93-94); B (rows, ld)
 int launch_predict_reduce(pgp_ctx* ctx, const double* B, int64_t ld, int64_t rows, int64_t n,

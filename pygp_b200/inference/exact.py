@@ -94,6 +94,24 @@ class ExactGP(GP):
         hyp = _lib.as_f64(self.get_hyper())
         _lib.check(self._dev.ctx, L.pgp_exact_update(self._dev.handle, _lib.ptr(hyp)))
 
+    def _updateinc(self, X, y):
+        """Grow the factor by the new rows (exact.py:57-62): O(n^2 m) on the device."""
+        if self._dev is None or self._ndev != self.ndata:
+            raise NotImplementedError
+        cfg = self.distributed
+        if cfg and self.ndata + len(X) >= cfg.get('min_n', 32768):
+            raise NotImplementedError          # the distributed path refactors
+        Xn, yn = _lib.as_f64(X, 2), _lib.as_f64(y, 1)
+        try:
+            _lib.check(self._dev.ctx, _lib.lib().pgp_exact_append_inc(self._dev.handle, _lib.ptr(Xn), _lib.ptr(yn),
+                                                                      len(Xn)))
+        except Exception:
+            # the device copy may already hold the new rows while the host does not:
+            # drop it, the next _update uploads the host's data again
+            self._dev, self._ndev = None, 0
+            raise
+        self._ndev += len(Xn)
+
     def _factor(self):
         n = self.ndata
         R, a = np.empty((n, n)), np.empty(n)

@@ -274,3 +274,59 @@ def test_posterior_input_gradients(name, golden):
     gp.reset()
     out = gp.posterior(Xt[:5], grad=True)
     assert np.all(out[2] == 0) and np.all(out[3] == 0)
+
+
+@pytest.mark.parametrize('spec,d,n0,adds', [
+    (('se', 1.0, [0.5, 0.6]), 2, 10, [10]),                       # reference tests/test_inference.py:65-79
+    (('matern', 1.0, [0.7, 0.8, 0.9], 5), 3, 301, [1, 1, 64, 130, 3]),   # odd sizes, across tile edges
+    (('sum', ('se', 1.0, 0.5), ('periodic', 0.5, 1.0, 0.25)), 1, 1000, [24]),
+])
+def test_incremental_update_equals_full(spec, d, n0, adds):
+    """_updateinc (exact.py:57-62 + mwhutils.linalg.chol_update): growing the
+    factor by new rows == refactoring from scratch (the reference's test_add_data),
+    for lZ, gradient, posterior and the factor itself; and against the oracle."""
+    import pygp_b200 as pygp
+    ntot = n0 + sum(adds)
+    X, y, Xs = synthetic_problem(ntot, d, 40)
+    if spec[0] == 'sum':
+        X, Xs = X*8, Xs*8
+    mk = lambda: pygp.inference.ExactGP(pygp.likelihoods.Gaussian(0.1), product_kernel(spec), 0.1)
+    inc = mk()
+    inc.add_data(X[:n0], y[:n0])
+    lo = n0
+    for a in adds:
+        inc.add_data(X[lo:lo + a], y[lo:lo + a])      # -> _updateinc -> pgp_exact_append_inc
+        lo += a
+    full = mk()
+    full.add_data(X, y)
+    assert inc.ndata == full.ndata == ntot
+    lZ, dlZ = inc.loglikelihood(True)
+    lZ0, dlZ0 = full.loglikelihood(True)
+    nt.assert_allclose(lZ, lZ0, rtol=1e-10)
+    assert_grad_close(dlZ, dlZ0)
+    mu, s2 = inc.posterior(Xs)
+    mu0, s20 = full.posterior(Xs)
+    nt.assert_allclose(mu, mu0, rtol=1e-9, atol=1e-10)
+    nt.assert_allclose(s2, s20, rtol=1e-8, atol=1e-11)
+    nt.assert_allclose(inc._a, full._a, rtol=1e-8, atol=1e-9)
+    ogp = OExactGP(0.1, make_kernel(spec), 0.1)
+    ogp.add_data(X, y)
+    nt.assert_allclose(lZ, ogp.loglikelihood(), rtol=1e-10)
+    # hypers can still be changed afterwards (full refactorisation of the grown data set)
+    inc.set_hyper(inc.get_hyper() + 0.01)
+    full.set_hyper(full.get_hyper() + 0.01)
+    nt.assert_allclose(inc.loglikelihood(), full.loglikelihood(), rtol=1e-12)
+
+
+def test_incremental_update_not_positive_definite():
+    import pygp_b200 as pygp
+    X, y, _ = synthetic_problem(50, 1, 0)
+    gp = pygp.inference.ExactGP(pygp.likelihoods.Gaussian(1e-9), pygp.kernels.SE(1.0, 5.0, ndim=1), 0.0)
+    gp.add_data(X[:3], y[:3])
+    with pytest.raises(np.linalg.LinAlgError):
+        gp.add_data(np.r_[X[:3], X[:3]], np.r_[y[:3], y[:3]])      # duplicates, no noise: singular
+    # the model recovers: a later well-posed call refactors from the host's data
+    gp2 = pygp.inference.ExactGP(pygp.likelihoods.Gaussian(0.1), pygp.kernels.SE(1.0, 0.5, ndim=1), 0.0)
+    gp2.add_data(X[:20], y[:20])
+    gp2.add_data(X[20:], y[20:])
+    assert np.isfinite(gp2.loglikelihood())
