@@ -152,6 +152,14 @@ int pgp_exact_predict_grad(pgp_model* m, const double* Xs, int64_t ms,
 /* device-resident test points / outputs (bench.py `value`, sharded predict) */
 int pgp_exact_predict_dev(pgp_model* m, const double* d_Xs, int64_t ms,
                           double* d_mu, double* d_s2);
+/* ExactGP._full_posterior(X) (exact.py:64-79): mu (ms), Sigma (ms, ms). */
+int pgp_exact_full_posterior(pgp_model* m, const double* Xs, int64_t ms,
+                             double* mu, double* Sigma);
+/* the arithmetic of GP.sample (_base.py:168-172): out (m, n) = mu + Z chol(Sigma + jitter I)
+ * with Z (m, n) standard normals drawn by the caller (the host rng stream stays
+ * the reference's); info > 0 if Sigma + jitter I is not positive definite. */
+int pgp_mvn_transform(pgp_ctx* ctx, const double* mu, const double* Sigma, int64_t n,
+                      double jitter, const double* Z, int64_t m, double* out);
 /* the factor as the reference holds it: upper R (n, n) C-order, a (n) */
 int pgp_exact_get_factor(pgp_model* m, double* R_out, double* a_out);
 
@@ -191,6 +199,9 @@ int pgp_fitc_loglike(pgp_fitc* f, int want_grad, double* lZ, double* dlZ);
 /* FITC._marg_posterior(X, grad=False) (fitc.py:122-142) */
 int pgp_fitc_predict(pgp_fitc* f, const double* Xs, int64_t ms,
                      double* mu, double* s2);
+/* FITC._full_posterior(X) (fitc.py:102-120): mu (ms), Sigma (ms, ms) */
+int pgp_fitc_full_posterior(pgp_fitc* f, const double* Xs, int64_t ms,
+                            double* mu, double* Sigma);
 /* FITC._marg_posterior(X, grad=True) (fitc.py:122-165): dmu, ds2 (ms, ndim) */
 int pgp_fitc_predict_grad(pgp_fitc* f, const double* Xs, int64_t ms,
                           double* mu, double* s2, double* dmu, double* ds2);

@@ -97,6 +97,15 @@ def gp_golden(pygp):
         _close(omu, mu, name + '.mu')
         _close(os2, s2, name + '.s2', 1e-11, 1e-13)
         rec = {'hyper': rgp.get_hyper(), 'lZ': lZ, 'dlZ': dlZ, 'mu': mu, 's2': s2, 'dmu': dmu, 'ds2': ds2}
+        # joint posterior and draws (exact.py:64-79 / fitc.py:102-120, _base.py:143-177)
+        Xj = np.random.RandomState(13).rand(6, d)
+        fmu, fS = rgp._full_posterior(Xj)
+        omu_f, oS = ogp.full_posterior(Xj)
+        _close(omu_f, fmu, name + '.full_mu')
+        _close(oS, fS, name + '.full_Sigma', 1e-10, 1e-13)
+        smp = rgp.sample(Xj, 3, latent=False, rng=5)
+        _close(ogp.sample(Xj, 3, latent=False, rng=5), smp, name + '.sample', 1e-8, 1e-9)
+        rec.update({'Xj': Xj, 'full_mu': fmu, 'full_Sigma': fS, 'sample': smp})
         if not fitc:
             rec['R'] = rgp._R if N <= 64 else rgp._R[:8, :8]
             rec['a'] = rgp._a

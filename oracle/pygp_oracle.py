@@ -462,6 +462,21 @@ def make_kernel(spec):
     raise ValueError('unknown kernel tag %r' % (tag,))
 
 
+def _gp_sample(gp, X, m, latent, rng):
+    # _base.py:143-177 (rstate: int seed -> RandomState(seed)); Gaussian.sample gaussian.py:47-49
+    X = np.array(X, ndmin=2, dtype=float)
+    flatten = (m is None)
+    m = 1 if flatten else m
+    n = len(X)
+    rng = rng if isinstance(rng, np.random.RandomState) else np.random.RandomState(rng)
+    mu, Sigma = gp.full_posterior(X)
+    Sigma += 1e-10 * np.eye(n)
+    f = mu[None] + np.dot(rng.normal(size=(m, n)), sla.cholesky(Sigma))
+    if not latent:
+        f = (f.ravel() + rng.normal(size=f.size, scale=np.sqrt(gp.s2))).reshape(m, n)
+    return f.ravel() if flatten else f
+
+
 # -- ExactGP: pygp/inference/exact.py:20-143, _base.py:47-141 -----------------
 
 class OExactGP(object):
@@ -528,6 +543,21 @@ class OExactGP(object):
             [-0.5*np.sum(Q*dK) for dK in self._kernel.grad(self._X)],
             np.sum(alpha)]
         return lZ, dlZ
+
+    def full_posterior(self, X):
+        # exact.py:64-79
+        X = np.array(X, ndmin=2, dtype=float)
+        mu = np.full(X.shape[0], self._mean)
+        Sigma = self._kernel.get(X)
+        if self._X is not None:
+            K = self._kernel.get(self._X, X)
+            V = sla.solve_triangular(self._R, K, trans=True)
+            mu += np.dot(V.T, self._a)
+            Sigma -= np.dot(V.T, V)
+        return mu, Sigma
+
+    def sample(self, X, m=None, latent=True, rng=None):
+        return _gp_sample(self, X, m, latent, rng)
 
     def posterior(self, X, grad=False):
         # exact.py:81-116, via _base.py:179-186
@@ -613,6 +643,22 @@ class OFITC(object):
         self._a = np.dot(Kux, r)
         self._R = np.dot(sla.cholesky(self._A), self._L)
         self._b = sla.solve_triangular(self._R, self._a, trans=True)
+
+    def full_posterior(self, X):
+        # fitc.py:102-120
+        X = np.array(X, ndmin=2, dtype=float)
+        mu = np.full(X.shape[0], self._mean)
+        Sigma = self._kernel.get(X)
+        if self._X is not None:
+            K = self._kernel.get(self._U, X)
+            LK = sla.solve_triangular(self._L, K, trans=True)
+            RK = sla.solve_triangular(self._R, K, trans=True)
+            mu += np.dot(RK.T, self._b)
+            Sigma += np.dot(RK.T, RK) - np.dot(LK.T, LK)
+        return mu, Sigma
+
+    def sample(self, X, m=None, latent=True, rng=None):
+        return _gp_sample(self, X, m, latent, rng)
 
     def posterior(self, X, grad=False):
         # fitc.py:122-165

@@ -76,6 +76,8 @@ SIGNATURES = {
     'pgp_exact_predict': (C.c_int, [_vp, _dp, _i64, _dp, _dp]),
     'pgp_exact_predict_grad': (C.c_int, [_vp, _dp, _i64, _dp, _dp, _dp, _dp]),
     'pgp_exact_predict_dev': (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
+    'pgp_exact_full_posterior': (C.c_int, [_vp, _dp, _i64, _dp, _dp]),
+    'pgp_mvn_transform': (C.c_int, [_vp, _dp, _dp, _i64, C.c_double, _dp, _i64, _dp]),
     'pgp_exact_get_factor': (C.c_int, [_vp, _dp, _dp]),
     'pgp_exact_factor_buffer': (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_i64)]),
     'pgp_exact_adopt_factor': (C.c_int, [_vp, _dp]),
@@ -86,6 +88,7 @@ SIGNATURES = {
     'pgp_fitc_update': (C.c_int, [_vp, _dp]),
     'pgp_fitc_loglike': (C.c_int, [_vp, C.c_int, _dp, _dp]),
     'pgp_fitc_predict': (C.c_int, [_vp, _dp, _i64, _dp, _dp]),
+    'pgp_fitc_full_posterior': (C.c_int, [_vp, _dp, _i64, _dp, _dp]),
     'pgp_fitc_predict_grad': (C.c_int, [_vp, _dp, _i64, _dp, _dp, _dp, _dp]),
     'pgp_dev_gemm_nt': (C.c_int, [_vp, _i64, _i64, _i64, C.c_double, _vp, _i64, _vp, _i64,
                                   C.c_double, _vp, _i64, C.c_int]),

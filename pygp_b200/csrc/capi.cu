@@ -879,6 +879,112 @@ extern "C" int pgp_exact_predict_dev(pgp_model* m, const double* d_Xs, int64_t m
     return predict_chunked(m, d_Xs, true, ms, d_mu, d_s2, true);
 }
 
+// ExactGP._full_posterior (exact.py:64-79): mu (ms), Sigma (ms, ms) = k(X*, X*) - V^T V with
+// V = R^-T k(X, X*).  One chunk: the solved rows (ms, ld) must fit an 8 GiB buffer.
+extern "C" int pgp_exact_full_posterior(pgp_model* m, const double* Xs, int64_t ms, double* mu, double* Sigma) {
+    if (!m) return PGP_E_ARG;
+    pgp_ctx* ctx = m->ctx;
+    if (!Xs || !mu || !Sigma || ms < 0) return ctx->fail(PGP_E_ARG, "null or negative argument");
+    if (!m->factored) return ctx->fail(PGP_E_STATE, "full posterior before a successful update");
+    if (ms == 0) return 0;
+    PGP_TRY(set_device(ctx));
+    const int64_t n = m->n, ld = m->ld, lds = lead_dim(ms);
+    const int d = m->ndim, np = m->spec.n_parts;
+    if ((double)ms * ld * 8 > 8.0 * (1ull << 30)) return ctx->fail(PGP_E_ARG, "full posterior: too many test points for one chunk");
+    PoolBuf B, S;
+    DevBuf xs, zs, o;
+    PGP_TRY(B.get(ctx, (size_t)ms * ld));
+    PGP_TRY(S.get(ctx, (size_t)ms * lds));
+    PGP_TRY(alloc<double>(ctx, xs, (size_t)ms * d));
+    PGP_TRY(alloc<double>(ctx, zs, (size_t)np * ms * d));
+    PGP_TRY(alloc<double>(ctx, o, (size_t)2 * ms));
+    cudaStream_t st = ctx->stream;
+    PGP_CUDA(ctx, cudaMemcpyAsync(xs.p, Xs, sizeof(double) * ms * d, cudaMemcpyHostToDevice, st));
+    PGP_TRY(launch_scale(ctx, m->d_spec, xs.as<double>(), ms, d, np, zs.as<double>(), 1));
+    GramArgs g;
+    g.spec = m->d_spec;
+    g.Z1 = zs.as<double>(); g.n1 = ms;
+    g.Z2 = m->d_Z; g.n2 = n;
+    g.ndim = d; g.n_parts = np;
+    g.out = B.p; g.ldo = ld;
+    g.single_type = single_type(&m->spec);
+    PGP_TRY(launch_gram(ctx, g));
+    Mat Bm, F;
+    Bm.p = B.p; Bm.ld = ld;
+    F.p = m->d_F; F.ld = ld;
+    PGP_TRY(trsm_right_lt(ctx, Bm, ms, F, n));
+    PGP_TRY(launch_predict_reduce(ctx, B.p, ld, ms, n, m->d_F + n * ld, m->d_spec, o.as<double>(),
+                                  o.as<double>() + ms, 1, 0, 0, 0));
+    GramArgs gs = g;                              // Sigma = k(X*, X*), exactly symmetric
+    gs.Z2 = zs.as<double>(); gs.n2 = ms;
+    gs.out = S.p; gs.ldo = lds;
+    gs.symmetric = 1;
+    PGP_TRY(launch_gram(ctx, gs));
+    GemmArgs ga;                                  // Sigma -= V^T V  (rows of B are the columns of V)
+    ga.A = B.p; ga.lda = ld;
+    ga.B = B.p; ga.ldb = ld;
+    ga.C = S.p; ga.ldc = lds;
+    ga.M = ms; ga.N = ms; ga.K = n;
+    ga.alpha = -1.0; ga.beta = 1.0;
+    ga.splitk = 0;
+    PGP_TRY(launch_gemm(ctx, ga));
+    PGP_CUDA(ctx, cudaMemcpyAsync(mu, o.p, sizeof(double) * ms, cudaMemcpyDeviceToHost, st));
+    PGP_CUDA(ctx, cudaMemcpy2DAsync(Sigma, sizeof(double) * ms, S.p, sizeof(double) * lds, sizeof(double) * ms, ms,
+                                    cudaMemcpyDeviceToHost, st));
+    PGP_CUDA(ctx, cudaStreamSynchronize(st));
+    return 0;
+}
+
+// The arithmetic of GP.sample (_base.py:168-172): f = mu + Z chol(Sigma + jitter I), Z (m, n) standard
+// normals drawn by the caller (so the host rng stream is the reference's), Sigma (n, n).
+extern "C" int pgp_mvn_transform(pgp_ctx* ctx, const double* mu, const double* Sigma, int64_t n, double jitter,
+                                 const double* Z, int64_t m, double* out) {
+    if (!ctx) return PGP_E_ARG;
+    if (!mu || !Sigma || !Z || !out || n < 0 || m < 0) return ctx->fail(PGP_E_ARG, "null or negative argument");
+    if (n == 0 || m == 0) return 0;
+    PGP_TRY(set_device(ctx));
+    const int64_t ld = lead_dim(n);
+    DevBuf S, Zd, O, mud, info;
+    PGP_TRY(alloc<double>(ctx, S, (size_t)n * ld));
+    PGP_TRY(alloc<double>(ctx, Zd, (size_t)m * ld));
+    PGP_TRY(alloc<double>(ctx, O, (size_t)m * ld));
+    PGP_TRY(alloc<double>(ctx, mud, (size_t)n));
+    PGP_TRY(alloc<int>(ctx, info, 1));
+    cudaStream_t st = ctx->stream;
+    PGP_CUDA(ctx, cudaMemsetAsync(info.p, 0, sizeof(int), st));
+    PGP_CUDA(ctx, cudaMemsetAsync(Zd.p, 0, sizeof(double) * m * ld, st));
+    PGP_CUDA(ctx, cudaMemcpy2DAsync(S.p, sizeof(double) * ld, Sigma, sizeof(double) * n, sizeof(double) * n, n,
+                                    cudaMemcpyHostToDevice, st));
+    PGP_CUDA(ctx, cudaMemcpy2DAsync(Zd.p, sizeof(double) * ld, Z, sizeof(double) * n, sizeof(double) * n, m,
+                                    cudaMemcpyHostToDevice, st));
+    PGP_CUDA(ctx, cudaMemcpyAsync(mud.p, mu, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+    PGP_TRY(launch_mvn_prepare(ctx, S.as<double>(), ld, n, jitter));
+    Mat Sm;
+    Sm.p = S.as<double>(); Sm.ld = ld;
+    PGP_TRY(potrf_lower(ctx, Sm, n, 0, info.as<int>()));
+    PGP_TRY(launch_mvn_finish(ctx, S.as<double>(), ld, n, O.as<double>(), mud.as<double>(), m, 0));   // tril(L)
+    // out = Z L^T : out[i][j] = sum_k Z[i][k] L[j][k]   (upper R = L^T of sla.cholesky)
+    GemmArgs ga;
+    ga.A = Zd.as<double>(); ga.lda = ld;
+    ga.B = S.as<double>(); ga.ldb = ld;
+    ga.C = O.as<double>(); ga.ldc = ld;
+    ga.M = m; ga.N = n; ga.K = n;
+    ga.alpha = 1.0; ga.beta = 0.0;
+    PGP_TRY(launch_gemm_nt(ctx, ga));
+    PGP_TRY(launch_mvn_finish(ctx, S.as<double>(), ld, n, O.as<double>(), mud.as<double>(), m, 1));   // += mu
+    int h = 0;
+    PGP_CUDA(ctx, cudaMemcpyAsync(&h, info.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    PGP_CUDA(ctx, cudaMemcpy2DAsync(out, sizeof(double) * n, O.p, sizeof(double) * ld, sizeof(double) * n, m,
+                                    cudaMemcpyDeviceToHost, st));
+    PGP_CUDA(ctx, cudaStreamSynchronize(st));
+    if (h) {
+        char buf[160];
+        snprintf(buf, sizeof buf, "%d-th leading minor of the array is not positive definite", h);
+        ctx->err = buf;
+    }
+    return h;
+}
+
 extern "C" int pgp_exact_get_factor(pgp_model* m, double* R_out, double* a_out) {
     if (!m) return PGP_E_ARG;
     pgp_ctx* ctx = m->ctx;

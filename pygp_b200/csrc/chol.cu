@@ -624,6 +624,36 @@ int launch_predict_grad_reduce(pgp_ctx* ctx, const double* B, int64_t ld, int64_
     return check_launch(ctx, "predict_grad_reduce_kernel");
 }
 
+// GP.sample helpers: S += jitter I;  then (mode 0) zero the strict upper triangle of the factor,
+// (mode 1) O[i][j] += mu[j]
+__global__ void mvn_prepare_kernel(double* S, int64_t ld, int64_t n, double jitter) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        S[i * ld + i] += jitter;
+}
+
+__global__ void mvn_finish_kernel(double* S, int64_t ld, int64_t n, double* O, const double* mu, int64_t m, int mode) {
+    const int64_t rows = mode == 0 ? n : m;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < rows * n;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = idx / n, c = idx - r * n;
+        if (mode == 0) { if (c > r) S[r * ld + c] = 0.0; }
+        else O[r * ld + c] += mu[c];
+    }
+}
+
+int launch_mvn_prepare(pgp_ctx* ctx, double* S, int64_t ld, int64_t n, double jitter) {
+    Launch L(ctx, PC_OTHER, 16.0 * n);
+    mvn_prepare_kernel<<<(unsigned)std::min<int64_t>(ceil_div(n, 256), 1184), 256, 0, ctx->stream>>>(S, ld, n, jitter);
+    return check_launch(ctx, "mvn_prepare_kernel");
+}
+
+int launch_mvn_finish(pgp_ctx* ctx, double* S, int64_t ld, int64_t n, double* O, const double* mu, int64_t m, int mode) {
+    const int64_t total = (mode == 0 ? n : m) * n;
+    Launch L(ctx, PC_OTHER, 16.0 * total);
+    mvn_finish_kernel<<<(unsigned)std::min<int64_t>(ceil_div(total, 256), 1184), 256, 0, ctx->stream>>>(S, ld, n, O, mu, m, mode);
+    return check_launch(ctx, "mvn_finish_kernel");
+}
+
 __global__ void extract_upper_kernel(const double* F, int64_t ld, int64_t n, double* R) {
     // R[i][j] = L[j][i] for j >= i else 0 ; tile transpose through shared memory
     __shared__ double tile[32][33];

@@ -64,6 +64,10 @@ int launch_predict_reduce(pgp_ctx* ctx, const double* B, int64_t ld, int64_t row
 int launch_predict_grad_reduce(pgp_ctx* ctx, const double* B, int64_t ld, int64_t mc, int d, int64_t n,
                                const double* a, double* dmu, double* ds2);
 
+// GP.sample (_base.py:168-172) pieces: S += jitter I; zero the strict upper triangle (mode 0) / O += mu (mode 1)
+int launch_mvn_prepare(pgp_ctx* ctx, double* S, int64_t ld, int64_t n, double jitter);
+int launch_mvn_finish(pgp_ctx* ctx, double* S, int64_t ld, int64_t n, double* O, const double* mu, int64_t m, int mode);
+
 // R_out (n, n) dense upper = L^T  (the reference's self._R)
 int launch_extract_upper(pgp_ctx* ctx, const double* F, int64_t ld, int64_t n, double* R);
 

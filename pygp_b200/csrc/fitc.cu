@@ -753,3 +753,70 @@ extern "C" int pgp_fitc_predict_grad(pgp_fitc* f, const double* Xs, int64_t ms, 
     if (!Xs || !mu || !s2 || !dmu || !ds2 || ms < 0) return f->ctx->fail(PGP_E_ARG, "null or negative argument");
     return fitc_predict_impl(f, Xs, ms, mu, s2, dmu, ds2);
 }
+
+// FITC._full_posterior (fitc.py:102-120): mu (ms), Sigma (ms, ms) = k(X*, X*) + RK^T RK - LK^T LK
+extern "C" int pgp_fitc_full_posterior(pgp_fitc* f, const double* Xs, int64_t ms, double* mu, double* Sigma) {
+    if (!f) return PGP_E_ARG;
+    pgp_ctx* ctx = f->ctx;
+    if (!Xs || !mu || !Sigma || ms < 0) return ctx->fail(PGP_E_ARG, "null or negative argument");
+    if (!f->factored) return ctx->fail(PGP_E_STATE, "full posterior before a successful update");
+    if (ms == 0) return 0;
+    PGP_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int d = f->ndim, np = f->spec.n_parts;
+    const int64_t p = f->p, ldp = f->ldp, lds = lead_dim(ms);
+    cudaStream_t s = ctx->stream;
+    if ((double)ms * ldp * 16 > 8.0 * (1ull << 30)) return ctx->fail(PGP_E_ARG, "full posterior: too many test points for one chunk");
+    double *LK = nullptr, *RK = nullptr, *S = nullptr, *dxs = nullptr, *dzs = nullptr, *dout = nullptr;
+    int rc = pool_alloc(ctx, &LK, (size_t)ms * ldp);
+    if (!rc) rc = pool_alloc(ctx, &RK, (size_t)ms * ldp);
+    if (!rc) rc = pool_alloc(ctx, &S, (size_t)ms * lds);
+    if (!rc) rc = dev_alloc(ctx, &dxs, (size_t)ms * d);
+    if (!rc) rc = dev_alloc(ctx, &dzs, (size_t)np * ms * d);
+    if (!rc) rc = dev_alloc(ctx, &dout, (size_t)2 * ms);
+    auto body = [&]() -> int {
+        PGP_CUDA(ctx, cudaMemcpyAsync(dxs, Xs, sizeof(double) * ms * d, cudaMemcpyHostToDevice, s));
+        PGP_TRY(launch_scale(ctx, f->d_spec, dxs, ms, d, np, dzs, 1));
+        GramArgs g;
+        g.spec = f->d_spec;
+        g.Z1 = dzs; g.n1 = ms;
+        g.Z2 = f->d_ZU; g.n2 = p;
+        g.ndim = d; g.n_parts = np;
+        g.out = LK; g.ldo = ldp;
+        g.single_type = single_type(&f->spec);
+        PGP_TRY(launch_gram(ctx, g));
+        PGP_CUDA(ctx, cudaMemcpyAsync(RK, LK, sizeof(double) * ms * ldp, cudaMemcpyDeviceToDevice, s));
+        Mat L; L.p = f->d_L; L.ld = ldp;
+        Mat R; R.p = f->d_R; R.ld = ldp;
+        Mat Lk; Lk.p = LK; Lk.ld = ldp;
+        Mat Rk; Rk.p = RK; Rk.ld = ldp;
+        PGP_TRY(trsm_right_lt(ctx, Lk, ms, L, p));
+        PGP_TRY(trsm_right_lt(ctx, Rk, ms, R, p));
+        {
+            Launch Lc(ctx, PC_OTHER, 16.0 * ms * p);
+            fitc_predict_reduce_kernel<<<warp_rows_grid(ms), 256, 0, s>>>(LK, RK, ldp, ms, p, f->d_b, f->d_spec, dout,
+                                                                         dout + ms);
+            PGP_TRY(check_launch(ctx, "fitc_predict_reduce_kernel"));
+        }
+        GramArgs gs = g;
+        gs.Z2 = dzs; gs.n2 = ms;
+        gs.out = S; gs.ldo = lds;
+        gs.symmetric = 1;
+        PGP_TRY(launch_gram(ctx, gs));
+        PGP_TRY(gemm(ctx, RK, ldp, 0, RK, ldp, 0, S, lds, ms, ms, p, 1.0, 1.0, 0, 1));
+        PGP_TRY(gemm(ctx, LK, ldp, 0, LK, ldp, 0, S, lds, ms, ms, p, -1.0, 1.0, 0, 1));
+        PGP_CUDA(ctx, cudaMemcpyAsync(mu, dout, sizeof(double) * ms, cudaMemcpyDeviceToHost, s));
+        PGP_CUDA(ctx, cudaMemcpy2DAsync(Sigma, sizeof(double) * ms, S, sizeof(double) * lds, sizeof(double) * ms, ms,
+                                        cudaMemcpyDeviceToHost, s));
+        PGP_CUDA(ctx, cudaStreamSynchronize(s));
+        return 0;
+    };
+    if (!rc) rc = body();
+    cudaStreamSynchronize(s);
+    pool_free(ctx, LK, (size_t)ms * ldp);
+    pool_free(ctx, RK, (size_t)ms * ldp);
+    pool_free(ctx, S, (size_t)ms * lds);
+    cudaFree(dxs);
+    cudaFree(dzs);
+    cudaFree(dout);
+    return rc;
+}

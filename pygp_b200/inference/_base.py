@@ -88,10 +88,29 @@ class GP(Parameterized):
         """Marginal posterior mean and variance at the rows of X."""
         return self._marg_posterior(self._kernel.transform(X), grad)
 
-    # joint posterior draws and Fourier sampling are outside the accelerated
-    # path this round (SURVEY.md 8f, row N3)
     def sample(self, X, m=None, latent=True, rng=None):
-        raise NotImplementedError('GP.sample is outside the B200 hot path (next: N3)')
+        """Sample values from the posterior at the points X (_base.py:143-177):
+        an n-vector, or an (m, n) array of m samples; `latent=False` adds
+        observation noise.  The normal variates come from the host rng in the
+        reference's order; the Cholesky of the joint covariance and the
+        transform run on the device."""
+        from .. import _lib
+        from ..utils.random import rstate
+        X = self._kernel.transform(X)
+        flatten = (m is None)
+        m = 1 if flatten else m
+        n = len(X)
+        rng = rstate(rng)
+        mu, Sigma = self._full_posterior(X)
+        Z = _lib.as_f64(rng.normal(size=(m, n)), 2)
+        f = np.empty((m, n))
+        ctx = _lib.context()
+        mu, Sigma = _lib.as_f64(mu), _lib.as_f64(Sigma, 2)
+        _lib.check(ctx, _lib.lib().pgp_mvn_transform(ctx.handle, _lib.ptr(mu), _lib.ptr(Sigma), n, 1e-10,
+                                                     _lib.ptr(Z), m, _lib.ptr(f)))
+        if not latent:
+            f = self._likelihood.sample(f.ravel(), rng).reshape(m, n)
+        return f.ravel() if flatten else f
 
     def sample_fourier(self, N, rng=None):
         raise NotImplementedError('GP.sample_fourier is outside the B200 hot path')
@@ -104,7 +123,7 @@ class GP(Parameterized):
         raise NotImplementedError
 
     def _full_posterior(self, X):
-        raise NotImplementedError('_full_posterior is outside the B200 hot path (next: N3)')
+        raise NotImplementedError('_full_posterior is not provided for this model (next: N3)')
 
     @abc.abstractmethod
     def _marg_posterior(self, X, grad=False):

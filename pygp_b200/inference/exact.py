@@ -135,6 +135,16 @@ class ExactGP(GP):
             self._dev.handle, int(bool(grad)), C.byref(lZ), None if dlZ is None else _lib.ptr(dlZ)))
         return (lZ.value, dlZ) if grad else lZ.value
 
+    def _full_posterior(self, X):
+        """Joint posterior mean and covariance at the rows of X (exact.py:64-79)."""
+        X = _lib.as_f64(X, 2)
+        if self._X is None:
+            return np.full(X.shape[0], self._mean), self._kernel.get(X)
+        mu, Sigma = np.empty(len(X)), np.empty((len(X), len(X)))
+        _lib.check(self._dev.ctx, _lib.lib().pgp_exact_full_posterior(
+            self._dev.handle, _lib.ptr(X), len(X), _lib.ptr(mu), _lib.ptr(Sigma)))
+        return mu, Sigma
+
     def _marg_posterior(self, X, grad=False):
         X = _lib.as_f64(X, 2)
         if self._X is None:

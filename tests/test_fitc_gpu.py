@@ -163,3 +163,28 @@ def test_posterior_input_gradients(name, golden):
     assert_pred_close(mu, s2, g[name + '/mu'], g[name + '/s2'])
     nt.assert_allclose(dmu, g[name + '/dmu'], rtol=1e-8, atol=1e-9*max(1.0, np.abs(g[name + '/dmu']).max()))
     nt.assert_allclose(ds2, g[name + '/ds2'], rtol=1e-7, atol=1e-9*max(1.0, np.abs(g[name + '/ds2']).max()))
+
+
+@pytest.mark.parametrize('name', FITC_CASES)
+def test_full_posterior_and_sample(name, golden):
+    """_full_posterior and GP.sample (_base.py:143-177) against the reference's own
+    joint covariance and its draws for the same seed (the normal variates come from
+    the host rng in the reference's order; Cholesky + transform run on the device)."""
+    g = golden['gp']
+    gp, _ = build(name)
+    Xj = g[name + '/Xj']
+    mu, Sigma = gp._full_posterior(Xj)
+    nt.assert_allclose(mu, g[name + '/full_mu'], rtol=1e-10, atol=1e-10)
+    nt.assert_allclose(Sigma, g[name + '/full_Sigma'], rtol=1e-8, atol=1e-11)
+    nt.assert_allclose(Sigma, Sigma.T, rtol=0, atol=1e-14)
+    # marginals of the joint == the marginal posterior
+    m1, s1 = gp.posterior(Xj)
+    nt.assert_allclose(np.diag(Sigma), s1, rtol=1e-9, atol=1e-12)
+    nt.assert_allclose(mu, m1, rtol=1e-12)
+    f = gp.sample(Xj, 3, latent=False, rng=5)
+    # the draws go through chol(Sigma + 1e-10 I): the factor of a covariance with 1e-4..1e-2
+    # eigenvalues amplifies 1e-11 differences in Sigma; 1e-6 is the reference-vs-oracle level too
+    nt.assert_allclose(f, g[name + '/sample'], rtol=1e-6, atol=1e-7)
+    assert gp.sample(Xj, rng=0).shape == (len(Xj),)
+    gp.reset()                                         # prior draws
+    assert gp.sample(Xj, 2, rng=1).shape == (2, len(Xj))

@@ -67,6 +67,10 @@ def test_gp_vs_golden(name, golden):
     mu, s2, dmu, ds2 = gp.posterior(Xs, grad=True)
     nt.assert_allclose(dmu, g[name + '/dmu'], rtol=1e-10, atol=1e-12)
     nt.assert_allclose(ds2, g[name + '/ds2'], rtol=1e-10, atol=1e-12)
+    fmu, fS = gp.full_posterior(g[name + '/Xj'])
+    nt.assert_allclose(fmu, g[name + '/full_mu'], rtol=1e-12)
+    nt.assert_allclose(fS, g[name + '/full_Sigma'], rtol=1e-10, atol=1e-13)
+    nt.assert_allclose(gp.sample(g[name + '/Xj'], 3, latent=False, rng=5), g[name + '/sample'], rtol=1e-8, atol=1e-9)
     nt.assert_allclose(lZ, g[name + '/lZ'], rtol=1e-12)
     nt.assert_allclose(dlZ, g[name + '/dlZ'], rtol=1e-10, atol=1e-10)
     nt.assert_allclose(mu, g[name + '/mu'], rtol=1e-12)
