@@ -1,4 +1,5 @@
-"""Meta-models marginalising the hypers (meta.SMC is not provided this round)."""
+"""Meta-models marginalising the hypers: same names as pygp.meta."""
 from .mcmc import MCMC
+from .smc import SMC
 
-__all__ = ['MCMC']
+__all__ = ['MCMC', 'SMC']

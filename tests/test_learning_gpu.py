@@ -194,3 +194,46 @@ def test_mcmc_posterior_input_gradients():
     f_s2 = lambda x: model.posterior(x[None])[1][0]
     nt.assert_allclose(dmu, [spop.approx_fprime(x, f_mu, 1e-7) for x in Xq], rtol=1e-5, atol=1e-5)
     nt.assert_allclose(ds2, [spop.approx_fprime(x, f_s2, 1e-7) for x in Xq], rtol=1e-4, atol=1e-5)
+
+
+def test_smc_particles():
+    """meta.SMC (pygp/meta/smc.py:53-150; the reference only smoke-tests it,
+    tests/test_plotting.py:62-63): weights stay normalised, every particle's
+    incrementally grown factor equals a from-scratch model at its hypers, the
+    mixture posterior is the weighted moment match of the particles, and its
+    input-gradients agree with finite differences."""
+    import scipy.optimize as spop
+    import pygp_b200 as pygp
+    rng = np.random.RandomState(3)
+    X = rng.rand(12, 2)
+    y = np.sin(3*X.sum(1)) + 0.1*rng.randn(12)
+    priors = {'sn': pygp.priors.Uniform(0.05, 1.0), 'sf': pygp.priors.Uniform(0.2, 5.0),
+              'ell': pygp.priors.Uniform([0.05, 0.05], [2.0, 2.0]), 'mu': pygp.priors.Uniform(-2, 2)}
+    model = pygp.meta.SMC(pygp.BasicGP(0.5, 1, [1, 1]), priors, n=6, rng=0)
+    assert model.ndata == 0
+    model.add_data(X[:7], y[:7])
+    model.add_data(X[7:], y[7:])
+    assert model.ndata == 12
+    nt.assert_allclose(np.exp(model._logweights).sum(), 1.0, rtol=1e-12)
+    for p in model:
+        fresh = pygp.BasicGP(0.5, 1, [1, 1])
+        fresh.set_hyper(p.get_hyper())
+        fresh.add_data(*p.data)
+        nt.assert_allclose(p.loglikelihood(), fresh.loglikelihood(), rtol=1e-9)
+    Xq = rng.rand(3, 2)
+    mu, s2, dmu, ds2 = model.posterior(Xq, grad=True)
+    w = np.exp(model._logweights)
+    parts = [p.posterior(Xq) for p in model]
+    mu_ = np.array([p[0] for p in parts])
+    s2_ = np.array([p[1] for p in parts])
+    nt.assert_allclose(mu, w @ mu_, rtol=1e-12)
+    nt.assert_allclose(s2, w @ (s2_ + (mu_ - mu)**2), rtol=1e-12)
+    f_mu = lambda x: model.posterior(x[None])[0][0]
+    f_s2 = lambda x: model.posterior(x[None])[1][0]
+    nt.assert_allclose(dmu, [spop.approx_fprime(x, f_mu, 1e-7) for x in Xq], rtol=1e-5, atol=1e-5)
+    nt.assert_allclose(ds2, [spop.approx_fprime(x, f_s2, 1e-7) for x in Xq], rtol=1e-4, atol=1e-5)
+    # a model that already holds data replays it (smc.py:62-76)
+    gp = pygp.BasicGP(0.5, 1, [1, 1])
+    gp.add_data(X[:5], y[:5])
+    m2 = pygp.meta.SMC(gp, priors, n=4, rng=1)
+    assert m2.ndata == 5 and gp.ndata == 5
