@@ -245,7 +245,7 @@ template <bool IDENT, bool NOTRANS = false>
 int launch_trsm_base(pgp_ctx* ctx, const Mat& B, int64_t rows, const Mat& L, int64_t j0, int n) {
     if (rows <= 0) return 0;
     auto kern = trsm_base_kernel<IDENT, NOTRANS>;
-    PGP_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTrsmSmem));
+    PGP_TRY(ensure_dyn_smem(ctx, kern, kTrsmSmem));
     int64_t blocks = ceil_div(rows, kTrsmRows);
     Launch Lc(ctx, PC_TRSM, (double)rows * n * n * B.batch);
     kern<<<dim3((unsigned)blocks, B.batch), kTrsmRows, kTrsmSmem, ctx->stream>>>(
@@ -256,7 +256,7 @@ int launch_trsm_base(pgp_ctx* ctx, const Mat& B, int64_t rows, const Mat& L, int
 // G's diagonal 64-blocks <- (L's diagonal blocks)^-T, all in one launch
 int launch_inv_diag_blocks(pgp_ctx* ctx, const Mat& G, const Mat& L, int64_t n) {
     auto kern = trsm_base_kernel<true, false>;
-    PGP_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTrsmSmem));
+    PGP_TRY(ensure_dyn_smem(ctx, kern, kTrsmSmem));
     int64_t nblk = ceil_div(n, (int64_t)kNB);
     if (nblk > 65535) return ctx->fail(PGP_E_ARG, "triangular inverse: more than 65535 diagonal blocks");
     Launch Lc(ctx, PC_TRSM, (double)n * kNB * kNB / 3.0);
@@ -457,7 +457,7 @@ int launch_trsv_lower(pgp_ctx* ctx, const Mat& F, int64_t n) {
     if (n <= 0) return 0;
     if (n > kTrsvMaxN) return ctx->fail(PGP_E_ARG, "trsv_lower: n too large for the shared-memory vector");
     size_t smem = ((size_t)((n + 1) & ~1) + (size_t)kNB * (kNB + 1)) * sizeof(double);
-    PGP_CUDA(ctx, cudaFuncSetAttribute(trsv_lower_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PGP_TRY(ensure_dyn_smem(ctx, trsv_lower_kernel, smem));
     Launch L(ctx, PC_TRSM, (double)n * n * F.batch);
     trsv_lower_kernel<<<F.batch, 1024, smem, ctx->stream>>>(F.p, F.ld, F.bstride, (int)n);
     return check_launch(ctx, "trsv_lower_kernel");

@@ -6,7 +6,9 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/pygp_b200.h"
@@ -173,6 +175,24 @@ inline void pool_release(pgp_ctx* ctx) {
     for (auto& e : ctx->pool) cudaFree(e.p);
     ctx->pool.clear();
     ctx->pool_bytes = 0;
+}
+
+// opt a kernel in to `bytes` of dynamic shared memory.  The attribute is sticky, so
+// it is set only when a launch needs more than any earlier one did (a high-water
+// mark per (device, kernel entry point)): cudaFuncSetAttribute costs ~1-2 us of
+// host time, which shows when thousands of short kernels are chained.
+inline int ensure_dyn_smem_ptr(pgp_ctx* ctx, const void* kernel, size_t bytes) {
+    static std::map<std::pair<int, const void*>, size_t> high;
+    size_t& h = high[std::make_pair(ctx->device, kernel)];
+    if (bytes <= h) return 0;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return ctx->cuda_fail(e, "cudaFuncSetAttribute", __FILE__, __LINE__);
+    h = bytes;
+    return 0;
+}
+template <class K>
+inline int ensure_dyn_smem(pgp_ctx* ctx, K kernel, size_t bytes) {
+    return ensure_dyn_smem_ptr(ctx, reinterpret_cast<const void*>(kernel), bytes);
 }
 
 inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }

@@ -28,15 +28,18 @@ namespace pgp {
 
 namespace {
 
-constexpr int BM = 128, BN = 128;
 // CTAs are rasterised in groups of GROUP_M tile rows (column index fastest
 // inside a group) so that the ~148 CTAs in flight share a ~12 x 12 block of
 // tiles: each operand k-slice is then fetched from HBM once per wave and
 // served to the other CTAs from L2.
 constexpr int GROUP_M = 12;
 
-template <int BK_, int STAGES_>
+// T = CTA tile edge (T x T outputs): 128 for the big updates, 64 for launches with
+// too few 128-tiles to fill the GPU (leaf levels of the recursions, batched small
+// blocks), where a 128 x 128 tile computes mostly padding on a fraction of the SMs.
+template <int T_, int BK_, int STAGES_>
 struct Cfg {
+    static constexpr int BM = T_, BN = T_;
     static constexpr int BK = BK_, STAGES = STAGES_;
     static constexpr int LDS = BK + 4;  // padded shared row (doubles): conflict-free fragment loads
     static constexpr int LDT = BM + 4;  // row of a transposed-operand tile ([k][m]); 132 = 4 mod 16
@@ -69,7 +72,8 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 // [k][m] with a row of BM + 4 doubles, which keeps the fragment loads
 // (lane -> m = lane/4, k = lane%4) conflict-free as well: 132 = 4 (mod 16).
 template <int WM, int WN, class C, bool TA, bool TB>
-__global__ void __launch_bounds__(WM * WN * 32, 1) gemm_kernel(GemmArgs a, int tm, int tn) {
+__global__ void __launch_bounds__(WM * WN * 32, C::BM == 64 ? 2 : 1) gemm_kernel(GemmArgs a, int tm, int tn) {
+    constexpr int BM = C::BM, BN = C::BN;
     constexpr int THREADS = WM * WN * 32;
     constexpr int MI = BM / WM / 8, NJ = BN / WN / 8;
     constexpr int BK = C::BK, STAGES = C::STAGES, LDS = C::LDS, LDT = C::LDT;
@@ -374,7 +378,7 @@ namespace {
 template <int WM, int WN, class C, bool TA, bool TB>
 int launch_variant(pgp_ctx* ctx, const GemmArgs& a, int64_t tm, int64_t tn) {
     auto kern = gemm_kernel<WM, WN, C, TA, TB>;
-    PGP_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    PGP_TRY(ensure_dyn_smem(ctx, kern, C::SMEM));
     dim3 grid((unsigned)(tm * tn), (unsigned)std::max(a.splitk, 1), a.batch);
     kern<<<grid, WM * WN * 32, C::SMEM, ctx->stream>>>(a, (int)tm, (int)tn);
     return 0;
@@ -390,14 +394,30 @@ int launch_gemm(pgp_ctx* ctx, const GemmArgs& a_in) {
     if (a.transA && a.krow) return ctx->fail(PGP_E_ARG, "gemm: krow needs A stored (M, K)");
     if (a.kcol && !a.transB) return ctx->fail(PGP_E_ARG, "gemm: kcol needs B stored (K, N)");
     static const int variant = [] { const char* e = getenv("PGP_GEMM_VARIANT"); return e ? atoi(e) : 0; }();
-    int64_t tm = ceil_div(a.M, BM), tn = ceil_div(a.N, BN);
+    // CTA tile: 64 x 64 when 128 x 128 tiles would leave most SMs idle
+    auto count_tiles = [&](int64_t T) {           // CTA tiles that do work (tri skips those above the diagonal)
+        const int64_t tmT = ceil_div(a.M, T), tnT = ceil_div(a.N, T);
+        if (!a.tri) return tmT * tnT;
+        int64_t cnt = 0;
+        for (int64_t ti = 0; ti < tmT; ++ti) {
+            int64_t last = (ti * T + T - 1 + a.tri_off) / T;          // last tile column on / below the diagonal
+            if (ti * T + T - 1 + a.tri_off < 0) continue;
+            cnt += std::min(tnT, last + 1);
+        }
+        return cnt;
+    };
+    const int64_t tiles128 = count_tiles(128) * a.batch;
+    static const int force_tile = [] { const char* e = getenv("PGP_GEMM_TILE"); return e ? atoi(e) : 0; }();
+    const bool small = force_tile ? force_tile == 64 : tiles128 < (int64_t)ctx->sm_count;
+    const int BM = small ? 64 : 128, BN = BM;
+    int64_t tm = ceil_div(a.M, (int64_t)BM), tn = ceil_div(a.N, (int64_t)BN);
     if (tm * tn > 0x7fffffffLL || a.batch > 65535) return ctx->fail(PGP_E_ARG, "gemm: grid too large");
     // split the contraction when the output has too few tiles to fill the GPU
     // (FITC: p x p results contracted over n >> p): partials go to a workspace
     // and are summed in a fixed order
     a.splitk = 1;
     if (a_in.splitk != 1 && !a.krow && !a.kcol && a.batch == 1) {
-        int64_t tiles = a.tri ? tm * (tm + 1) / 2 : tm * tn;
+        int64_t tiles = count_tiles(BM);
         int64_t want = a_in.splitk > 1 ? a_in.splitk : (2 * ctx->sm_count) / std::max<int64_t>(tiles, 1);
         int64_t max_by_k = a.K / 2048;  // keep >= 2048 contraction steps per slice
         int64_t S = std::min<int64_t>(std::min<int64_t>(want, max_by_k), 64);
@@ -421,7 +441,7 @@ int launch_gemm(pgp_ctx* ctx, const GemmArgs& a_in) {
     // columns on/below the diagonal times the contraction length actually needed
     double flops = 0.0;
     for (int64_t ti = 0; ti < tm; ++ti) {
-        double rows = (double)std::min<int64_t>(BM, a.M - ti * BM);
+        double rows = (double)std::min<int64_t>(BM, a.M - ti * (int64_t)BM);
         double mid = (double)(ti * BM) + 0.5 * (rows - 1.0);
         double cols = (double)a.N, klen = (double)a.K;
         if (a.tri) cols = std::min(std::max(mid + (double)a.tri_off + 1.0, 0.0), (double)a.N);
@@ -440,14 +460,19 @@ int launch_gemm(pgp_ctx* ctx, const GemmArgs& a_in) {
         Launch L(ctx, PC_GEMM, flops * a.batch);
         L.shape(a.M, a.N, a.K, a.tri | (a.krow << 1) | (a.transA << 2) | (a.transB << 3) | (a.kcol << 4) | (a.batch << 8));
         int rc;
-        if (a.transA && a.transB) rc = launch_variant<4, 4, Cfg<32, 3>, true, true>(ctx, a, tm, tn);
-        else if (a.transA) rc = launch_variant<4, 4, Cfg<32, 3>, true, false>(ctx, a, tm, tn);
-        else if (a.transB) rc = launch_variant<4, 4, Cfg<32, 3>, false, true>(ctx, a, tm, tn);
+        if (small) {
+            if (a.transA && a.transB) rc = launch_variant<2, 2, Cfg<64, 32, 3>, true, true>(ctx, a, tm, tn);
+            else if (a.transA) rc = launch_variant<2, 2, Cfg<64, 32, 3>, true, false>(ctx, a, tm, tn);
+            else if (a.transB) rc = launch_variant<2, 2, Cfg<64, 32, 3>, false, true>(ctx, a, tm, tn);
+            else rc = launch_variant<2, 2, Cfg<64, 32, 3>, false, false>(ctx, a, tm, tn);
+        } else if (a.transA && a.transB) rc = launch_variant<4, 4, Cfg<128, 32, 3>, true, true>(ctx, a, tm, tn);
+        else if (a.transA) rc = launch_variant<4, 4, Cfg<128, 32, 3>, true, false>(ctx, a, tm, tn);
+        else if (a.transB) rc = launch_variant<4, 4, Cfg<128, 32, 3>, false, true>(ctx, a, tm, tn);
         else switch (variant) {
-            case 1: rc = launch_variant<4, 4, Cfg<16, 4>, false, false>(ctx, a, tm, tn); break;
-            case 2: rc = launch_variant<2, 4, Cfg<32, 3>, false, false>(ctx, a, tm, tn); break;
-            case 4: rc = launch_variant<2, 4, Cfg<16, 4>, false, false>(ctx, a, tm, tn); break;
-            default: rc = launch_variant<4, 4, Cfg<32, 3>, false, false>(ctx, a, tm, tn); break;
+            case 1: rc = launch_variant<4, 4, Cfg<128, 16, 4>, false, false>(ctx, a, tm, tn); break;
+            case 2: rc = launch_variant<2, 4, Cfg<128, 32, 3>, false, false>(ctx, a, tm, tn); break;
+            case 4: rc = launch_variant<2, 4, Cfg<128, 16, 4>, false, false>(ctx, a, tm, tn); break;
+            default: rc = launch_variant<4, 4, Cfg<128, 32, 3>, false, false>(ctx, a, tm, tn); break;
         }
         PGP_TRY(rc);
         PGP_TRY(check_launch(ctx, "gemm_kernel"));

@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(kThreads) gram_kernel(GramArgs a) {
 template <int PTYPE, int MODE>
 static int launch_gram_t(pgp_ctx* ctx, const GramArgs& a, size_t smem) {
     auto kern = gram_kernel<PTYPE, MODE>;
-    PGP_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PGP_TRY(ensure_dyn_smem(ctx, kern, smem));
     int64_t t1 = ceil_div(a.n1, kTile), t2 = ceil_div(a.n2, kTile);
     dim3 grid;
     double entries;
@@ -628,7 +628,7 @@ template <int PTYPE>
 static int launch_trace_rect_t(pgp_ctx* ctx, const TraceRectArgs& a, size_t smem, int64_t t2, int64_t n_tiles,
                                int grid) {
     auto kern = trace_rect_kernel<PTYPE>;
-    PGP_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PGP_TRY(ensure_dyn_smem(ctx, kern, smem));
     Launch L(ctx, PC_TRACE, (a.mode == 0 ? 8.0 : 16.0) * (double)a.n1 * (double)a.n2);
     kern<<<grid, kThreads, smem, ctx->stream>>>(a, t2, n_tiles);
     return check_launch(ctx, "trace_rect_kernel");
@@ -696,7 +696,7 @@ int64_t trace_cta_count(int64_t n) {
 template <int PTYPE>
 static int launch_trace_t(pgp_ctx* ctx, const TraceArgs& a, size_t smem, int64_t n_tiles, int grid) {
     auto kern = trace_kernel<PTYPE>;
-    PGP_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PGP_TRY(ensure_dyn_smem(ctx, kern, smem));
     Launch L(ctx, PC_TRACE, 4.0 * (double)a.n * (double)a.n);
     kern<<<grid, kThreads, smem, ctx->stream>>>(a, n_tiles);
     return check_launch(ctx, "trace_kernel");
