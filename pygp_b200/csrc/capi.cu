@@ -78,6 +78,11 @@ extern "C" void pgp_ctx_destroy(pgp_ctx* ctx) {
     prof_clear(ctx);
     pool_release(ctx);
     if (ctx->gemm_ws) cudaFree(ctx->gemm_ws);
+    for (cudaEvent_t ev : ctx->sync_events) cudaEventDestroy(ev);
+    if (ctx->stream2) {
+        cudaStreamSynchronize(ctx->stream2);
+        cudaStreamDestroy(ctx->stream2);
+    }
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     cudaStreamDestroy(ctx->stream);
     delete ctx;

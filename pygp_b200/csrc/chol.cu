@@ -17,6 +17,8 @@
 //       level (n^3/3 flops, ~2 log2(n/64) launches),
 //   syrk_upper_lower: K~^-1 = V V^T on the lower tiles with k >= row (n^3/3).
 
+#include <cstdlib>
+
 #include "chol.cuh"
 #include "spec.cuh"
 
@@ -295,6 +297,80 @@ int chol_rec(pgp_ctx* ctx, const Mat& F, int64_t j0, int64_t n, int64_t mrows, i
     return chol_rec(ctx, F, c0, n2, mrows, d_info);
 }
 
+// ---------------------------------------------------------------------------
+// Mid-size N: blocked right-looking factorisation with one-panel LOOKAHEAD on a
+// second stream.  The recursion above is ideal for large N (three quarters of the
+// flops in GEMMs with K >= N/4) but strictly sequential: for N <~ 16k the ~N/64
+// latency-bound leaf steps (potrf_base + trsm_base + K <= 256 updates) are half of
+// the time while the big updates wait.  Here the columns are cut into panels of
+// kLaNB; panel p+1 is brought up to date and factored (with the recursion) on the
+// panel stream WHILE the main stream applies panel p to the rest of the matrix:
+//     main : .. | update(p-1 -> cols >= c_{p+1}) | update(p -> cols >= c_{p+2}) | ..
+//     panel: .. | update(p-1 -> panel p), factor p | update(p -> panel p+1), factor p+1 | ..
+// ---------------------------------------------------------------------------
+constexpr int64_t kLaNB = 512;          // panel width
+constexpr int64_t kLaMinN = 1536;       // below: plain recursion (too few panels to overlap)
+constexpr int64_t kLaMaxN = 20480;      // above: the recursion's big-K GEMMs win
+
+struct StreamSwap {                     // run the enclosed launches on another stream
+    pgp_ctx* ctx;
+    cudaStream_t saved;
+    StreamSwap(pgp_ctx* c, cudaStream_t s) : ctx(c), saved(c->stream) { c->stream = s; }
+    ~StreamSwap() { ctx->stream = saved; }
+};
+
+int chol_lookahead(pgp_ctx* ctx, const Mat& F, int64_t n, int64_t mrows, int* d_info) {
+    if (!ctx->stream2) {
+        // highest priority: the panel's short kernels must get the next free SM even
+        // while thousands of CTAs of a trailing update are still pending
+        int lo = 0, hi = 0;
+        PGP_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        PGP_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, hi));
+    }
+    const int64_t np_ = ceil_div(n, kLaNB);
+    while ((int64_t)ctx->sync_events.size() < 2 * np_ + 2) {
+        cudaEvent_t ev;
+        PGP_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        ctx->sync_events.push_back(ev);
+    }
+    cudaStream_t sA = ctx->stream, sB = ctx->stream2;
+    auto ev_panel = [&](int64_t p) { return ctx->sync_events[2 * p]; };       // panel p factored (recorded on sB)
+    auto ev_trail = [&](int64_t p) { return ctx->sync_events[2 * p + 1]; };   // trailing update by panel p done (on sA)
+    auto col = [&](int64_t p) { return std::min(p * kLaNB, n); };
+    // the panel stream starts after everything queued on the main stream (Gram build, residual)
+    PGP_CUDA(ctx, cudaEventRecord(ctx->sync_events[2 * np_], sA));
+    PGP_CUDA(ctx, cudaStreamWaitEvent(sB, ctx->sync_events[2 * np_], 0));
+    {
+        StreamSwap sw(ctx, sB);
+        PGP_TRY(chol_rec(ctx, F, 0, col(1), mrows, d_info));
+    }
+    PGP_CUDA(ctx, cudaEventRecord(ev_panel(0), sB));
+    for (int64_t p = 0; p < np_; ++p) {
+        const int64_t c0 = col(p), c1 = col(p + 1), c2 = col(p + 2), w = c1 - c0;
+        if (c1 >= n) break;
+        const double* P1 = F.p + c1 * F.ld + c0;      // rows c1.., the factored panel's columns
+        {   // panel stream: bring panel p+1 up to date with panel p, then factor it
+            StreamSwap sw(ctx, sB);
+            if (p > 0) PGP_CUDA(ctx, cudaStreamWaitEvent(sB, ev_trail(p - 1), 0));
+            PGP_TRY(gemm_update(ctx, P1, F.ld, 0, P1, F.ld, 0, F.p + c1 * F.ld + c1, F.ld, 0, mrows - c1, c2 - c1, w,
+                                -1.0, 1.0, /*tri=*/1, 0, 1));
+            PGP_TRY(chol_rec(ctx, F, c1, c2 - c1, mrows, d_info));
+            PGP_CUDA(ctx, cudaEventRecord(ev_panel(p + 1), sB));
+        }
+        if (c2 < n) {   // main stream: panel p onto everything right of panel p+1
+            PGP_CUDA(ctx, cudaStreamWaitEvent(sA, ev_panel(p), 0));
+            const double* P2 = F.p + c2 * F.ld + c0;
+            PGP_TRY(gemm_update(ctx, P2, F.ld, 0, P2, F.ld, 0, F.p + c2 * F.ld + c2, F.ld, 0, mrows - c2, n - c2, w,
+                                -1.0, 1.0, /*tri=*/1, 0, 1));
+            PGP_CUDA(ctx, cudaEventRecord(ev_trail(p), sA));
+        }
+    }
+    // the main stream continues once the last panel is done
+    PGP_CUDA(ctx, cudaEventRecord(ctx->sync_events[2 * np_ + 1], sB));
+    PGP_CUDA(ctx, cudaStreamWaitEvent(sA, ctx->sync_events[2 * np_ + 1], 0));
+    return 0;
+}
+
 int trsm_rec(pgp_ctx* ctx, const Mat& B, int64_t rows, const Mat& L, int64_t j0, int64_t n) {
     if (n <= kNB) return launch_trsm_base<false>(ctx, B, rows, L, j0, (int)n);
     int64_t n1 = split_point(n), n2 = n - n1, c0 = j0 + n1;
@@ -326,6 +402,8 @@ int trsm_nt_rec(pgp_ctx* ctx, const Mat& B, int64_t rows, const Mat& L, int64_t 
 
 int potrf_lower(pgp_ctx* ctx, const Mat& F, int64_t n, int64_t extra, int* d_info) {
     if (n <= 0) return 0;
+    static const int la = [] { const char* e = getenv("PGP_CHOL_LOOKAHEAD"); return e ? atoi(e) : 1; }();
+    if (la && F.batch == 1 && n >= kLaMinN && n <= kLaMaxN) return chol_lookahead(ctx, F, n, n + extra, d_info);
     return chol_rec(ctx, F, 0, n, n + extra, d_info);
 }
 

@@ -37,6 +37,8 @@ struct pgp_ctx {
     int sm_count = 148;
     size_t smem_optin = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;   // panel stream of the lookahead Cholesky (created on first use)
+    std::vector<cudaEvent_t> sync_events;   // reusable untimed events for cross-stream ordering
     std::string err;
     int64_t launches = 0;
     bool profile = false;

@@ -88,7 +88,7 @@ def c4():
     H = base + np.random.RandomState(2).uniform(-0.5, 0.5, size=(B, len(base)))
     from pygp_b200 import sharding
     sharding.sharded_batched_loglike(gp, H[:64])
-    t, lZ = best(lambda: sharding.sharded_batched_loglike(gp, H), 2)
+    t, lZ = best(lambda: sharding.sharded_batched_loglike(gp, H), 3)
     # spot-check 3 samples against single-model evaluations
     err = 0.0
     for i in (0, 1000, 4095):
