@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <ctime>
 #include <new>
 
 #include "chol.cuh"
@@ -76,8 +77,8 @@ extern "C" void pgp_ctx_destroy(pgp_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     prof_clear(ctx);
+    if (ctx->gemm_ws) dev_free(ctx, ctx->gemm_ws);
     pool_release(ctx);
-    if (ctx->gemm_ws) cudaFree(ctx->gemm_ws);
     for (cudaEvent_t ev : ctx->sync_events) cudaEventDestroy(ev);
     if (ctx->stream2) {
         cudaStreamSynchronize(ctx->stream2);
@@ -146,7 +147,13 @@ namespace {
 
 struct DevBuf {
     void* p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
+    pgp_ctx* ctx = nullptr;
+    ~DevBuf() {
+        if (p) {
+            cudaStreamSynchronize(ctx->stream);
+            dev_free(ctx, p);
+        }
+    }
     template <class T> T* as() { return reinterpret_cast<T*>(p); }
 };
 
@@ -173,6 +180,7 @@ int alloc(pgp_ctx* ctx, DevBuf& b, size_t count) {
     T* p = nullptr;
     PGP_TRY(dev_alloc(ctx, &p, std::max<size_t>(count, 1)));
     b.p = p;
+    b.ctx = ctx;
     return 0;
 }
 
@@ -400,8 +408,8 @@ void model_free_work(pgp_model* m) {
     pool_free(ctx, m->d_F, (size_t)(m->n + 1) * m->ld);
     pool_free(ctx, m->d_G, (size_t)m->n * m->ld);
     pool_free(ctx, m->d_H, (size_t)m->n * m->ld);
-    cudaFree(m->d_alpha); m->d_alpha = nullptr;
-    cudaFree(m->d_partials); m->d_partials = nullptr;
+    dev_free(ctx, m->d_alpha); m->d_alpha = nullptr;
+    dev_free(ctx, m->d_partials); m->d_partials = nullptr;
     pool_free(ctx, m->d_Bc, (size_t)m->bc_rows * m->ld);
     m->bc_rows = 0;
     m->factored = false;
@@ -430,8 +438,8 @@ int model_upload(pgp_model* m, const double* X, const double* y, int64_t n_old, 
     PGP_CUDA(ctx, cudaMemcpyAsync(nx + n_old * d, X, sizeof(double) * n_new * d, cudaMemcpyHostToDevice, ctx->stream));
     PGP_CUDA(ctx, cudaMemcpyAsync(ny + n_old, y, sizeof(double) * n_new, cudaMemcpyHostToDevice, ctx->stream));
     PGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    cudaFree(m->d_X);
-    cudaFree(m->d_y);
+    dev_free(ctx, m->d_X);
+    dev_free(ctx, m->d_y);
     m->d_X = nx;
     m->d_y = ny;
     m->n = n;
@@ -510,7 +518,7 @@ extern "C" int pgp_exact_append_inc(pgp_model* m, const double* X, const double*
         cudaStreamSynchronize(s);
         pool_free(ctx, nF, (size_t)(n + 1) * ld);
         pool_free(ctx, nZ, (size_t)np * n * d);
-        cudaFree(nAlpha);
+        dev_free(ctx, nAlpha);
         return code;
     };
     if (rc) return bail(rc);
@@ -598,14 +606,23 @@ extern "C" int pgp_exact_append_inc(pgp_model* m, const double* X, const double*
 
 extern "C" void pgp_model_destroy(pgp_model* m) {
     if (!m) return;
+    static const bool dbg = getenv("PGP_DEBUG_DESTROY") != nullptr;
+    auto now = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; };
+    double t0 = dbg ? now() : 0.0;
+    pgp_ctx* ctx = m->ctx;
     cudaSetDevice(m->ctx->device);
     cudaStreamSynchronize(m->ctx->stream);
+    double t1 = dbg ? now() : 0.0;
     model_free_work(m);
-    cudaFree(m->d_X);
-    cudaFree(m->d_y);
-    cudaFree(m->d_spec);
-    cudaFree(m->d_res);
-    cudaFree(m->d_info);
+    double t2 = dbg ? now() : 0.0;
+    dev_free(ctx, m->d_X);
+    dev_free(ctx, m->d_y);
+    dev_free(ctx, m->d_spec);
+    dev_free(ctx, m->d_res);
+    dev_free(ctx, m->d_info);
+    double t3 = dbg ? now() : 0.0;
+    if (dbg) fprintf(stderr, "[pgp destroy] sync %.4f free_work %.4f small %.4f pool %.1f GiB (%zu entries)\n", t1 - t0, t2 - t1,
+                     t3 - t2, m->ctx->pool_bytes / 1073741824.0, m->ctx->pool.size());
     delete m;
 }
 

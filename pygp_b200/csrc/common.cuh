@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <unordered_map>
 #include <string>
 #include <utility>
 #include <vector>
@@ -54,9 +55,10 @@ struct pgp_ctx {
     // cudaFree of multi-GiB buffers cost ~0.1 s each, more than the transfer of
     // the inputs they serve (the e2e path creates a model per call)
     struct PoolEntry { void* p; size_t bytes; };
+    std::unordered_map<void*, size_t> live;                   // every device allocation handed out -> its size
     std::vector<PoolEntry> pool;
     size_t pool_bytes = 0;
-    static constexpr size_t kPoolMin = (size_t)1 << 20;       // do not pool < 1 MiB
+    static constexpr size_t kPoolMaxEntries = 512;            // distinct cached buffers
     static constexpr size_t kPoolCap = (size_t)96 << 30;      // keep at most 96 GiB cached
 
     int fail(int code, const std::string& msg) {
@@ -121,55 +123,76 @@ inline int check_launch(pgp_ctx* ctx, const char* what) {
     return 0;
 }
 
-template <class T>
-inline int dev_alloc(pgp_ctx* ctx, T** p, size_t count) {
+// ---- device memory ---------------------------------------------------------------
+// Every device buffer of the library comes from dev_alloc and goes back through
+// dev_free, which parks it in a per-context cache (exact-size reuse) instead of
+// calling cudaFree: cudaMalloc / cudaFree of multi-GiB buffers cost ~0.1 s each, and
+// even a 4 MB cudaFree was measured at up to 0.6 s while tens of GiB are mapped
+// (tools/e2e_probe.py) -- more than the H2D copy of the inputs the buffers serve.
+// Reuse is stream-ordered: all work of a context runs on (or is joined back to) its
+// stream, so a recycled buffer cannot be touched by an earlier user any more.
+inline int dev_alloc_bytes(pgp_ctx* ctx, void** p, size_t bytes) {
     *p = nullptr;
-    if (count == 0) return 0;
-    cudaError_t e = cudaMalloc((void**)p, count * sizeof(T));
+    if (bytes == 0) return 0;
+    for (size_t i = 0; i < ctx->pool.size(); ++i) {
+        if (ctx->pool[i].bytes == bytes) {
+            *p = ctx->pool[i].p;
+            ctx->pool_bytes -= bytes;
+            ctx->pool.erase(ctx->pool.begin() + i);
+            ctx->live[*p] = bytes;
+            return 0;
+        }
+    }
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess && !ctx->pool.empty()) {   // give the cache back and retry
+        cudaGetLastError();
+        for (auto& en : ctx->pool) cudaFree(en.p);
+        ctx->pool.clear();
+        ctx->pool_bytes = 0;
+        e = cudaMalloc(p, bytes);
+    }
     if (e != cudaSuccess) {
         cudaGetLastError();
+        *p = nullptr;
         char buf[256];
-        snprintf(buf, sizeof buf, "cudaMalloc of %zu bytes failed: %s", count * sizeof(T),
-                 cudaGetErrorString(e));
+        snprintf(buf, sizeof buf, "cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
         return ctx->fail(PGP_E_NOMEM, buf);
     }
+    ctx->live[*p] = bytes;
     return 0;
 }
 
-// pooled allocation for the large per-model buffers
-template <class T>
-inline int pool_alloc(pgp_ctx* ctx, T** p, size_t count) {
-    size_t bytes = count * sizeof(T);
-    if (bytes >= pgp_ctx::kPoolMin) {
-        for (size_t i = 0; i < ctx->pool.size(); ++i) {
-            if (ctx->pool[i].bytes == bytes) {
-                *p = reinterpret_cast<T*>(ctx->pool[i].p);
-                ctx->pool_bytes -= bytes;
-                ctx->pool.erase(ctx->pool.begin() + i);
-                return 0;
-            }
-        }
-    }
-    int rc = dev_alloc(ctx, p, count);
-    if (rc == PGP_E_NOMEM && !ctx->pool.empty()) {  // give the cache back and retry
-        for (auto& e : ctx->pool) cudaFree(e.p);
-        ctx->pool.clear();
-        ctx->pool_bytes = 0;
-        rc = dev_alloc(ctx, p, count);
-    }
-    return rc;
-}
-
-template <class T>
-inline void pool_free(pgp_ctx* ctx, T*& p, size_t count) {
+inline void dev_free(pgp_ctx* ctx, void* p) {
     if (!p) return;
-    size_t bytes = count * sizeof(T);
-    if (bytes >= pgp_ctx::kPoolMin && ctx->pool_bytes + bytes <= pgp_ctx::kPoolCap) {
-        ctx->pool.push_back({(void*)p, bytes});
+    auto it = ctx->live.find(p);
+    if (it == ctx->live.end()) {        // not ours (should not happen): release it the slow way
+        cudaFree(p);
+        return;
+    }
+    const size_t bytes = it->second;
+    ctx->live.erase(it);
+    if (ctx->pool_bytes + bytes <= pgp_ctx::kPoolCap && ctx->pool.size() < pgp_ctx::kPoolMaxEntries) {
+        ctx->pool.push_back({p, bytes});
         ctx->pool_bytes += bytes;
     } else {
         cudaFree(p);
     }
+}
+
+template <class T>
+inline int dev_alloc(pgp_ctx* ctx, T** p, size_t count) {
+    return dev_alloc_bytes(ctx, reinterpret_cast<void**>(p), count * sizeof(T));
+}
+
+// historical names of the large-buffer path (same cache)
+template <class T>
+inline int pool_alloc(pgp_ctx* ctx, T** p, size_t count) {
+    return dev_alloc(ctx, p, count);
+}
+
+template <class T>
+inline void pool_free(pgp_ctx* ctx, T*& p, size_t /*count*/) {
+    dev_free(ctx, p);
     p = nullptr;
 }
 

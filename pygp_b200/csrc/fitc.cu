@@ -334,7 +334,7 @@ int ensure_part(pgp_fitc* f, size_t need) {
     if (f->part_doubles >= need) return 0;
     pgp_ctx* ctx = f->ctx;
     PGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    cudaFree(f->d_part);
+    dev_free(ctx, f->d_part);
     f->d_part = nullptr;
     f->part_doubles = 0;
     PGP_TRY(dev_alloc(ctx, &f->d_part, need));
@@ -394,11 +394,11 @@ void fitc_free(pgp_fitc* f) {
                         &f->d_rs, &f->d_c, &f->d_alpha, &f->d_q, &f->d_cw, &f->d_bb, &f->d_a, &f->d_b, &f->d_t,
                         &f->d_w, &f->d_P, &f->d_Cuu, &f->d_part, &f->d_res};
     for (double** q : small) {
-        cudaFree(*q);
+        dev_free(ctx, *q);
         *q = nullptr;
     }
-    cudaFree(f->d_spec);
-    cudaFree(f->d_info);
+    dev_free(ctx, f->d_spec);
+    dev_free(ctx, f->d_info);
 }
 
 }  // namespace
@@ -735,9 +735,9 @@ static int fitc_predict_impl(pgp_fitc* f, const double* Xs, int64_t ms, double* 
         };
         rc = step();
     }
-    cudaFree(dxs);
-    cudaFree(dzs);
-    cudaFree(dout);
+    dev_free(ctx, dxs);
+    dev_free(ctx, dzs);
+    dev_free(ctx, dout);
     return rc;
 }
 
@@ -815,8 +815,8 @@ extern "C" int pgp_fitc_full_posterior(pgp_fitc* f, const double* Xs, int64_t ms
     pool_free(ctx, LK, (size_t)ms * ldp);
     pool_free(ctx, RK, (size_t)ms * ldp);
     pool_free(ctx, S, (size_t)ms * lds);
-    cudaFree(dxs);
-    cudaFree(dzs);
-    cudaFree(dout);
+    dev_free(ctx, dxs);
+    dev_free(ctx, dzs);
+    dev_free(ctx, dout);
     return rc;
 }

@@ -428,7 +428,7 @@ int launch_gemm(pgp_ctx* ctx, const GemmArgs& a_in) {
             size_t need = (size_t)S * a.M * a.ldws;
             if (ctx->gemm_ws_doubles < need) {
                 PGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-                if (ctx->gemm_ws) cudaFree(ctx->gemm_ws);
+                if (ctx->gemm_ws) dev_free(ctx, ctx->gemm_ws);
                 ctx->gemm_ws = nullptr;
                 ctx->gemm_ws_doubles = 0;
                 PGP_TRY(dev_alloc(ctx, &ctx->gemm_ws, need));
