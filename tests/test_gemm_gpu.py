@@ -57,7 +57,8 @@ def test_gemm_tri_skips_upper_tiles():
     nt.assert_array_equal(C[128:256, 256:], C0[128:256, 256:])
 
 
-@pytest.mark.parametrize('n,extra', [(1, 0), (63, 1), (64, 1), (65, 2), (128, 1), (200, 0), (513, 3), (1000, 1)])
+@pytest.mark.parametrize('n,extra', [(1, 0), (63, 1), (64, 1), (65, 2), (128, 1), (200, 0), (513, 3), (1000, 1),
+                                     (1536, 1), (2100, 2), (3333, 1)])       # >= 1536: lookahead path
 def test_potrf_with_extra_rows(n, extra):
     import torch
     _lib, ctx, L = _ctx()
@@ -164,3 +165,44 @@ def test_trsm_forms(n, rows, notrans):
     # notrans: X T = B  ->  X = (T^-T B^T)^T ; else X T^T = B -> X = (T^-1 B^T)^T
     ref = sla.solve_triangular(T, B.T, lower=True, trans=1 if notrans else 0).T
     nt.assert_allclose(X, ref, rtol=1e-10, atol=1e-10)
+
+
+@pytest.mark.parametrize('tA,tB', [(0, 0), (0, 1), (1, 1), (1, 0)])
+@pytest.mark.parametrize('m,n,k', [(2048, 1920, 300), (1601, 1537, 67), (4000, 700, 129)])
+def test_gemm_large_tile_forms(tA, tB, m, n, k):
+    """Shapes with more 128 x 128 tiles than SMs, so the large-tile kernel runs
+    (the small shapes above all take the 64 x 64 variant): interior fast loop,
+    ragged edges and a k tail, in every operand layout."""
+    import torch
+    _lib, ctx, L = _ctx()
+    rng = np.random.RandomState(m + n + k + tA + 2*tB)
+    ev = lambda x: x + (x % 2)
+    A, B = rng.randn(m, k), rng.randn(n, k)
+    As = np.zeros((k, ev(m))) if tA else np.zeros((m, ev(k) + 2))
+    Bs = np.zeros((k, ev(n) + 2)) if tB else np.zeros((n, ev(k)))
+    if tA: As[:, :m] = A.T
+    else: As[:, :k] = A
+    if tB: Bs[:, :n] = B.T
+    else: Bs[:, :k] = B
+    ldc = ev(n)
+    C0 = rng.randn(m, ldc)
+    dA, dB, dC = (torch.tensor(x, device='cuda') for x in (As, Bs, C0))
+    torch.cuda.synchronize()
+    _lib.check(ctx, L.pgp_dev_gemm(ctx.handle, tA, tB, m, n, k, 1.5, dA.data_ptr(), As.shape[1], dB.data_ptr(),
+                                   Bs.shape[1], -1.0, dC.data_ptr(), ldc, 0, 1))
+    ctx.sync()
+    ref = C0.copy()
+    ref[:, :n] = -C0[:, :n] + 1.5*(A @ B.T)
+    nt.assert_allclose(dC.cpu().numpy(), ref, rtol=1e-12, atol=1e-12*np.sqrt(k))
+
+
+def test_potrf_reports_failing_minor_lookahead():
+    """same on the two-stream lookahead path (n >= 1536), failing inside a later panel"""
+    import torch
+    _lib, ctx, L = _ctx()
+    n = 2000
+    K = np.eye(n)
+    K[1700, 1700] = -1.0
+    dF = torch.tensor(K, device='cuda')
+    torch.cuda.synchronize()
+    assert L.pgp_dev_potrf(ctx.handle, dF.data_ptr(), n, n, 0) == 1701
