@@ -93,7 +93,8 @@ __global__ void __launch_bounds__(256) potrf_base_kernel(double* F, int64_t ld, 
                 for (int x = 0; x < 4; ++x) {
                     int r = ty + 16 * x;
                     if (r > k) a[x][kb] = li[x];
-                    else if (r == k) a[x][kb] = (d > 0.0) ? sqrt(d) : nan("");
+                    else if (r == k) a[x][kb] = d * inv;   // = sqrt(d) to ~1 ulp (NaN if not PD); a full sqrt() here sits on
+                                                           // the per-column critical path of the whole warp
                 }
             }
             buf ^= 1;
