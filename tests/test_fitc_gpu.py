@@ -3,7 +3,6 @@ pygp/inference/fitc.py:66-232) with the oracle, the committed reference
 outputs and the survey's known answer.  Tolerances: 1e-10 relative on lZ / mu /
 s2, 1e-8 on gradients (BASELINE.json north_star)."""
 
-import copy
 
 import numpy as np
 import numpy.testing as nt

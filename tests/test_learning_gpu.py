@@ -147,7 +147,6 @@ def test_sharding_single_rank_uses_device_path():
     """pygp_b200.sharding without a process group (world size 1) runs the real
     batched device calls; the N > 1 logic is covered on CPU (tests/test_sharding.py)
     and on GPUs by tools/dist_check.py."""
-    import copy
     import pygp_b200 as pygp
     from pygp_b200 import sharding
     X, y, Xs = synthetic_problem(150, 3, 17)
