@@ -619,8 +619,9 @@ extern "C" int pgp_fitc_loglike(pgp_fitc* f, int want_grad, double* lZ, double* 
     PGP_TRY(gemm(ctx, f->d_Bt, ldp, 1, f->d_Wt, ldp, 1, f->d_P, ldp, p, p, n, 1.0, 0.0, 0, 0));     // P = B W^T
     // Cuu = Bt^T diag(q) Bt - P P^T - w w^T
     PGP_TRY(scale_rows(f, f->d_Bt, f->d_T, f->d_q, 0));
-    PGP_TRY(gemm(ctx, f->d_T, ldp, 1, f->d_Bt, ldp, 1, f->d_Cuu, ldp, p, p, n, 1.0, 0.0, 0, 0));
-    PGP_TRY(gemm(ctx, f->d_P, ldp, 0, f->d_P, ldp, 0, f->d_Cuu, ldp, p, p, p, -1.0, 1.0, 0, 1));
+    // (symmetric: only its lower tiles are formed; the trace doubles the strict lower part)
+    PGP_TRY(gemm(ctx, f->d_T, ldp, 1, f->d_Bt, ldp, 1, f->d_Cuu, ldp, p, p, n, 1.0, 0.0, /*tri=*/1, 0));
+    PGP_TRY(gemm(ctx, f->d_P, ldp, 0, f->d_P, ldp, 0, f->d_Cuu, ldp, p, p, p, -1.0, 1.0, /*tri=*/1, 1));
     {
         Launch Lc(ctx, PC_OTHER, 16.0 * p * p);
         rank1_sub_kernel<<<flat_grid(p * p), 256, 0, s>>>(f->d_Cuu, ldp, p, f->d_w);
@@ -648,9 +649,10 @@ extern "C" int pgp_fitc_loglike(pgp_fitc* f, int want_grad, double* lZ, double* 
     t.single_type = single_type(&f->spec);
     t.ldw = ldp;
     t.Z1 = f->d_ZU; t.Z2 = f->d_ZU; t.n1 = p; t.n2 = p;
-    t.mode = 0; t.Wd = f->d_Cuu;
+    t.mode = 0; t.Wd = f->d_Cuu; t.sym = 1;
     PGP_TRY(launch_trace_rect(ctx, t));
     t.Z1 = f->d_ZX; t.n1 = n;
+    t.sym = 0;
     t.mode = 1; t.Bt = f->d_Bt; t.T2 = f->d_T; t.al = f->d_alpha; t.q = f->d_q; t.wv = f->d_w;
     PGP_TRY(launch_trace_rect(ctx, t));
     double* hp = ctx->h_pin;

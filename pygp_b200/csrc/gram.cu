@@ -580,7 +580,12 @@ __global__ void __launch_bounds__(kThreads) trace_rect_kernel(TraceRectArgs a, i
                 const int64_t gj = j0 + t.col(y);
                 double w = 0.0;
                 if (rok && gj < a.n2) {
-                    if (a.mode == 0) w = a.Wd[gi * a.ldw + gj];
+                    if (a.mode == 0) {
+                        // sym: only the lower triangle of a symmetric weight matrix is stored
+                        if (!a.sym) w = a.Wd[gi * a.ldw + gj];
+                        else if (gj < gi) w = 2.0 * a.Wd[gi * a.ldw + gj];
+                        else if (gj == gi) w = a.Wd[gi * a.ldw + gj];
+                    }
                     else w = 2.0 * (ai * a.wv[gj] - qi * a.Bt[gi * a.ldw + gj] + a.T2[gi * a.ldw + gj]);
                 }
                 wq[x][y] = w;

@@ -60,6 +60,7 @@ struct TraceRectArgs {
     int64_t n1 = 0, n2 = 0;
     int ndim = 0, n_parts = 0, nhyper = 0;
     int mode = 0;
+    int sym = 0;                     // mode 0, n1 == n2, X1 == X2: Wd holds the lower triangle of a symmetric W
     const double* Wd = nullptr;      // mode 0: (n1, ldw)
     const double* Bt = nullptr;      // mode 1: (n1, ldw)
     const double* T2 = nullptr;      // mode 1: (n1, ldw)
