@@ -320,8 +320,7 @@ def run_ours(args):
     gp = make_gp()
     gp.add_data(Xh, yh)
     extra = {}
-    m_total = args.predict_pts
-    m_loc = m_total // world
+    m_loc = args.predict_pts            # per rank: test points shard with no collective (weak scaling, like `value`)
     Xs = torch.rand(m_loc, d, dtype=torch.float64, device='cuda',
                     generator=torch.Generator('cuda').manual_seed(1 + rank))
     mu = torch.empty(m_loc, dtype=torch.float64, device='cuda')
@@ -433,7 +432,7 @@ def main():
     ap.add_argument('--n', type=int, default=32768)
     ap.add_argument('--d', type=int, default=16)
     ap.add_argument('--cpu-n', type=int, default=3072, dest='cpu_n')
-    ap.add_argument('--predict-pts', type=int, default=16384, dest='predict_pts')
+    ap.add_argument('--predict-pts', type=int, default=16384, dest='predict_pts', help='test points per rank')
     ap.add_argument('--no-cpu', action='store_true', dest='no_cpu')
     args = ap.parse_args()
     if args.impl == 'reference':
