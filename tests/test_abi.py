@@ -120,3 +120,24 @@ def test_hyper_roundtrip_and_names():
     assert [p[0] for p in g2._params()] == ['like.sigma', 'kern.part0.sf', 'kern.part0.ell',
                                             'kern.part1.sf', 'kern.part1.ell', 'kern.part1.alpha', 'mean']
     assert repr(gp).startswith('BasicGP(sn=')
+
+
+def _build_c_client(built, tmp_path):
+    exe = str(tmp_path / 'c_smoke')
+    libdir = os.path.dirname(built.LIB_PATH)
+    subprocess.check_call(['gcc', '-std=c99', '-Wall', '-Wextra', '-pedantic', '-Werror', '-I', os.path.join(ROOT, 'include'),
+                           os.path.join(ROOT, 'tests', 'c_abi', 'smoke.c'), '-o', exe, '-L', libdir, '-lpygp_b200',
+                           '-Wl,-rpath,' + libdir, '-lm'])
+    return exe
+
+
+def test_header_is_plain_c_and_links(built, tmp_path):
+    """include/pygp_b200.h is a C header (strict C99, no torch / C++ types) and a
+    plain-C client links against the library; without a device it fails loudly."""
+    import torch
+    exe = _build_c_client(built, tmp_path)
+    if torch.cuda.is_available():
+        pytest.skip('a GPU is present (tests/test_exact_gpu.py runs the client)')
+    p = subprocess.run([exe], capture_output=True, text=True)
+    assert p.returncode == 2
+    assert 'no CPU fallback' in p.stderr

@@ -355,3 +355,38 @@ def test_full_posterior_and_sample(name, golden):
     assert gp.sample(Xj, rng=0).shape == (len(Xj),)
     gp.reset()                                         # prior draws
     assert gp.sample(Xj, 2, rng=1).shape == (2, len(Xj))
+
+
+def test_plain_c_client_matches_python_host(tmp_path):
+    """tests/c_abi/smoke.c drives the C ABI with no Python in the process; the
+    Python host package on the same inputs must give the same numbers."""
+    import os
+    import subprocess
+    import pygp_b200 as pygp
+    from pygp_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    exe = str(tmp_path / 'c_smoke')
+    subprocess.check_call(['gcc', '-std=c99', '-I', os.path.join(root, 'include'), os.path.join(root, 'tests', 'c_abi', 'smoke.c'),
+                           '-o', exe, '-L', libdir, '-lpygp_b200', '-Wl,-rpath,' + libdir, '-lm'])
+    p = subprocess.run([exe], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    assert 'not positive definite' in p.stderr            # the singular update came back as info > 0
+    vals = np.array([float(v) for v in p.stdout.split()])
+    # the client's LCG inputs, regenerated here
+    N, D, M = 200, 3, 3
+    s, out = 12345, []
+    for _ in range(N*D + M*D):
+        s = (s*1664525 + 1013904223) % 2**32
+        out.append((s >> 8)/16777216.0)
+    X, Xs = np.array(out[:N*D]).reshape(N, D), np.array(out[N*D:]).reshape(M, D)
+    y = np.sin(3.0*X.sum(1))
+    gp = pygp.inference.ExactGP(pygp.likelihoods.Gaussian(0.1), pygp.kernels.SE(1.2, [0.5, 0.6, 0.7]), 0.05)
+    gp.add_data(X, y)
+    lZ, dlZ = gp.loglikelihood(True)
+    mu, s2 = gp.posterior(Xs)
+    ref = np.r_[lZ, dlZ, mu, s2]
+    nt.assert_allclose(vals, ref, rtol=1e-12, atol=1e-13)
+    ogp = OExactGP(0.1, make_kernel(('se', 1.2, [0.5, 0.6, 0.7])), 0.05)
+    ogp.add_data(X, y)
+    nt.assert_allclose(vals[0], ogp.loglikelihood(), rtol=LZ_RTOL)
