@@ -192,6 +192,13 @@ int pgp_fitc_create(pgp_ctx* ctx, const pgp_kernel_spec* spec,
                     const double* X, const double* y, int64_t n,
                     pgp_fitc** out);
 void pgp_fitc_destroy(pgp_fitc* f);
+/* DTC (pygp/inference/dtc.py:20-199) shares FITC's state and entry points: a handle
+ * created here makes pgp_fitc_update / _loglike / _predict / _predict_grad /
+ * _full_posterior follow dtc.py:54-75, 137-199, 94-135, 77-92 instead. */
+int pgp_dtc_create(pgp_ctx* ctx, const pgp_kernel_spec* spec,
+                   const double* U, int64_t nu,
+                   const double* X, const double* y, int64_t n,
+                   pgp_fitc** out);
 /* FITC._update (fitc.py:66-100) */
 int pgp_fitc_update(pgp_fitc* f, const double* hyp);
 /* FITC.loglikelihood(grad) (fitc.py:167-232) */

@@ -93,3 +93,60 @@ def fitc_loglike(kernel, st, U, X, grad=False):
         dlZ[h] = 0.5*(d0[0]*sq + np.sum(duu*Cuu) + np.sum(dxu*Cxu))
     dlZ[-1] = np.sum(alpha)
     return lZ, dlZ
+
+
+# -- DTC (pygp/inference/dtc.py:54-199) in the same device formulation ----------------
+#   Luu = chol(Kuu + su2 I) (lower);  Lux = chol(Kuu + su2 I + Kxu^T Kxu / sn2),  a = Lux^-1 Kxu^T r
+#   Vs = Kxu Luu^-T / ell, ell = sqrt(sn2);  rs = r / ell;  Al = chol(I + Vs^T Vs);  beta = Al^-1 Vs^T rs
+#   alpha = rs - Vs Al^-T beta;  Bt = Vs Luu^-1;  Wt = Vs Al^-T;  w = Bt^T alpha;  v = Vs^T alpha
+#   P = Bt^T Wt;  VW = Vs^T Wt;  C = Bt^T Bt - P P^T - w w^T;  T2 = Wt P^T
+#   dlZ_h = 1/2 sum(dKuu_h o C) + (1 / (2 ell)) sum(dKxu_h o 2 (alpha w^T - Bt + T2))
+
+def dtc_update(kernel, sn2, mean, U, X, y):
+    su2 = sn2 * 1e-6
+    p = U.shape[0]
+    Kuu = kernel.get(U)
+    Luu = sla.cholesky(Kuu + su2*np.eye(p), lower=True)
+    Kxu = kernel.get(X, U)
+    r = y - mean
+    Lux = sla.cholesky(Kuu + su2*np.eye(p) + Kxu.T.dot(Kxu)/sn2, lower=True)
+    a = sla.solve_triangular(Lux, Kxu.T.dot(r), lower=True)
+    ell = np.sqrt(sn2)
+    Vs = sla.solve_triangular(Luu, Kxu.T, lower=True).T / ell
+    rs = r / ell
+    Al = sla.cholesky(np.eye(p) + Vs.T.dot(Vs), lower=True)
+    beta = sla.solve_triangular(Al, Vs.T.dot(rs), lower=True)
+    return dict(Luu=Luu, Lux=Lux, a=a, Vs=Vs, rs=rs, Al=Al, beta=beta, sn2=sn2, su2=su2, ell=ell, mean=mean)
+
+
+def dtc_predict(kernel, st, U, Xs):
+    Ksu = kernel.get(Xs, U)
+    b = sla.solve_triangular(st['Luu'], Ksu.T, lower=True).T
+    c = sla.solve_triangular(st['Lux'], Ksu.T, lower=True).T
+    mu = st['mean'] + c.dot(st['a'])/st['sn2']
+    s2 = kernel.dget(Xs) + (np.sum(c**2, axis=1) - np.sum(b**2, axis=1))
+    return mu, s2
+
+
+def dtc_loglike(kernel, st, U, X, grad=False):
+    Luu, Al, Vs, rs, beta = st['Luu'], st['Al'], st['Vs'], st['rs'], st['beta']
+    su2, ell = st['su2'], st['ell']
+    n = X.shape[0]
+    lZ = -np.sum(np.log(np.diag(Al))) - n*np.log(ell) - 0.5*(rs.dot(rs) - beta.dot(beta)) - 0.5*n*np.log(2*np.pi)
+    if not grad:
+        return lZ
+    alpha = rs - Vs.dot(sla.solve_triangular(Al, beta, lower=True, trans=1))
+    Bt = sla.solve_triangular(Luu, Vs.T, lower=True, trans=1).T          # Vs Luu^-1
+    Wt = sla.solve_triangular(Al, Vs.T, lower=True).T                    # Vs Al^-T
+    w, v = Bt.T.dot(alpha), Vs.T.dot(alpha)
+    P, VW = Bt.T.dot(Wt), Vs.T.dot(Wt)
+    C = Bt.T.dot(Bt) - P.dot(P.T) - np.outer(w, w)
+    Cxu = 2*(np.outer(alpha, w) - Bt + Wt.dot(P.T))
+    nk = kernel.nhyper
+    dlZ = np.zeros(nk + 2)
+    dlZ[0] = -(-rs.dot(rs) + beta.dot(beta) + v.dot(v) + su2*w.dot(w) + n - np.sum(Vs**2) + np.sum(VW**2)
+               - su2*(np.sum(Bt**2) - np.sum(P**2)))
+    for h, (duu, dxu) in enumerate(zip(kernel.grad(U), kernel.grad(X, U)), 1):
+        dlZ[h] = 0.5*np.sum(duu*C) + 0.5/ell*np.sum(dxu*Cxu)
+    dlZ[-1] = np.sum(alpha)/ell
+    return lZ, dlZ

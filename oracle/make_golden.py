@@ -15,9 +15,9 @@ import sys
 import numpy as np
 
 from . import ref_loader
-from .cases import (KERNEL_CASES, GP_CASES, GP_SN, GP_MEAN, kernel_inputs,
+from .cases import (KERNEL_CASES, GP_CASES, DTC_CASES, GP_SN, GP_MEAN, kernel_inputs,
                     gp_inputs)
-from .pygp_oracle import make_kernel, OExactGP, OFITC
+from .pygp_oracle import make_kernel, OExactGP, OFITC, ODTC
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 GOLDEN = os.path.join(os.path.dirname(HERE), 'tests', 'golden')
@@ -124,12 +124,48 @@ def gp_golden(pygp):
     return out
 
 
+def dtc_golden(pygp):
+    out = {}
+    for name, (spec, N, d) in DTC_CASES.items():
+        X, y, Xs, U = gp_inputs(N, d, True)
+        rgp = pygp.inference.DTC(pygp.likelihoods.Gaussian(GP_SN), ref_loader.ref_kernel(pygp, spec), GP_MEAN, U)
+        ogp = ODTC(GP_SN, make_kernel(spec), GP_MEAN, U)
+        rgp.add_data(X, y)
+        ogp.add_data(X, y)
+        rec = {}
+        for tag, h in (('', None), ('_h2', rgp.get_hyper() + 0.05*np.random.RandomState(11).randn(rgp.nhyper))):
+            if h is not None:
+                rgp.set_hyper(h)
+                ogp.set_hyper(h)
+                rec['hyper2'] = h
+            lZ, dlZ = rgp.loglikelihood(True)
+            mu, s2, dmu, ds2 = rgp.posterior(Xs, grad=True)
+            fmu, fS = rgp._full_posterior(Xs)
+            olZ, odlZ = ogp.loglikelihood(True)
+            omu, os2, odmu, ods2 = ogp.posterior(Xs, grad=True)
+            _close(olZ, lZ, name + '.lZ' + tag)
+            _close(odlZ, dlZ, name + '.dlZ' + tag, 1e-9, 1e-10)
+            _close(omu, mu, name + '.mu' + tag, 1e-10, 1e-12)
+            _close(os2, s2, name + '.s2' + tag, 1e-9, 1e-12)
+            _close(odmu, dmu, name + '.dmu' + tag, 1e-9, 1e-11)
+            _close(ods2, ds2, name + '.ds2' + tag, 1e-8, 1e-11)
+            _close(ogp.full_posterior(Xs)[1], fS, name + '.Sigma' + tag, 1e-8, 1e-11)
+            rec.update({'lZ' + tag: lZ, 'dlZ' + tag: dlZ, 'mu' + tag: mu, 's2' + tag: s2, 'dmu' + tag: dmu,
+                        'ds2' + tag: ds2, 'full_Sigma' + tag: fS})
+        rec['hyper'] = ogp.get_hyper() if False else None
+        rec.pop('hyper')
+        for k, v in rec.items():
+            out['%s/%s' % (name, k)] = np.asarray(v)
+    return out
+
+
 def main():
     pygp = ref_loader.load()
     os.makedirs(GOLDEN, exist_ok=True)
     kg = kernel_golden(pygp)
     np.savez_compressed(os.path.join(GOLDEN, 'kernels.npz'), **kg)
     gg = gp_golden(pygp)
+    gg.update(dtc_golden(pygp))
     np.savez_compressed(os.path.join(GOLDEN, 'gp.npz'), **gg)
     # the reference's own demo data set (pygp/demos/xy.npz, X:(20,1) y:(20,)), used by
     # its tests/test_learning.py:26-30 -- a data fixture, copied verbatim

@@ -25,7 +25,7 @@ import scipy.linalg as sla
 import scipy.spatial.distance as ssd
 
 __all__ = ['make_kernel', 'OSE', 'OMatern', 'OPeriodic', 'ORQ', 'OSum',
-           'OProduct', 'OExactGP', 'OFITC', 'synthetic_problem']
+           'OProduct', 'OExactGP', 'OFITC', 'ODTC', 'synthetic_problem']
 
 
 # -- distances: pygp/kernels/_distances.py:17-52 ------------------------------
@@ -730,6 +730,138 @@ class OFITC(object):
                 + np.inner(alpha, v*alpha) + np.inner(np.sum(W**2, axis=0), v)
                 + np.sum(M.dot(W.T) * B.dot(W.T))) / 2.0
         dlZ[-1] = np.sum(alpha)
+        return lZ, dlZ
+
+
+# -- DTC: pygp/inference/dtc.py:20-199 ------------------------------------------
+
+class ODTC(object):
+    def __init__(self, sn, kernel, mean, U):
+        self._logsn = np.log(float(sn))
+        self._kernel = kernel
+        self._mean = float(mean)
+        self._U = np.array(U, ndmin=2, dtype=float, copy=True)      # dtc.py:31
+        self._X = self._y = None
+        self._Ruu = self._Rux = self._a = None
+        self.nhyper = 1 + kernel.nhyper + 1
+
+    @property
+    def s2(self):
+        return np.exp(self._logsn*2)
+
+    @property
+    def ndata(self):
+        return 0 if self._X is None else self._X.shape[0]
+
+    def get_hyper(self):
+        return np.r_[self._logsn, self._kernel.get_hyper(), self._mean]
+
+    def set_hyper(self, hyper):
+        hyper = np.asarray(hyper, dtype=float)
+        self._logsn = hyper[0]
+        self._kernel.set_hyper(hyper[1:1+self._kernel.nhyper])
+        self._mean = hyper[-1]
+        if self.ndata > 0:
+            self._update()
+
+    def add_data(self, X, y):
+        X = np.array(X, ndmin=2, dtype=float)
+        y = np.array(y, ndmin=1, dtype=float)
+        if self._X is None:
+            self._X, self._y = X.copy(), y.copy()
+        else:
+            self._X = np.r_[self._X, X]
+            self._y = np.r_[self._y, y]
+        self._update()
+
+    def _update(self):
+        # dtc.py:54-75
+        p = self._U.shape[0]
+        su2 = self.s2 * 1e-6
+        Kuu = self._kernel.get(self._U)
+        self._Ruu = sla.cholesky(Kuu + su2 * np.eye(p))
+        Kux = self._kernel.get(self._U, self._X)
+        S = Kuu + np.dot(Kux, Kux.T) / self.s2
+        r = self._y - self._mean
+        self._Rux = sla.cholesky(S + su2 * np.eye(p))
+        self._a = sla.solve_triangular(self._Rux, np.dot(Kux, r), trans=True)
+
+    def full_posterior(self, X):
+        # dtc.py:77-92
+        X = np.array(X, ndmin=2, dtype=float)
+        mu = np.full(X.shape[0], self._mean)
+        Sigma = self._kernel.get(X)
+        if self._X is not None:
+            K = self._kernel.get(self._U, X)
+            b = sla.solve_triangular(self._Ruu, K, trans=True)
+            c = sla.solve_triangular(self._Rux, K, trans=True)
+            mu += np.dot(c.T, self._a) / self.s2
+            Sigma += -np.dot(b.T, b) + np.dot(c.T, c)
+        return mu, Sigma
+
+    def sample(self, X, m=None, latent=True, rng=None):
+        return _gp_sample(self, X, m, latent, rng)
+
+    def posterior(self, X, grad=False):
+        # dtc.py:94-135 (the input-gradient of the mean is NOT divided by sn2 in the
+        # reference, dtc.py:127 -- kept, parity is with the reference as it is)
+        X = np.array(X, ndmin=2, dtype=float)
+        mu = np.full(X.shape[0], self._mean)
+        s2 = self._kernel.dget(X)
+        if self._X is not None:
+            K = self._kernel.get(self._U, X)
+            b = sla.solve_triangular(self._Ruu, K, trans=True)
+            c = sla.solve_triangular(self._Rux, K, trans=True)
+            mu += np.dot(c.T, self._a) / self.s2
+            s2 += -np.sum(b * b, axis=0) + np.sum(c * c, axis=0)
+        if not grad:
+            return mu, s2
+        dmu = np.zeros_like(X)
+        ds2 = np.zeros_like(X)
+        if self._X is not None:
+            dK = self._kernel.grady(self._U, X)
+            dK = dK.reshape(self._U.shape[0], -1)
+            db = sla.solve_triangular(self._Ruu, dK, trans=True)
+            db = np.rollaxis(np.reshape(db, (-1,) + X.shape), 2)
+            dc = sla.solve_triangular(self._Rux, dK, trans=True)
+            dmu += np.dot(dc.T, self._a).reshape(X.shape)
+            dc = np.rollaxis(np.reshape(dc, (-1,) + X.shape), 2)
+            ds2 += -2 * np.sum(db * b, axis=1).T + 2 * np.sum(dc * c, axis=1).T
+        return mu, s2, dmu, ds2
+
+    def loglikelihood(self, grad=False):
+        # dtc.py:137-199
+        sn2 = self.s2
+        su2 = sn2 * 1e-6
+        ell = np.sqrt(sn2)
+        Kux = self._kernel.get(self._U, self._X)
+        r = self._y.copy() - self._mean
+        r /= ell
+        V = sla.solve_triangular(self._Ruu, Kux, trans=True)
+        V /= ell
+        p = self._U.shape[0]
+        A = sla.cholesky(np.eye(p) + np.dot(V, V.T))
+        beta = sla.solve_triangular(A, V.dot(r), trans=True)
+        lZ = -np.sum(np.log(np.diag(A))) - self.ndata * np.log(ell)
+        lZ -= 0.5 * (np.inner(r, r) - np.inner(beta, beta))
+        lZ -= 0.5 * self.ndata * np.log(2*np.pi)
+        if not grad:
+            return lZ
+        alpha = (r - V.T.dot(sla.solve_triangular(A, beta)))
+        B = sla.solve_triangular(self._Ruu, V)
+        W = sla.solve_triangular(A, V, trans=True)
+        VW = np.dot(V, W.T)
+        BW = np.dot(B, W.T)
+        w = B.dot(alpha)
+        v = V.dot(alpha)
+        dlZ = np.zeros(self.nhyper)
+        dlZ[0] = -(- np.inner(r, r) + np.inner(beta, beta) + np.inner(v, v) + su2 * np.inner(w, w)
+                   + self.ndata - np.sum(V**2) + np.sum(VW**2) - su2 * (np.sum(B**2) - np.sum(BW**2)))
+        dK = zip(self._kernel.grad(self._U), self._kernel.grad(self._U, self._X))
+        for i, (dKuu, dKux) in enumerate(dK, 1):
+            M = 2 * dKux / ell - dKuu.dot(B)
+            dlZ[i] = -0.5 * (- np.inner(w, np.dot(M, alpha)) + np.sum(M*B) - np.sum(M.dot(W.T) * B.dot(W.T)))
+        dlZ[-1] = np.sum(alpha) / ell
         return lZ, dlZ
 
 

@@ -84,6 +84,7 @@ SIGNATURES = {
     'pgp_batched_loglike': (C.c_int, [_vp, _sp, _dp, _dp, _i64, _dp, _i64, _dp, _ip]),
     'pgp_batched_predict': (C.c_int, [_vp, _sp, _dp, _dp, _i64, _dp, _i64, _dp, _i64, _dp, _dp, _ip]),
     'pgp_fitc_create': (C.c_int, [_vp, _sp, _dp, _i64, _dp, _dp, _i64, C.POINTER(_vp)]),
+    'pgp_dtc_create': (C.c_int, [_vp, _sp, _dp, _i64, _dp, _dp, _i64, C.POINTER(_vp)]),
     'pgp_fitc_destroy': (None, [_vp]),
     'pgp_fitc_update': (C.c_int, [_vp, _dp]),
     'pgp_fitc_loglike': (C.c_int, [_vp, C.c_int, _dp, _dp]),

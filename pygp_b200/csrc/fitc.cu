@@ -37,6 +37,7 @@ using namespace pgp;
 
 struct pgp_fitc {
     pgp_ctx* ctx = nullptr;
+    int dtc = 0;                    // 1: deterministic training conditional (pygp/inference/dtc.py) on the same state
     pgp_kernel_spec spec;
     int ndim = 0;
     int64_t n = 0, p = 0, ldp = 0;
@@ -53,7 +54,7 @@ struct pgp_fitc {
     double *d_q = nullptr, *d_cw = nullptr, *d_bb = nullptr;                       // (n)
     double *d_a = nullptr, *d_b = nullptr, *d_t = nullptr, *d_w = nullptr;         // (ldp) row vectors
     double *d_Bt = nullptr, *d_Wt = nullptr, *d_T = nullptr;                       // (n, ldp), gradient only
-    double *d_P = nullptr, *d_Cuu = nullptr;                                       // (p, ldp)
+    double *d_P = nullptr, *d_Cuu = nullptr, *d_VW = nullptr;                      // (p, ldp)
     double* d_part = nullptr;       // partial sums (gemv_t / trace)
     size_t part_doubles = 0;
     double* d_res = nullptr;        // [0] lZ, [1..] dlZ, scratch scalars after
@@ -95,8 +96,9 @@ __device__ __forceinline__ double kernel_diag(const DevSpecHdr& S) {
 
 // one warp per row: ell_i = sqrt(kxx + sn2 - |Vt_i|^2); Vt_i /= ell_i;
 // rs_i = (y_i - mean)/ell_i; c_i = (y_i - mean)/ell_i^2        (fitc.py:87-91)
+// dtc: ell = sqrt(sn2) for every point (dtc.py:140-147)
 __global__ void fitc_ell_kernel(double* V, int64_t ld, int64_t n, int64_t p, const double* y, const DevSpec* spec,
-                                double* ell, double* rs, double* c) {
+                                double* ell, double* rs, double* c, int dtc) {
     __shared__ double kd;
     if (threadIdx.x == 0) kd = kernel_diag(spec->h);
     __syncthreads();
@@ -105,9 +107,11 @@ __global__ void fitc_ell_kernel(double* V, int64_t ld, int64_t n, int64_t p, con
     if (row >= n) return;
     double* v = V + row * ld;
     double s = 0.0;
-    for (int64_t k = lane; k < p; k += 32) s += v[k] * v[k];
-    s = warp_sum(s);
-    const double l = sqrt(kd + spec->h.sn2 - s);
+    if (!dtc) {
+        for (int64_t k = lane; k < p; k += 32) s += v[k] * v[k];
+        s = warp_sum(s);
+    }
+    const double l = dtc ? sqrt(spec->h.sn2) : sqrt(kd + spec->h.sn2 - s);
     const double inv = 1.0 / l;
     for (int64_t k = lane; k < p; k += 32) v[k] = v[k] / l;
     if (lane == 0) {
@@ -118,7 +122,7 @@ __global__ void fitc_ell_kernel(double* V, int64_t ld, int64_t n, int64_t p, con
     }
 }
 
-// out[i][:] = in[i][:] * (mode 0: s_i ; mode 1: 1/s_i)
+// out[i][:] = in[i][:] * (mode 0: s_i ; mode 1: 1/s_i ; mode 2: 1)
 __global__ void scale_rows_kernel(const double* in, double* out, int64_t ld, int64_t n, int64_t p, const double* s,
                                   int mode) {
     const int lane = threadIdx.x & 31;
@@ -128,7 +132,20 @@ __global__ void scale_rows_kernel(const double* in, double* out, int64_t ld, int
     const double* a = in + row * ld;
     double* o = out + row * ld;
     if (mode == 0) for (int64_t k = lane; k < p; k += 32) o[k] = a[k] * f;
-    else for (int64_t k = lane; k < p; k += 32) o[k] = a[k] / f;
+    else if (mode == 1) for (int64_t k = lane; k < p; k += 32) o[k] = a[k] / f;
+    else for (int64_t k = lane; k < p; k += 32) o[k] = a[k];
+}
+
+// out[i] = |M_i|^2
+__global__ void rownorm2_kernel(const double* M, int64_t ld, int64_t n, int64_t p, double* out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n) return;
+    const double* m = M + row * ld;
+    double s = 0.0;
+    for (int64_t k = lane; k < p; k += 32) s += m[k] * m[k];
+    s = warp_sum(s);
+    if (lane == 0) out[row] = s;
 }
 
 // partial[blk][j] = sum_{i in block's rows} M[i][j] c[i]
@@ -152,8 +169,9 @@ __global__ void gemv_t_reduce_kernel(const double* partial, int blocks, int64_t 
 }
 
 // alpha_i = (rs_i - <Vs_i, t>)/ell_i                         (fitc.py:189)
+// dtc: alpha_i = rs_i - <Vs_i, t>                          (dtc.py:160)
 __global__ void fitc_alpha_kernel(const double* Vs, int64_t ld, int64_t n, int64_t p, const double* t,
-                                  const double* rs, const double* ell, double* alpha) {
+                                  const double* rs, const double* ell, double* alpha, int dtc) {
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= n) return;
@@ -161,7 +179,7 @@ __global__ void fitc_alpha_kernel(const double* Vs, int64_t ld, int64_t n, int64
     double s = 0.0;
     for (int64_t k = lane; k < p; k += 32) s += v[k] * t[k];
     s = warp_sum(s);
-    if (lane == 0) alpha[row] = (rs[row] - s) / ell[row];
+    if (lane == 0) alpha[row] = dtc ? rs[row] - s : (rs[row] - s) / ell[row];
 }
 
 // cw_i = |Wt_i|^2, bb_i = |Bt_i|^2, q_i = alpha_i^2 + cw_i
@@ -273,9 +291,51 @@ __global__ void fitc_grad_scalars_kernel(const DevSpec* spec, int64_t n, int64_t
     }
 }
 
+// DTC (dtc.py:170-198): res[0] = dlZ[0], res[1 + h] = 0 (traces accumulate on top), res[nk + 1] = sum(alpha) / ell
+//   dlZ[0] = -(-rs.rs + beta.beta + v.v + su2 w.w + n - sum V^2 + sum VW^2 - su2 (sum B^2 - sum BW^2))
+__global__ void dtc_grad_scalars_kernel(const DevSpec* spec, int64_t n, int64_t p, int nk, const double* rs,
+                                        const double* alpha, const double* vs2, const double* bb, const double* beta,
+                                        const double* w, const double* v, const double* P, const double* VW,
+                                        int64_t ldp, double* res) {
+    __shared__ double red[32];
+    double s_rr = 0.0, s_v2 = 0.0, s_b2 = 0.0, s_a = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+        s_rr += rs[i] * rs[i];
+        s_v2 += vs2[i];
+        s_b2 += bb[i];
+        s_a += alpha[i];
+    }
+    double s_bb = 0.0, s_ww = 0.0, s_vv = 0.0, s_pp = 0.0, s_vw = 0.0;
+    for (int64_t j = threadIdx.x; j < p; j += blockDim.x) {
+        s_bb += beta[j] * beta[j];
+        s_ww += w[j] * w[j];
+        s_vv += v[j] * v[j];
+    }
+    for (int64_t idx = threadIdx.x; idx < p * p; idx += blockDim.x) {
+        double x = P[(idx / p) * ldp + idx % p], z = VW[(idx / p) * ldp + idx % p];
+        s_pp += x * x;
+        s_vw += z * z;
+    }
+    s_rr = block_sum(s_rr, red); s_v2 = block_sum(s_v2, red); s_b2 = block_sum(s_b2, red); s_a = block_sum(s_a, red);
+    s_bb = block_sum(s_bb, red); s_ww = block_sum(s_ww, red); s_vv = block_sum(s_vv, red);
+    s_pp = block_sum(s_pp, red); s_vw = block_sum(s_vw, red);
+    if (threadIdx.x == 0) {
+        const double sn2 = spec->h.sn2, su2 = sn2 * 1e-6;
+        res[0] = -(-s_rr + s_bb + s_vv + su2 * s_ww + (double)n - s_v2 + s_vw - su2 * (s_b2 - s_pp));
+        for (int h = 0; h < nk; ++h) res[1 + h] = 0.0;
+        res[1 + nk] = s_a / sqrt(sn2);
+    }
+}
+
+// out[i] = y[i] - mean
+__global__ void residual_kernel(const double* y, const DevSpec* spec, int64_t n, double* out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = y[i] - spec->h.mean;
+}
+
 // one warp per test point: mu = mean + <RKt_i, b>; s2 = kss + (|RKt_i|^2 - |LKt_i|^2)  (fitc.py:140-141)
 __global__ void fitc_predict_reduce_kernel(const double* LK, const double* RK, int64_t ld, int64_t rows, int64_t p,
-                                           const double* b, const DevSpec* spec, double* mu, double* s2) {
+                                           const double* b, const DevSpec* spec, double* mu, double* s2, int dtc) {
     __shared__ double kd;
     if (threadIdx.x == 0) kd = kernel_diag(spec->h);
     __syncthreads();
@@ -295,7 +355,7 @@ __global__ void fitc_predict_reduce_kernel(const double* LK, const double* RK, i
     sr = warp_sum(sr);
     sl = warp_sum(sl);
     if (lane == 0) {
-        mu[row] = spec->h.mean + sm;
+        mu[row] = spec->h.mean + (dtc ? sm / spec->h.sn2 : sm);   // dtc.py:108: c^T a / sn2
         s2[row] = kd + (sr - sl);
     }
 }
@@ -392,7 +452,7 @@ void fitc_free(pgp_fitc* f) {
     pool_free(ctx, f->d_pred, (size_t)2 * f->pc_rows * f->ldp);
     double** small[] = {&f->d_X, &f->d_y, &f->d_U, &f->d_ZX, &f->d_ZU, &f->d_L, &f->d_A, &f->d_R, &f->d_ell,
                         &f->d_rs, &f->d_c, &f->d_alpha, &f->d_q, &f->d_cw, &f->d_bb, &f->d_a, &f->d_b, &f->d_t,
-                        &f->d_w, &f->d_P, &f->d_Cuu, &f->d_part, &f->d_res};
+                        &f->d_w, &f->d_P, &f->d_Cuu, &f->d_VW, &f->d_part, &f->d_res};
     for (double** q : small) {
         dev_free(ctx, *q);
         *q = nullptr;
@@ -432,12 +492,12 @@ extern "C" int pgp_fitc_create(pgp_ctx* ctx, const pgp_kernel_spec* spec, const 
     auto A = [&](double** q, size_t cnt) { if (!rc) rc = dev_alloc(ctx, q, cnt); };
     A(&f->d_X, (size_t)n * d); A(&f->d_y, n); A(&f->d_U, (size_t)p * d);
     A(&f->d_ZX, (size_t)np * n * d); A(&f->d_ZU, (size_t)np * p * d);
-    A(&f->d_L, (size_t)p * ldp); A(&f->d_A, (size_t)(p + 1) * ldp); A(&f->d_R, (size_t)p * ldp);
+    A(&f->d_L, (size_t)p * ldp); A(&f->d_A, (size_t)(p + 1) * ldp); A(&f->d_R, (size_t)(p + 1) * ldp);
     A(&f->d_ell, n); A(&f->d_rs, n); A(&f->d_c, n); A(&f->d_alpha, n);
     A(&f->d_a, ldp); A(&f->d_b, ldp); A(&f->d_t, ldp); A(&f->d_w, ldp);
     A(&f->d_res, (size_t)2 * kMaxHyper + kScal);
     if (!rc) rc = dev_alloc(ctx, &f->d_spec, 2);
-    if (!rc) rc = dev_alloc(ctx, &f->d_info, 2);
+    if (!rc) rc = dev_alloc(ctx, &f->d_info, 4);
     if (!rc) rc = pool_alloc(ctx, &f->d_Vs, (size_t)n * ldp);
     if (!rc) rc = pool_alloc(ctx, &f->d_Kc, (size_t)f->kc_rows * ldp);
     if (rc) {
@@ -457,6 +517,13 @@ extern "C" int pgp_fitc_create(pgp_ctx* ctx, const pgp_kernel_spec* spec, const 
     return 0;
 }
 
+extern "C" int pgp_dtc_create(pgp_ctx* ctx, const pgp_kernel_spec* spec, const double* U, int64_t nu, const double* X,
+                              const double* y, int64_t n, pgp_fitc** out) {
+    int rc = pgp_fitc_create(ctx, spec, U, nu, X, y, n, out);
+    if (rc == 0) (*out)->dtc = 1;
+    return rc;
+}
+
 extern "C" void pgp_fitc_destroy(pgp_fitc* f) {
     if (!f) return;
     cudaSetDevice(f->ctx->device);
@@ -474,11 +541,11 @@ extern "C" int pgp_fitc_update(pgp_fitc* f, const double* hyp) {
     const double sn2 = std::exp(hyp[0] * 2), mean = hyp[1 + nk];
     PGP_TRY(compile_spec(&f->spec, hyp + 1, sn2, mean, &f->hspec[0], &ctx->err));
     f->hspec[1] = f->hspec[0];
-    f->hspec[1].h.sn2 = sn2 / 1e6;                       // su2, fitc.py:68
+    f->hspec[1].h.sn2 = f->dtc ? sn2 * 1e-6 : sn2 / 1e6;   // su2: fitc.py:68 / dtc.py:56
     f->factored = false;
     cudaStream_t s = ctx->stream;
     PGP_CUDA(ctx, cudaMemcpyAsync(f->d_spec, f->hspec, sizeof(DevSpec) * 2, cudaMemcpyHostToDevice, s));
-    PGP_CUDA(ctx, cudaMemsetAsync(f->d_info, 0, sizeof(int) * 2, s));
+    PGP_CUDA(ctx, cudaMemsetAsync(f->d_info, 0, sizeof(int) * 4, s));
     PGP_TRY(launch_scale(ctx, f->d_spec, f->d_X, n, d, np, f->d_ZX, 1));
     PGP_TRY(launch_scale(ctx, f->d_spec, f->d_U, p, d, np, f->d_ZU, 1));
     const int st = single_type(&f->spec);
@@ -506,15 +573,32 @@ extern "C" int pgp_fitc_update(pgp_fitc* f, const double* hyp) {
     gx.single_type = st;
     PGP_TRY(launch_gram(ctx, gx));
     Mat V; V.p = f->d_Vs; V.ld = ldp;
+    Mat R; R.p = f->d_R; R.ld = ldp;
+    if (f->dtc) {
+        // DTC (dtc.py:54-75): Rux = chol(Kuu + Kux Kux^T / sn2 + su2 I), a = Rux^-T (Kux r), formed from the
+        // un-solved Kxu that sits in the Vs buffer right now; a rides along as row p of the factor
+        GramArgs gS = g;
+        gS.out = f->d_R;
+        PGP_TRY(launch_gram(ctx, gS));
+        PGP_TRY(gemm(ctx, f->d_Vs, ldp, 1, f->d_Vs, ldp, 1, f->d_R, ldp, p, p, n, 1.0 / sn2, 1.0, /*tri=*/1, /*splitk=*/0));
+        {
+            Launch Lc(ctx, PC_OTHER, 16.0 * n);
+            residual_kernel<<<flat_grid(n), 256, 0, s>>>(f->d_y, f->d_spec, n, f->d_c);
+            PGP_TRY(check_launch(ctx, "residual_kernel"));
+        }
+        PGP_TRY(gemv_t(f, f->d_Vs, n, f->d_c, f->d_R + p * ldp, 0));
+        PGP_TRY(potrf_lower(ctx, R, p, 1, f->d_info + 2));
+        PGP_CUDA(ctx, cudaMemcpyAsync(f->d_b, f->d_R + p * ldp, sizeof(double) * p, cudaMemcpyDeviceToDevice, s));
+    }
     PGP_TRY(trsm_right_lt(ctx, V, n, L, p));
     {
         Launch Lc(ctx, PC_OTHER, 16.0 * n * p);
         fitc_ell_kernel<<<warp_rows_grid(n), 256, 0, s>>>(f->d_Vs, ldp, n, p, f->d_y, f->d_spec, f->d_ell, f->d_rs,
-                                                         f->d_c);
+                                                         f->d_c, f->dtc);
         PGP_TRY(check_launch(ctx, "fitc_ell_kernel"));
     }
     // a = Kxu^T (r / ell^2), Kxu rebuilt chunk by chunk         fitc.py:88,96
-    for (int64_t r0 = 0; r0 < n; r0 += f->kc_rows) {
+    for (int64_t r0 = 0; !f->dtc && r0 < n; r0 += f->kc_rows) {
         const int64_t rows = std::min(f->kc_rows, n - r0);
         GramArgs gc = gx;
         gc.Z1 = f->d_ZX + r0 * d;
@@ -542,11 +626,12 @@ extern "C" int pgp_fitc_update(pgp_fitc* f, const double* hyp) {
         tril_kernel<<<flat_grid(p * p), 256, 0, s>>>(f->d_A, ldp, p);
         PGP_TRY(check_launch(ctx, "tril_kernel"));
     }
-    PGP_TRY(gemm(ctx, f->d_L, ldp, 0, f->d_A, ldp, 1, f->d_R, ldp, p, p, p, 1.0, 0.0, 0, 1));
-    PGP_CUDA(ctx, cudaMemcpyAsync(f->d_b, f->d_a, sizeof(double) * p, cudaMemcpyDeviceToDevice, s));
-    Mat R; R.p = f->d_R; R.ld = ldp;
-    Mat bv; bv.p = f->d_b; bv.ld = ldp;
-    PGP_TRY(trsm_right_lt(ctx, bv, 1, R, p));
+    if (!f->dtc) {
+        PGP_TRY(gemm(ctx, f->d_L, ldp, 0, f->d_A, ldp, 1, f->d_R, ldp, p, p, p, 1.0, 0.0, 0, 1));
+        PGP_CUDA(ctx, cudaMemcpyAsync(f->d_b, f->d_a, sizeof(double) * p, cudaMemcpyDeviceToDevice, s));
+        Mat bv; bv.p = f->d_b; bv.ld = ldp;
+        PGP_TRY(trsm_right_lt(ctx, bv, 1, R, p));
+    }
     {
         Launch Lc(ctx, PC_OTHER, 16.0 * n);
         fitc_lz_kernel<<<1, 1024, 0, s>>>(f->d_A, ldp, p, f->d_ell, f->d_rs, n, f->d_res);
@@ -554,15 +639,15 @@ extern "C" int pgp_fitc_update(pgp_fitc* f, const double* hyp) {
     }
     double* hp = ctx->h_pin;
     PGP_CUDA(ctx, cudaMemcpyAsync(hp, f->d_res, sizeof(double), cudaMemcpyDeviceToHost, s));
-    PGP_CUDA(ctx, cudaMemcpyAsync(hp + 1, f->d_info, sizeof(int) * 2, cudaMemcpyDeviceToHost, s));
+    PGP_CUDA(ctx, cudaMemcpyAsync(hp + 1, f->d_info, sizeof(int) * 4, cudaMemcpyDeviceToHost, s));
     PGP_CUDA(ctx, cudaStreamSynchronize(s));
     f->lZ = hp[0];
     const int* hi = reinterpret_cast<const int*>(hp + 1);
-    const int info = hi[0] ? hi[0] : hi[1];
+    const int info = hi[0] ? hi[0] : (hi[2] ? hi[2] : hi[1]);
     if (info != 0) {
         char buf[160];
         snprintf(buf, sizeof buf, "%d-th leading minor of the array is not positive definite (%s)", info,
-                 hi[0] ? "Kuu + su2 I" : "I + V V^T");
+                 hi[0] ? "Kuu + su2 I" : (hi[2] ? "Kuu + Kux Kux^T / sn2 + su2 I" : "I + V V^T"));
         ctx->err = buf;
         return info;
     }
@@ -599,14 +684,16 @@ extern "C" int pgp_fitc_loglike(pgp_fitc* f, int want_grad, double* lZ, double* 
     PGP_TRY(trsm_right_l(ctx, tv, 1, A, p));
     {
         Launch Lc(ctx, PC_OTHER, 8.0 * n * p);
-        fitc_alpha_kernel<<<warp_rows_grid(n), 256, 0, s>>>(f->d_Vs, ldp, n, p, f->d_t, f->d_rs, f->d_ell, f->d_alpha);
+        fitc_alpha_kernel<<<warp_rows_grid(n), 256, 0, s>>>(f->d_Vs, ldp, n, p, f->d_t, f->d_rs, f->d_ell, f->d_alpha,
+                                                           f->dtc);
         PGP_TRY(check_launch(ctx, "fitc_alpha_kernel"));
     }
     // Bt = (Vs ell) Lc^-1 ; Wt = (Vs / ell) Al^-T            fitc.py:197-198
-    PGP_TRY(scale_rows(f, f->d_Vs, f->d_Bt, f->d_ell, 0));
+    // DTC (dtc.py:161-162): B = Ruu^-1 V, W = A^-T V on the ell-scaled V itself
+    PGP_TRY(scale_rows(f, f->d_Vs, f->d_Bt, f->d_ell, f->dtc ? 2 : 0));
     Mat Bt; Bt.p = f->d_Bt; Bt.ld = ldp;
     PGP_TRY(trsm_right_l(ctx, Bt, n, L, p));
-    PGP_TRY(scale_rows(f, f->d_Vs, f->d_Wt, f->d_ell, 1));
+    PGP_TRY(scale_rows(f, f->d_Vs, f->d_Wt, f->d_ell, f->dtc ? 2 : 1));
     Mat Wt; Wt.p = f->d_Wt; Wt.ld = ldp;
     PGP_TRY(trsm_right_lt(ctx, Wt, n, A, p));
     {
@@ -617,10 +704,14 @@ extern "C" int pgp_fitc_loglike(pgp_fitc* f, int want_grad, double* lZ, double* 
     }
     PGP_TRY(gemv_t(f, f->d_Bt, n, f->d_alpha, f->d_w, 0));                                          // w = B alpha
     PGP_TRY(gemm(ctx, f->d_Bt, ldp, 1, f->d_Wt, ldp, 1, f->d_P, ldp, p, p, n, 1.0, 0.0, 0, 0));     // P = B W^T
-    // Cuu = Bt^T diag(q) Bt - P P^T - w w^T
-    PGP_TRY(scale_rows(f, f->d_Bt, f->d_T, f->d_q, 0));
+    // Cuu = Bt^T diag(q) Bt - P P^T - w w^T   (DTC: q = 1)
     // (symmetric: only its lower tiles are formed; the trace doubles the strict lower part)
-    PGP_TRY(gemm(ctx, f->d_T, ldp, 1, f->d_Bt, ldp, 1, f->d_Cuu, ldp, p, p, n, 1.0, 0.0, /*tri=*/1, 0));
+    if (f->dtc) {
+        PGP_TRY(gemm(ctx, f->d_Bt, ldp, 1, f->d_Bt, ldp, 1, f->d_Cuu, ldp, p, p, n, 1.0, 0.0, /*tri=*/1, 0));
+    } else {
+        PGP_TRY(scale_rows(f, f->d_Bt, f->d_T, f->d_q, 0));
+        PGP_TRY(gemm(ctx, f->d_T, ldp, 1, f->d_Bt, ldp, 1, f->d_Cuu, ldp, p, p, n, 1.0, 0.0, /*tri=*/1, 0));
+    }
     PGP_TRY(gemm(ctx, f->d_P, ldp, 0, f->d_P, ldp, 0, f->d_Cuu, ldp, p, p, p, -1.0, 1.0, /*tri=*/1, 1));
     {
         Launch Lc(ctx, PC_OTHER, 16.0 * p * p);
@@ -631,8 +722,18 @@ extern "C" int pgp_fitc_loglike(pgp_fitc* f, int want_grad, double* lZ, double* 
     PGP_TRY(gemm(ctx, f->d_Wt, ldp, 0, f->d_P, ldp, 0, f->d_T, ldp, n, p, p, 1.0, 0.0, 0, 1));
     // scalars, then the two traces accumulate into res[1 + h]
     double* dk0 = f->d_res + 1 + kMaxHyper + kScal / 2;   // (nk) d k(x,x) / d hyper
-    PGP_TRY(launch_diag(ctx, f->d_spec, 1, 1, nk, dk0));
-    {
+    if (f->dtc) {
+        // v = V alpha, VW = V W^T, sum V^2 (dtc.py:163-181); d_a / d_q are free in DTC mode
+        if (!f->d_VW) PGP_TRY(dev_alloc(ctx, &f->d_VW, (size_t)p * ldp));
+        PGP_TRY(gemv_t(f, f->d_Vs, n, f->d_alpha, f->d_a, 0));
+        PGP_TRY(gemm(ctx, f->d_Vs, ldp, 1, f->d_Wt, ldp, 1, f->d_VW, ldp, p, p, n, 1.0, 0.0, 0, 0));
+        Launch Lc(ctx, PC_OTHER, 8.0 * n * p + 40.0 * n);
+        rownorm2_kernel<<<warp_rows_grid(n), 256, 0, s>>>(f->d_Vs, ldp, n, p, f->d_q);
+        dtc_grad_scalars_kernel<<<1, 1024, 0, s>>>(f->d_spec, n, p, nk, f->d_rs, f->d_alpha, f->d_q, f->d_bb,
+                                                  f->d_A + p * ldp, f->d_w, f->d_a, f->d_P, f->d_VW, ldp, f->d_res + 1);
+        PGP_TRY(check_launch(ctx, "dtc_grad_scalars_kernel"));
+    } else {
+        PGP_TRY(launch_diag(ctx, f->d_spec, 1, 1, nk, dk0));
         Launch Lc(ctx, PC_OTHER, 40.0 * n);
         fitc_grad_scalars_kernel<<<1, 1024, 0, s>>>(f->d_spec, n, p, nk, f->d_ell, f->d_alpha, f->d_cw, f->d_bb,
                                                    f->d_q, f->d_w, f->d_P, ldp, dk0, f->d_res + 1);
@@ -653,7 +754,8 @@ extern "C" int pgp_fitc_loglike(pgp_fitc* f, int want_grad, double* lZ, double* 
     PGP_TRY(launch_trace_rect(ctx, t));
     t.Z1 = f->d_ZX; t.n1 = n;
     t.sym = 0;
-    t.mode = 1; t.Bt = f->d_Bt; t.T2 = f->d_T; t.al = f->d_alpha; t.q = f->d_q; t.wv = f->d_w;
+    t.mode = 1; t.Bt = f->d_Bt; t.T2 = f->d_T; t.al = f->d_alpha; t.q = f->dtc ? nullptr : f->d_q; t.wv = f->d_w;
+    if (f->dtc) t.scale = 0.5 / std::sqrt(f->hspec[0].h.sn2);      // the 2 / ell of M = 2 dKux / ell - dKuu B (dtc.py:189)
     PGP_TRY(launch_trace_rect(ctx, t));
     double* hp = ctx->h_pin;
     PGP_CUDA(ctx, cudaMemcpyAsync(hp, f->d_res + 1, sizeof(double) * (nk + 2), cudaMemcpyDeviceToHost, s));
@@ -717,7 +819,7 @@ static int fitc_predict_impl(pgp_fitc* f, const double* Xs, int64_t ms, double* 
             {
                 Launch Lc(ctx, PC_OTHER, 16.0 * mc * p);
                 fitc_predict_reduce_kernel<<<warp_rows_grid(mc), 256, 0, s>>>(LK, RK, ldp, mc, p, f->d_b, f->d_spec,
-                                                                             dout, dout + chunk);
+                                                                             dout, dout + chunk, f->dtc);
                 PGP_TRY(check_launch(ctx, "fitc_predict_reduce_kernel"));
             }
             if (want_grad) {
@@ -796,7 +898,7 @@ extern "C" int pgp_fitc_full_posterior(pgp_fitc* f, const double* Xs, int64_t ms
         {
             Launch Lc(ctx, PC_OTHER, 16.0 * ms * p);
             fitc_predict_reduce_kernel<<<warp_rows_grid(ms), 256, 0, s>>>(LK, RK, ldp, ms, p, f->d_b, f->d_spec, dout,
-                                                                         dout + ms);
+                                                                         dout + ms, f->dtc);
             PGP_TRY(check_launch(ctx, "fitc_predict_reduce_kernel"));
         }
         GramArgs gs = g;

@@ -574,7 +574,7 @@ __global__ void __launch_bounds__(kThreads) trace_rect_kernel(TraceRectArgs a, i
             const int64_t gi = i0 + t.row(x);
             const bool rok = gi < a.n1;
             double ai = 0.0, qi = 0.0;
-            if (a.mode == 1 && rok) { ai = a.al[gi]; qi = a.q[gi]; }
+            if (a.mode == 1 && rok) { ai = a.al[gi]; qi = a.q ? a.q[gi] : 1.0; }
 #pragma unroll
             for (int y = 0; y < 4; ++y) {
                 const int64_t gj = j0 + t.col(y);

@@ -65,7 +65,7 @@ struct TraceRectArgs {
     const double* Bt = nullptr;      // mode 1: (n1, ldw)
     const double* T2 = nullptr;      // mode 1: (n1, ldw)
     const double* al = nullptr;      // mode 1: (n1) alpha
-    const double* q = nullptr;       // mode 1: (n1)
+    const double* q = nullptr;       // mode 1: (n1); nullptr = all ones (DTC)
     const double* wv = nullptr;      // mode 1: (n2) w
     int64_t ldw = 0;
     double scale = 1.0;

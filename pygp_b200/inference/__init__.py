@@ -1,10 +1,7 @@
-"""GP inference objects: same names as pygp.inference (DTC is not provided)."""
+"""GP inference objects: same names as pygp.inference."""
 from .exact import ExactGP
 from .basic import BasicGP
+from .fitc import FITC
+from .dtc import DTC
 
-__all__ = ['ExactGP', 'BasicGP']
-try:
-    from .fitc import FITC
-    __all__.append('FITC')
-except ImportError:      # pragma: no cover
-    pass
+__all__ = ['ExactGP', 'BasicGP', 'FITC', 'DTC']

@@ -26,12 +26,13 @@ class _DeviceFITC(object):
         self.ctx, self.handle = ctx, handle
 
     @classmethod
-    def create(cls, kernel, U, X, y):
+    def create(cls, kernel, U, X, y, dtc=False):
         ctx = _lib.context()
         U, X, y = _lib.as_f64(U, 2), _lib.as_f64(X, 2), _lib.as_f64(y, 1)
         h = C.c_void_p()
-        _lib.check(ctx, _lib.lib().pgp_fitc_create(ctx.handle, kernel._spec(), _lib.ptr(U), len(U),
-                                                   _lib.ptr(X), _lib.ptr(y), len(X), C.byref(h)))
+        make = _lib.lib().pgp_dtc_create if dtc else _lib.lib().pgp_fitc_create
+        _lib.check(ctx, make(ctx.handle, kernel._spec(), _lib.ptr(U), len(U), _lib.ptr(X), _lib.ptr(y), len(X),
+                             C.byref(h)))
         return cls(ctx, h)
 
     def __deepcopy__(self, memo):
@@ -48,6 +49,8 @@ class _DeviceFITC(object):
 
 class FITC(GP):
     """GP inference using sparse pseudo-inputs."""
+
+    _dtc = False        # DTC (inference/dtc.py) runs the same device state with the dtc.py algebra
 
     def __init__(self, likelihood, kernel, mean, U):
         # exact FITC inference only works with Gaussian likelihoods (fitc.py:24-26)
@@ -88,7 +91,7 @@ class FITC(GP):
             # FITC has no incremental update in the reference either (every
             # add_data re-runs _update on all the data, _base.py:133-141)
             self._dev = None
-            self._dev = _DeviceFITC.create(self._kernel, self._U, self._X, self._y)
+            self._dev = _DeviceFITC.create(self._kernel, self._U, self._X, self._y, self._dtc)
             self._ndev = self.ndata
         hyp = _lib.as_f64(self.get_hyper())
         _lib.check(self._dev.ctx, _lib.lib().pgp_fitc_update(self._dev.handle, _lib.ptr(hyp)))

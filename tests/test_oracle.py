@@ -157,3 +157,33 @@ def test_exact_device_model(N):
     nt.assert_allclose(out['dlZ'], dlZ, rtol=1e-9, atol=1e-9*np.abs(dlZ).max())
     nt.assert_allclose(out['mu'], mu, rtol=1e-10, atol=1e-11)
     nt.assert_allclose(out['s2'], s2, rtol=1e-10, atol=1e-12)
+
+
+@pytest.mark.parametrize('name', ['dtc_se_2d', 'dtc_ard4_500'])
+def test_dtc_vs_golden_and_device_model(name, golden):
+    """ODTC against the reference's outputs, and the regrouped DTC algebra the device
+    runs (oracle/fitc_model.py: dtc_*) against ODTC."""
+    from oracle import fitc_model as fm
+    from oracle.cases import DTC_CASES
+    from oracle.pygp_oracle import ODTC
+    g = golden['gp']
+    spec, N, d = DTC_CASES[name]
+    X, y, Xs, U = gp_inputs(N, d, True)
+    k = make_kernel(spec)
+    gp = ODTC(GP_SN, k, GP_MEAN, U)
+    gp.add_data(X, y)
+    lZ, dlZ = gp.loglikelihood(True)
+    mu, s2, dmu, ds2 = gp.posterior(Xs, grad=True)
+    nt.assert_allclose(lZ, g[name + '/lZ'], rtol=1e-12)
+    nt.assert_allclose(dlZ, g[name + '/dlZ'], rtol=1e-9, atol=1e-10)
+    nt.assert_allclose(mu, g[name + '/mu'], rtol=1e-10, atol=1e-12)
+    nt.assert_allclose(s2, g[name + '/s2'], rtol=1e-9, atol=1e-12)
+    nt.assert_allclose(dmu, g[name + '/dmu'], rtol=1e-9, atol=1e-11)
+    nt.assert_allclose(ds2, g[name + '/ds2'], rtol=1e-8, atol=1e-11)
+    st = fm.dtc_update(k, GP_SN**2, GP_MEAN, U, X, y)
+    lZ2, dlZ2 = fm.dtc_loglike(k, st, U, X, True)
+    mu2, s22 = fm.dtc_predict(k, st, U, Xs)
+    nt.assert_allclose(lZ2, lZ, rtol=1e-11)
+    nt.assert_allclose(dlZ2, dlZ, rtol=1e-9, atol=1e-9*np.abs(dlZ).max())
+    nt.assert_allclose(mu2, mu, rtol=1e-10, atol=1e-11)
+    nt.assert_allclose(s22, s2, rtol=1e-10, atol=1e-13)
