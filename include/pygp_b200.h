@@ -114,6 +114,12 @@ int pgp_dgrad(pgp_ctx* ctx, const pgp_kernel_spec* spec, const double* hyp,
 int pgp_gram_gradx(pgp_ctx* ctx, const pgp_kernel_spec* spec, const double* hyp,
                    const double* X1, int64_t n1, const double* X2, int64_t n2,
                    int32_t wrt_y, double* out);
+/* Kernel.gradxy (se.py:88-99, _real.py:102-103,129-156): out (n1, n2, ndim, ndim),
+ * d2 k / d x1_a d x2_b.  SE leaves and their sums / products only, as in the
+ * reference (PGP_E_ARG otherwise -> the host raises NotImplementedError). */
+int pgp_gram_gradxy(pgp_ctx* ctx, const pgp_kernel_spec* spec, const double* hyp,
+                    const double* X1, int64_t n1, const double* X2, int64_t n2,
+                    double* out);
 /* same as pgp_gram with operands and result resident in HBM (bench.py `value`) */
 int pgp_gram_dev(pgp_ctx* ctx, const pgp_kernel_spec* spec, const double* hyp,
                  const double* d_X1, int64_t n1, const double* d_X2, int64_t n2,

@@ -52,6 +52,15 @@ def kernel_golden(pygp):
         _close(ok.gradx(x1, x2), rec['gradx12'], name + '.gradx12')
         _close(ok.grady(x1, x2), rec['grady12'], name + '.grady12')
         _close(ok.gradx(x1), rec['gradx11'], name + '.gradx11')
+        try:                                   # SE and its composites only (tests/test_kernels.py:130-146)
+            rec['gradxy12'] = rk.gradxy(x1, x2)
+            _close(ok.gradxy(x1, x2), rec['gradxy12'], name + '.gradxy12', 1e-11, 1e-13)
+        except NotImplementedError:
+            try:
+                ok.gradxy(x1, x2)
+                raise AssertionError('oracle defines gradxy where the reference does not: ' + name)
+            except NotImplementedError:
+                pass
         _close(ok.get(x1, x2), rec['get12'], name + '.get12')
         _close(ok.get(x1), rec['get11'], name + '.get11')
         _close(np.array(ok.grad(x1, x2)), rec['grad12'], name + '.grad12')

@@ -118,6 +118,17 @@ class OSE(_OKernel):
     def grady(self, X1, X2=None):
         return -self.gradx(X1, X2)      # se.py:85-86
 
+    def gradxy(self, X1, X2=None):
+        # se.py:88-99
+        ell = np.exp(self._logell)
+        X1, X2 = _rescale(ell, X1, X2)
+        D = _diff(X1, X2)
+        d = D.shape[2]
+        K = np.exp(self._logsf*2 - np.sum(D**2, axis=-1)/2)
+        D = D / ell
+        M = np.eye(d)/ell**2 - D[:, :, None] * D[:, :, :, None]
+        return M * K[:, :, None, None]
+
     def dget(self, X1):
         return np.exp(self._logsf*2) * np.ones(len(X1))  # se.py:68-69
 
@@ -204,6 +215,9 @@ class OMatern(_OKernel):
     def grady(self, X1, X2=None):
         return -self.gradx(X1, X2)      # matern.py:113-114
 
+    def gradxy(self, X1, X2=None):
+        raise NotImplementedError       # as the reference
+
     def dget(self, X1):
         return np.exp(self._logsf*2) * np.ones(len(X1))  # matern.py:92-93
 
@@ -259,6 +273,9 @@ class OPeriodic(_OKernel):
 
     def grady(self, X1, X2=None):
         return -self.gradx(X1, X2)      # periodic.py:96-97
+
+    def gradxy(self, X1, X2=None):
+        raise NotImplementedError       # as the reference
 
     def dget(self, X1):
         return np.exp(self._logsf*2) * np.ones(len(X1))  # periodic.py:76-77
@@ -335,6 +352,9 @@ class ORQ(_OKernel):
     def grady(self, X1, X2=None):
         return -self.gradx(X1, X2)      # rq.py:110-111
 
+    def gradxy(self, X1, X2=None):
+        raise NotImplementedError       # as the reference
+
     def dget(self, X1):
         return np.exp(self._logsf*2) * np.ones(len(X1))  # rq.py:86-87
 
@@ -393,6 +413,9 @@ class OSum(_OCombo):
     def grady(self, X1, X2=None):
         return sum(p.grady(X1, X2) for p in self._parts)        # _real.py:99-100
 
+    def gradxy(self, X1, X2=None):
+        return sum(p.gradxy(X1, X2) for p in self._parts)       # _real.py:102-103
+
     def dget(self, X):
         return sum(p.dget(X) for p in self._parts)
 
@@ -420,6 +443,21 @@ class OProduct(_OCombo):
         # _real.py:124-127
         F = _product_but([p.get(X1, X2)[:, :, None] for p in self._parts])
         return sum(f*p.grady(X1, X2) for f, p in zip(F, self._parts))
+
+    def gradxy(self, X1, X2=None):
+        # _real.py:129-156
+        K = [p.get(X1, X2) for p in self._parts]
+        Kn = _product_but(K)
+        Gx = [p.gradx(X1, X2) for p in self._parts]
+        Gy = [p.grady(X1, X2) for p in self._parts]
+        Gxy = [p.gradxy(X1, X2) for p in self._parts]
+        grad = sum(Kni[:, :, None, None] * dKi for Kni, dKi in zip(Kn, Gxy))
+        xpart = sum(dKi * Ki[:, :, None] for dKi, Ki in zip(Gx, Kn))
+        ypart = sum(dKi / Ki[:, :, None] for dKi, Ki in zip(Gy, K))
+        grad += xpart[:, :, :, None] * ypart[:, :, None, :]
+        grad -= sum((Kni / Ki)[:, :, None, None] * dKx[:, :, :, None] * dKy[:, :, None, :]
+                    for Kni, Ki, dKx, dKy in zip(Kn, K, Gx, Gy))
+        return grad
 
     def dget(self, X):
         out = 1

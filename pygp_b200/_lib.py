@@ -64,6 +64,7 @@ SIGNATURES = {
     'pgp_dget': (C.c_int, [_vp, _sp, _dp, _dp, _i64, _dp]),
     'pgp_dgrad': (C.c_int, [_vp, _sp, _dp, _dp, _i64, _dp]),
     'pgp_gram_gradx': (C.c_int, [_vp, _sp, _dp, _dp, _i64, _dp, _i64, C.c_int32, _dp]),
+    'pgp_gram_gradxy': (C.c_int, [_vp, _sp, _dp, _dp, _i64, _dp, _i64, _dp]),
     'pgp_gram_dev': (C.c_int, [_vp, _sp, _dp, _vp, _i64, _vp, _i64, _vp]),
     'pgp_exact_create': (C.c_int, [_vp, _sp, _dp, _dp, _i64, C.POINTER(_vp)]),
     'pgp_exact_append': (C.c_int, [_vp, _dp, _dp, _i64]),

@@ -340,6 +340,60 @@ extern "C" int pgp_gram_gradx(pgp_ctx* ctx, const pgp_kernel_spec* spec, const d
     return 0;
 }
 
+// Kernel.gradxy (se.py:88-99, _real.py:102-103,129-156): out (n1, n2, ndim, ndim); defined by the
+// reference for SE leaves and their sums / products only (the others raise NotImplementedError).
+extern "C" int pgp_gram_gradxy(pgp_ctx* ctx, const pgp_kernel_spec* spec, const double* hyp, const double* X1,
+                               int64_t n1, const double* X2, int64_t n2, double* out) {
+    if (!ctx) return PGP_E_ARG;
+    if (!spec || !hyp || !X1 || !out || n1 < 0 || n2 < 0) return ctx->fail(PGP_E_ARG, "null or negative argument");
+    for (int p = 0; p < spec->n_parts && p < PGP_MAX_PARTS; ++p)
+        if (spec->parts[p].type != PGP_SE) return ctx->fail(PGP_E_ARG, "gradxy is defined for SE kernels and their composites only");
+    PGP_TRY(set_device(ctx));
+    if (!X2) n2 = n1;
+    if (n1 == 0 || n2 == 0) return 0;
+    const int d = spec->ndim, np = spec->n_parts;
+    DevSpec hs;
+    PGP_TRY(compile_spec(spec, hyp, 0.0, 0.0, &hs, &ctx->err));
+    DevBuf dspec, x1, x2, z1, z2, o;
+    PGP_TRY(alloc<DevSpec>(ctx, dspec, 1));
+    PGP_TRY(upload_spec(ctx, hs, dspec.as<DevSpec>()));
+    PGP_TRY(alloc<double>(ctx, x1, (size_t)n1 * d));
+    PGP_CUDA(ctx, cudaMemcpyAsync(x1.p, X1, sizeof(double) * n1 * d, cudaMemcpyHostToDevice, ctx->stream));
+    PGP_TRY(alloc<double>(ctx, z1, (size_t)np * n1 * d));
+    PGP_TRY(launch_scale(ctx, dspec.as<DevSpec>(), x1.as<double>(), n1, d, np, z1.as<double>(), 1));
+    const double* Z2 = z1.as<double>();
+    if (X2) {
+        PGP_TRY(alloc<double>(ctx, x2, (size_t)n2 * d));
+        PGP_CUDA(ctx, cudaMemcpyAsync(x2.p, X2, sizeof(double) * n2 * d, cudaMemcpyHostToDevice, ctx->stream));
+        PGP_TRY(alloc<double>(ctx, z2, (size_t)np * n2 * d));
+        PGP_TRY(launch_scale(ctx, dspec.as<DevSpec>(), x2.as<double>(), n2, d, np, z2.as<double>(), 1));
+        Z2 = z2.as<double>();
+    }
+    const int64_t dd = (int64_t)d * d;
+    PGP_TRY(alloc<double>(ctx, o, (size_t)n1 * n2 * dd));
+    for (int a = 0; a < d; ++a)
+        for (int b = 0; b < d; ++b) {
+            GramArgs g;
+            g.spec = dspec.as<DevSpec>();
+            g.Z1 = z1.as<double>();
+            g.Z2 = Z2;
+            g.n1 = n1;
+            g.n2 = n2;
+            g.ndim = d;
+            g.n_parts = np;
+            g.out = o.as<double>() + a * d + b;
+            g.ldo = n2 * dd;
+            g.ostride = dd;
+            g.xdim = a;
+            g.ydim = b;
+            g.single_type = -1;
+            PGP_TRY(launch_gram(ctx, g));
+        }
+    PGP_CUDA(ctx, cudaMemcpyAsync(out, o.p, sizeof(double) * n1 * n2 * dd, cudaMemcpyDeviceToHost, ctx->stream));
+    PGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
 static int diag_host(pgp_ctx* ctx, const pgp_kernel_spec* spec, const double* hyp, int64_t n, int hmode,
                      double* out) {
     if (!ctx) return PGP_E_ARG;

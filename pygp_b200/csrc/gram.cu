@@ -110,6 +110,58 @@ __device__ __forceinline__ double leaf_gradx(const DevPart& p, const PartVal& v,
     return -v.ardw * sdiff / ellk;
 }
 
+// d^2 k / d x1_a d x2_b of a composite of SE leaves at one entry (se.py:88-99,
+// _real.py:102-103,129-156).  Every node carries (v, dv/dx1_a, dv/dx2_b, d2v/dx1_a dx2_b);
+// sums add them, products fold their children with the second-order product rule
+//     (u w)_xy = u_xy w + u_x w_y + u_y w_x + u w_xy
+// -- the reference's own form divides by the part values (_real.py:147-154), which
+// this one never does.
+struct Jet2 { double v, x, y, xy; };
+
+__device__ __forceinline__ double composite_gradxy(const DevSpecHdr& S, const DevSpec* gs, const double* z1,
+                                                   const double* z2, int da, int db) {
+    const int d = S.ndim;
+    Jet2 node[kMaxNodes];
+    for (int n = 0; n < S.n_nodes; ++n) {
+        const int kind = S.node_kind[n];
+        if (kind == NK_LEAF) {
+            const int p = S.node_leaf[n];
+            double D = 0.0;
+            for (int k = 0; k < d; ++k) {
+                double df = z1[(p * d + k) * kTile] - z2[(p * d + k) * kTile];
+                D += df * df;
+            }
+            const double K = exp(S.parts[p].two_logsf - D / 2);
+            const double ua = (z1[(p * d + da) * kTile] - z2[(p * d + da) * kTile]) / gs->ell[p][da];
+            const double ub = (z1[(p * d + db) * kTile] - z2[(p * d + db) * kTile]) / gs->ell[p][db];
+            Jet2 j;
+            j.v = K;
+            j.x = -K * ua;
+            j.y = K * ub;
+            j.xy = K * ((da == db ? 1.0 / (gs->ell[p][da] * gs->ell[p][da]) : 0.0) - ua * ub);
+            node[n] = j;
+        } else {
+            const int* ch = S.child + S.node_child0[n];
+            Jet2 acc = node[ch[0]];
+            for (int c = 1; c < S.node_nchild[n]; ++c) {
+                const Jet2 w = node[ch[c]];
+                if (kind == NK_SUM) {
+                    acc.v += w.v; acc.x += w.x; acc.y += w.y; acc.xy += w.xy;
+                } else {
+                    Jet2 r;
+                    r.v = acc.v * w.v;
+                    r.x = acc.x * w.v + acc.v * w.x;
+                    r.y = acc.y * w.v + acc.v * w.y;
+                    r.xy = acc.xy * w.v + acc.x * w.y + acc.y * w.x + acc.v * w.xy;
+                    acc = r;
+                }
+            }
+            node[n] = acc;
+        }
+    }
+    return node[S.n_nodes - 1].xy;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------
@@ -150,6 +202,7 @@ template <int PTYPE, int MODE>
 __global__ void __launch_bounds__(kThreads) gram_kernel(GramArgs a) {
     constexpr bool GRAD1 = MODE == 1;
     constexpr bool GRADX = MODE == 2;
+    constexpr bool GRADXY = MODE == 3;      // composite path only (PTYPE < 0)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     DevSpecHdr* S = reinterpret_cast<DevSpecHdr*>(smem_raw);
     double* Zs1 = reinterpret_cast<double*>(smem_raw + ((sizeof(DevSpecHdr) + 15) / 16) * 16);
@@ -227,7 +280,9 @@ __global__ void __launch_bounds__(kThreads) gram_kernel(GramArgs a) {
             for (int y = 0; y < 4; ++y) {
                 const double* z1 = Zs1 + t.row(x);
                 const double* z2 = Zs2 + t.col(y);
-                if (GRADX) {
+                if (GRADXY) {
+                    res[x][y] = composite_gradxy(*S, a.spec + b, z1, z2, xdim, a.ydim);
+                } else if (GRADX) {
                     PartVal pv[kMaxParts];
                     double val[kMaxNodes], adj[kMaxNodes];
                     eval_parts<true>(*S, z1, z2, pv);
@@ -333,9 +388,10 @@ int launch_gram(pgp_ctx* ctx, const GramArgs& a) {
         return ctx->fail(PGP_E_ARG, "gram: n_parts * ndim > 192 exceeds the shared-memory tile");
     size_t smem = ((sizeof(DevSpecHdr) + 15) / 16) * 16 + 2ull * a.n_parts * a.ndim * kTile * sizeof(double);
     if (a.symmetric) smem += (size_t)kTile * (kTile + 1) * sizeof(double);
-    const int mode = a.xdim >= 0 ? 2 : (a.hidx >= 0 ? 1 : 0);
-    if (mode == 2 && (a.xdim >= a.ndim || a.symmetric || a.lower_only))
+    const int mode = a.xdim >= 0 ? (a.ydim >= 0 ? 3 : 2) : (a.hidx >= 0 ? 1 : 0);
+    if (mode >= 2 && (a.xdim >= a.ndim || a.ydim >= a.ndim || a.symmetric || a.lower_only))
         return ctx->fail(PGP_E_ARG, "gram: bad input-gradient request");
+    if (mode == 3) return launch_gram_t<-1, 3>(ctx, a, smem);    // second derivatives: tree path only
     if (a.ostride != 1 && a.symmetric) return ctx->fail(PGP_E_ARG, "gram: strided output cannot be mirrored");
     int st = a.n_parts == 1 ? a.single_type : -1;
 #define PGP_GRAM_CASE(T)                                                                  \

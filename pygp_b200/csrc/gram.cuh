@@ -28,6 +28,7 @@ struct GramArgs {
     int add_noise = 0;               // out[i][i] += spec.sn2
     int hidx = -1;                   // >= 0: write d/d hyper[hidx] instead of K
     int xdim = -1;                   // >= 0: write d k(x1, x2) / d x1[xdim] instead of K (gradx)
+    int ydim = -1;                   // with xdim: write d2 k / d x1[xdim] d x2[ydim] (gradxy; SE leaves only)
     int64_t ostride = 1;             // doubles between consecutive columns of `out`
     int batch = 1;
     int single_type = -1;            // leaf type when n_parts == 1 (fast path)

@@ -133,7 +133,18 @@ class RealKernel(Kernel):
         return self._gradx(X1, X2, 1)
 
     def gradxy(self, X1, X2=None):
-        raise NotImplementedError('gradxy is outside the B200 hot path (SE-only in the reference; next: N1)')
+        """d2 k(x1, x2) / d x1 d x2: (n1, n2, ndim, ndim).  Defined, as in the
+        reference, for SE kernels and their sums / products only."""
+        spec = self._spec()
+        if any(spec.parts[i].type != _lib.SE for i in range(spec.n_parts)):
+            raise NotImplementedError
+        X1, X2 = self._inputs(X1, X2)
+        n1, n2 = len(X1), (len(X1) if X2 is None else len(X2))
+        out = np.empty((n1, n2, self.ndim, self.ndim))
+        ctx, L, hyp = _lib.context(), _lib.lib(), self._hyp()
+        _lib.check(ctx, L.pgp_gram_gradxy(ctx.handle, spec, _lib.ptr(hyp), _lib.ptr(X1), n1,
+                                          None if X2 is None else _lib.ptr(X2), n2, _lib.ptr(out)))
+        return out
 
     def sample_spectrum(self, N, rng=None):
         raise NotImplementedError('sample_spectrum is outside the B200 hot path')

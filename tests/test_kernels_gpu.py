@@ -83,8 +83,13 @@ def test_input_gradients_vs_golden(name, golden):
     nt.assert_allclose(k.gradx(x1, x2), g[name + '/gradx12'], rtol=1e-12, atol=1e-13)
     nt.assert_allclose(k.grady(x1, x2), g[name + '/grady12'], rtol=1e-12, atol=1e-13)
     nt.assert_allclose(k.gradx(x1), g[name + '/gradx11'], rtol=1e-12, atol=1e-13)
-    with pytest.raises(NotImplementedError):
-        k.gradxy(x1, x2)
+    # gradxy: SE and its sums / products (tests/test_kernels.py:130-146); NotImplementedError otherwise
+    if name + '/gradxy12' in g.files:
+        nt.assert_allclose(k.gradxy(x1, x2), g[name + '/gradxy12'], rtol=1e-11, atol=1e-12)
+        nt.assert_allclose(k.gradxy(x1), make_kernel(KERNEL_CASES[name]).gradxy(x1), rtol=1e-11, atol=1e-12)
+    else:
+        with pytest.raises(NotImplementedError):
+            k.gradxy(x1, x2)
 
 
 @pytest.mark.parametrize('name', ['matern3_ard', 'maunaloa', 'prod_mixed', 'periodic'])

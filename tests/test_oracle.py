@@ -27,6 +27,11 @@ def test_kernel_vs_golden(name, golden):
     nt.assert_allclose(k.gradx(x1, x2), g[name + '/gradx12'], rtol=1e-12, atol=1e-14)
     nt.assert_allclose(k.grady(x1, x2), g[name + '/grady12'], rtol=1e-12, atol=1e-14)
     nt.assert_allclose(k.gradx(x1), g[name + '/gradx11'], rtol=1e-12, atol=1e-14)
+    if name + '/gradxy12' in g.files:
+        nt.assert_allclose(k.gradxy(x1, x2), g[name + '/gradxy12'], rtol=1e-11, atol=1e-13)
+    else:
+        with pytest.raises(NotImplementedError):
+            k.gradxy(x1, x2)
     nt.assert_allclose(k.dget(x1), g[name + '/dget'], rtol=1e-15)
     nt.assert_allclose(np.array(k.dgrad(x1)), g[name + '/dgrad'], rtol=1e-15)
     k2 = k.copy_with(g[name + '/hyper2'])
