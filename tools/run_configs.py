@@ -142,8 +142,50 @@ def c5_fitc():
         dlZ_finite=bool(np.all(np.isfinite(dlZ))))
 
 
+def next_rows():
+    """The SURVEY 8f rows at a working size: input-gradient predict (N1), joint posterior + draws (N3),
+    incremental update (N4), DTC (N4), on N = 8192, d = 8."""
+    n, d = 8192, 8
+    X, y = problem(n + 64, d)
+    Xs = np.random.RandomState(1).rand(4096, d)
+    mk = lambda: pygp.inference.ExactGP(pygp.likelihoods.Gaussian(0.1), pygp.kernels.SE(1.0, [0.5*np.sqrt(d)]*d), 0.0)
+    gp = mk()
+    gp.add_data(X[:n], y[:n])
+    gp.posterior(Xs[:64], grad=True)
+    t_pg, _ = best(lambda: gp.posterior(Xs, grad=True), 2)
+    t_p, _ = best(lambda: gp.posterior(Xs), 2)
+    gp._full_posterior(Xs[:64])
+    t_full, _ = best(lambda: gp._full_posterior(Xs[:1024]), 2)
+    t_smp, _ = best(lambda: gp.sample(Xs[:1024], 8, rng=0), 2)
+    t_full_upd, _ = best(lambda: gp.set_hyper(gp.get_hyper()), 2)
+    t_inc = []
+    for i in range(8):                                   # one datum at a time, as a BO loop / SMC does
+        t0 = time.perf_counter()
+        gp.add_data(X[n + i:n + i + 1], y[n + i:n + i + 1])
+        t_inc.append(time.perf_counter() - t0)
+    t0 = time.perf_counter()
+    gp.add_data(X[n + 8:n + 64], y[n + 8:n + 64])        # a block of 56
+    t_inc56 = time.perf_counter() - t0
+    ref = mk()
+    ref.add_data(X, y)
+    err = abs(ref.loglikelihood() - gp.loglikelihood())/abs(ref.loglikelihood())
+    U = np.random.RandomState(3).rand(512, d)
+    dtc = pygp.inference.DTC(pygp.likelihoods.Gaussian(0.1), pygp.kernels.SE(1.0, [0.6]*d), 0.0, U)
+    Xb, yb = problem(262144, d)
+    dtc.add_data(Xb, yb)
+    dtc.loglikelihood(True)
+    h = dtc.get_hyper()
+    t_dtc, _ = best(lambda: (dtc.set_hyper(h), dtc.loglikelihood(True)), 2)
+    say(config='next-rows', workload='ExactGP SE-ARD d=8 N=8192: N1 predict with input-gradients, N3 joint posterior / draws, '
+        'N4 incremental update; DTC M=512 N=262144',
+        predict_points_per_s=len(Xs)/t_p, predict_grad_points_per_s=len(Xs)/t_pg,
+        full_posterior_1024_ms=t_full*1e3, sample_8x1024_ms=t_smp*1e3,
+        full_update_ms=t_full_upd*1e3, incremental_update_1_ms=float(np.median(t_inc))*1e3,
+        incremental_update_56_ms=t_inc56*1e3, incremental_vs_full_lZ_rel_err=err, dtc_eval_ms=t_dtc*1e3)
+
+
 def main():
-    what = sys.argv[1:] or ['c1', 'c2', 'c4', 'c5_fitc', 'c5_exact']
+    what = sys.argv[1:] or ['c1', 'c2', 'c4', 'c5_fitc', 'c5_exact', 'next_rows']
     _lib.context()
     for w in what:
         globals()[w]()
