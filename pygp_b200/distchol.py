@@ -42,24 +42,40 @@ def block_columns(n, nb):
     return [(j0, min(nb, n - j0)) for j0 in range(0, n, nb)]
 
 
-def distributed_factor(be, n, nb, rank, size, bcast):
+def distributed_factor(be, n, nb, rank, size, bcast, group=1):
     """Run the schedule.  `be` provides the arithmetic on this rank's buffers:
 
         be.build_panel(j0, w)          -> panel ((n - j0) + 1, w): K[j0:, j0:j0+w] + noise, last row r[j0:j0+w]
         be.recv_buffer(rows, w, slot)  -> buffer (rows, .) a broadcast panel is received into (two slots)
         be.factor_panel(panel, w)      -> LAPACK-style info (0 ok): potrf of the top w x w block in place,
                                           rows below <- rows L^-T
-        be.update_panel(pj, pk, off, w_j)  pj -= pk[off:, :] @ pk[off:off+w_j, :].T
-        be.store_panel(pk, j0, w)      copy a factored panel into the replicated factor (rows j0.., cols j0..j0+w)
+        be.store_panel(pk, j0, w)      copy a factored panel into the replicated factor F (rows j0.., cols j0..j0+w)
+        be.update_from_factor(pj, j0, w, c_lo, c_hi)
+                                       pj -= F[j0:, c_lo:c_hi] @ F[j0:j0+w, c_lo:c_hi].T   (stored panels only)
         be.sync()                      make the panel's producer visible before it is broadcast
 
     `bcast(buf, src) -> handle` starts the (asynchronous) broadcast of `buf` from
     rank `src`; `handle.wait()` completes it (None for world size 1).
+
+    `group` > 1: trailing panels are brought up to date with `group` factored panels
+    at a time (one GEMM with K = group * nb read from the replicated factor; the
+    panel after next is always kept fully up to date).  Measured on 8 GPUs at
+    N = 65536, nb = 512 this is SLOWER (0.58 s for 2, 0.60 s for 4, against 0.51 s
+    for 1): the per-rank GEMM work is already hidden behind the panel chain
+    (factor + broadcast), and deferring it only makes it arrive in bursts.
     Returns info (> 0: order of the first non positive-definite leading minor)."""
     cols = block_columns(n, nb)
     nblk = len(cols)
     mine = {j: be.build_panel(*cols[j]) for j in range(nblk) if j % size == rank}
+    applied = dict((j, 0) for j in mine)      # panels 0 .. applied[j] - 1 are already applied to panel j
     info = 0
+
+    def catch_up(j, upto):
+        if applied[j] < upto:
+            c_lo = cols[applied[j]][0]
+            c_hi = cols[upto - 1][0] + cols[upto - 1][1]
+            be.update_from_factor(mine[j], cols[j][0], cols[j][1], c_lo, c_hi)
+            applied[j] = upto
 
     def produce(k):
         """owner: factor panel k and start its broadcast; others: post the receive."""
@@ -79,18 +95,17 @@ def distributed_factor(be, n, nb, rank, size, bcast):
         j0, w = cols[k]
         if handle is not None:
             handle.wait()
-        pk = cur
-        be.store_panel(pk, j0, w)
+        be.store_panel(cur, j0, w)
         nxt = None
         # lookahead: the next panel first, then its factorisation and broadcast
         if k + 1 < nblk:
             if (k + 1) % size == rank:
-                be.update_panel(mine[k + 1], pk, cols[k + 1][0] - j0, cols[k + 1][1])
+                catch_up(k + 1, k + 1)
             nxt = produce(k + 1)
             info = info or nxt[2]
         for j in range(k + 2, nblk):
-            if j % size == rank:
-                be.update_panel(mine[j], pk, cols[j][0] - j0, cols[j][1])
+            if j % size == rank and (j == k + 2 or k + 1 - applied[j] >= group):
+                catch_up(j, k + 1)
         if nxt is not None:
             cur, handle = nxt[0], nxt[1]
     be.sync()
@@ -158,13 +173,12 @@ class DeviceBackend(object):
             self._lib.check(self.ctx, rc)
         return rc
 
-    def update_panel(self, pj, pk, off, wj):
-        # pk is a complete block column here (only the last one can be ragged and it is never a source)
-        nb = self.nb
-        a = pk[off:]
+    def update_from_factor(self, pj, j0, wj, c_lo, c_hi):
+        # operands straight from the replicated factor: rows j0.. of the stored block columns [c_lo, c_hi)
+        a = self.F_ptr + (j0*self.ld + c_lo)*8
         self._lib.check(self.ctx, self.L.pgp_dev_gemm_nt(
-            self.ctx.handle, pj.shape[0], wj, nb, -1.0, a.data_ptr(), nb, a.data_ptr(), nb,
-            1.0, pj.data_ptr(), nb, 0))
+            self.ctx.handle, pj.shape[0], wj, c_hi - c_lo, -1.0, a, self.ld, a, self.ld,
+            1.0, pj.data_ptr(), self.nb, 0))
 
     def store_panel(self, pk, j0, w):
         # strided device copy into the model's factor buffer (rows j0 .. n, columns j0 .. j0 + w)
@@ -176,7 +190,7 @@ class DeviceBackend(object):
         self.ctx.sync()
 
 
-def distributed_update(gp, nb=1024, group=None):
+def distributed_update(gp, nb=512, group=None, panels_per_update=1):
     """`ExactGP._update` with the factorisation spread over the ranks of `group`.
     Every rank must hold the same model (data and hypers).  Afterwards the model
     on every rank is factored exactly as after `pgp_exact_update`."""
@@ -202,7 +216,7 @@ def distributed_update(gp, nb=1024, group=None):
             return _Handle(dist.broadcast(buf, src=src_global, group=group, async_op=True))
 
     with torch.cuda.stream(be.stream):
-        info = distributed_factor(be, gp.ndata, nb, rank, size, bcast)
+        info = distributed_factor(be, gp.ndata, nb, rank, size, bcast, panels_per_update)
     if info:
         raise np.linalg.LinAlgError('%d-th leading minor of the array is not positive definite' % info)
     _lib.check(be.ctx, _lib.lib().pgp_exact_adopt_factor(gp._dev.handle, _lib.ptr(hyp)))

@@ -49,7 +49,7 @@ class _DeviceModel(object):
 
 
 class ExactGP(GP):
-    # Opt-in multi-GPU factorisation: set to e.g. {'nb': 1024, 'min_n': 32768} in a
+    # Opt-in multi-GPU factorisation: set to e.g. {'nb': 512, 'min_n': 32768} in a
     # one-process-per-GPU job whose ranks all hold the same model and call
     # set_hyper in lockstep (replicated optimiser); `_update` then runs the 1-D
     # block-column distributed Cholesky (pygp_b200/distchol.py) for ndata >= min_n.
@@ -89,7 +89,8 @@ class ExactGP(GP):
         if cfg and n >= cfg.get('min_n', 32768):
             from .. import sharding, distchol
             if sharding.world(cfg.get('group'))[1] > 1:
-                distchol.distributed_update(self, nb=cfg.get('nb', 1024), group=cfg.get('group'))
+                distchol.distributed_update(self, nb=cfg.get('nb', 512), group=cfg.get('group'),
+                                            panels_per_update=cfg.get('panels_per_update', 1))
                 return
         hyp = _lib.as_f64(self.get_hyper())
         _lib.check(self._dev.ctx, L.pgp_exact_update(self._dev.handle, _lib.ptr(hyp)))

@@ -41,8 +41,10 @@ class NumpyBackend(object):
         panel[w:, :w] = sla.solve_triangular(L, panel[w:, :w].T, lower=True).T
         return 0
 
-    def update_panel(self, pj, pk, off, wj):
-        pj[:, :wj] -= pk[off:] @ pk[off:off + wj].T
+    def update_from_factor(self, pj, j0, wj, c_lo, c_hi):
+        A = self.F[j0:, c_lo:c_hi]
+        assert not np.isnan(A).any()          # only stored (factored) panels may be read
+        pj[:, :wj] -= A @ self.F[j0:j0 + wj, c_lo:c_hi].T
 
     def store_panel(self, pk, j0, w):
         self.F[j0:, j0:j0 + w] = pk[:, :w]
@@ -57,13 +59,14 @@ def _problem(n, seed=0):
     return A @ A.T/n + np.eye(n), rng.randn(n)
 
 
-@pytest.mark.parametrize('n,nb', [(64, 64), (100, 64), (257, 64), (400, 128)])
-def test_schedule_single_rank(n, nb):
+@pytest.mark.parametrize('group', [1, 2, 3])
+@pytest.mark.parametrize('n,nb', [(64, 64), (100, 64), (257, 64), (400, 128), (700, 64)])
+def test_schedule_single_rank(n, nb, group):
     from pygp_b200.distchol import distributed_factor, block_columns
     assert sum(w for _, w in block_columns(n, nb)) == n
     K, r = _problem(n)
     be = NumpyBackend(K, r, nb)
-    assert distributed_factor(be, n, nb, 0, 1, None) == 0
+    assert distributed_factor(be, n, nb, 0, 1, None, group) == 0
     L = np.linalg.cholesky(K)
     low = np.tril_indices(n)
     nt.assert_allclose(be.F[:n][low], L[low], rtol=1e-11, atol=1e-12)
@@ -107,10 +110,10 @@ def _worker(rank, size, port, q):
             t = torch.from_numpy(np.ascontiguousarray(buf))
             return H(dist.broadcast(t, src=src, async_op=True), t, buf)
 
-        for n, nb in [(300, 64), (257, 128), (64, 64)]:
+        for n, nb, group in [(300, 64, 1), (257, 128, 2), (64, 64, 2), (900, 64, 3)]:
             K, r = _problem(n, seed=n)
             be = NumpyBackend(K, r, nb)
-            info = distributed_factor(be, n, nb, rank, size, bcast)
+            info = distributed_factor(be, n, nb, rank, size, bcast, group)
             assert info == 0
             L = np.linalg.cholesky(K)
             low = np.tril_indices(n)

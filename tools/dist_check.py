@@ -1,5 +1,5 @@
 """Multi-GPU check + timing (run under torchrun on the GPU box, one rank per GPU):
-  torchrun --nnodes=1 --nproc-per-node G --master-addr 127.0.0.1 --master-port 29511 tools/dist_check.py [N] [nb]
+  torchrun --nnodes=1 --nproc-per-node G --master-addr 127.0.0.1 --master-port 29511 tools/dist_check.py [N] [nb] [panels_per_update]
 * block-column distributed Cholesky (pygp_b200.distchol) == single-GPU update, and its speed-up
 * sharded predict (test points) and sharded batched loglike / mixture posterior == single rank.
 Rank 0 prints JSON lines."""
@@ -18,7 +18,8 @@ sys.path.insert(0, ROOT)
 
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
-    nb = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
+    nb = int(sys.argv[2]) if len(sys.argv) > 2 else 512
+    ppu = int(sys.argv[3]) if len(sys.argv) > 3 else 1
     rank, world, local = int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), int(os.environ['LOCAL_RANK'])
     torch.cuda.set_device(local)
     os.environ['PYGP_B200_DEVICE'] = str(local)
@@ -53,13 +54,13 @@ def main():
         dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        distchol.distributed_update(g2, nb=nb)
+        distchol.distributed_update(g2, nb=nb, panels_per_update=ppu)
         ctx.sync()
         dist.barrier()
         t_dist = time.perf_counter() - t0
     lZ1 = g2.loglikelihood()
     mu1, s21 = g2.posterior(Xs[:256])
-    say(check='distributed_cholesky', n=n, nb=nb, world=world, lZ_single=lZ0, lZ_dist=lZ1,
+    say(check='distributed_cholesky', n=n, nb=nb, panels_per_update=ppu, world=world, lZ_single=lZ0, lZ_dist=lZ1,
         rel_err=abs(lZ1 - lZ0)/abs(lZ0), mu_err=float(np.abs(mu1 - mu0).max()), s2_err=float(np.abs(s21 - s20).max()),
         t_single_s=t_single, t_dist_s=t_dist, speedup=t_single/t_dist,
         tflops_single=n**3/3/t_single/1e12, tflops_dist_aggregate=n**3/3/t_dist/1e12)
