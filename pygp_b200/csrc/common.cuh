@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <unordered_map>
 #include <string>
 #include <utility>
@@ -208,6 +209,8 @@ inline void pool_release(pgp_ctx* ctx) {
 // host time, which shows when thousands of short kernels are chained.
 inline int ensure_dyn_smem_ptr(pgp_ctx* ctx, const void* kernel, size_t bytes) {
     static std::map<std::pair<int, const void*>, size_t> high;
+    static std::mutex mu;                       // contexts of different devices may live on different threads
+    std::lock_guard<std::mutex> lock(mu);
     size_t& h = high[std::make_pair(ctx->device, kernel)];
     if (bytes <= h) return 0;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
