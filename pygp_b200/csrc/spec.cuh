@@ -158,6 +158,9 @@ struct PartVal {
 };
 
 constexpr double kPi = 3.141592653589793238462643383279502884;
+// r / 3 of matern.py:50,54 as a multiplication: an IEEE double division is ~20 instructions per entry
+// (differs from the quotient by at most one ulp)
+constexpr double kThird = 1.0 / 3.0;
 
 template <bool GRAD>
 __device__ __forceinline__ void part_eval(const DevPart& p, double D, PartVal& v) {
@@ -172,11 +175,11 @@ __device__ __forceinline__ void part_eval(const DevPart& p, double D, PartVal& v
         case PGP_MATERN5: {
             double r = sqrt(D);
             double S = exp(p.two_logsf - r);
-            double f = p.type == PGP_MATERN1 ? 1.0 : p.type == PGP_MATERN3 ? 1 + r : 1 + r * (1 + r / 3.);
+            double f = p.type == PGP_MATERN1 ? 1.0 : p.type == PGP_MATERN3 ? 1 + r : 1 + r * (1 + r * kThird);
             double K = S * f;
             v.K = K;
             if (GRAD) {
-                double df = p.type == PGP_MATERN1 ? 1.0 : p.type == PGP_MATERN3 ? r : r * (1 + r) / 3.;
+                double df = p.type == PGP_MATERN1 ? 1.0 : p.type == PGP_MATERN3 ? r : r * (1 + r) * kThird;
                 double M = S * df;
                 v.g_sf = 2 * K;
                 v.g_iso = M * r;
