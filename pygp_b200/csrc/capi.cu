@@ -434,6 +434,8 @@ struct pgp_model {
     int64_t n = 0;
     int ndim = 0;
     int64_t ld = 0;
+    int64_t cap = 0;             // rows F can hold in place (ld = lead_dim(cap)); grows in steps on append
+    int64_t xcap = 0;            // rows allocated for X, y, Z, alpha
     double* d_X = nullptr;
     double* d_y = nullptr;
     double* d_Z = nullptr;       // [parts][n][ndim]
@@ -471,10 +473,11 @@ void model_free_work(pgp_model* m) {
 
 int model_alloc_work(pgp_model* m) {
     pgp_ctx* ctx = m->ctx;
-    m->ld = lead_dim(m->n);
-    PGP_TRY(pool_alloc(ctx, &m->d_Z, (size_t)m->spec.n_parts * m->n * m->ndim));
-    PGP_TRY(pool_alloc(ctx, &m->d_F, (size_t)(m->n + 1) * m->ld));
-    PGP_TRY(dev_alloc(ctx, &m->d_alpha, (size_t)m->n));
+    m->cap = m->n;                       // exact fit; pgp_exact_append_inc adds slack when it has to grow
+    m->ld = lead_dim(m->cap);
+    PGP_TRY(pool_alloc(ctx, &m->d_Z, (size_t)m->spec.n_parts * m->xcap * m->ndim));
+    PGP_TRY(pool_alloc(ctx, &m->d_F, (size_t)(m->cap + 1) * m->ld));
+    PGP_TRY(dev_alloc(ctx, &m->d_alpha, (size_t)m->xcap));
     return 0;
 }
 
@@ -482,20 +485,25 @@ int model_upload(pgp_model* m, const double* X, const double* y, int64_t n_old, 
     pgp_ctx* ctx = m->ctx;
     const int d = m->ndim;
     int64_t n = n_old + n_new;
-    double *nx = nullptr, *ny = nullptr;
-    PGP_TRY(dev_alloc(ctx, &nx, (size_t)n * d));
-    PGP_TRY(dev_alloc(ctx, &ny, (size_t)n));
-    if (n_old) {
-        PGP_CUDA(ctx, cudaMemcpyAsync(nx, m->d_X, sizeof(double) * n_old * d, cudaMemcpyDeviceToDevice, ctx->stream));
-        PGP_CUDA(ctx, cudaMemcpyAsync(ny, m->d_y, sizeof(double) * n_old, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (n > m->xcap) {                   // grow X, y (row capacity in multiples of 256)
+        const int64_t xcap = round_up(n, 256);
+        double *nx = nullptr, *ny = nullptr;
+        PGP_TRY(dev_alloc(ctx, &nx, (size_t)xcap * d));
+        PGP_TRY(dev_alloc(ctx, &ny, (size_t)xcap));
+        if (n_old) {
+            PGP_CUDA(ctx, cudaMemcpyAsync(nx, m->d_X, sizeof(double) * n_old * d, cudaMemcpyDeviceToDevice, ctx->stream));
+            PGP_CUDA(ctx, cudaMemcpyAsync(ny, m->d_y, sizeof(double) * n_old, cudaMemcpyDeviceToDevice, ctx->stream));
+            PGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        }
+        dev_free(ctx, m->d_X);
+        dev_free(ctx, m->d_y);
+        m->d_X = nx;
+        m->d_y = ny;
+        m->xcap = xcap;
     }
-    PGP_CUDA(ctx, cudaMemcpyAsync(nx + n_old * d, X, sizeof(double) * n_new * d, cudaMemcpyHostToDevice, ctx->stream));
-    PGP_CUDA(ctx, cudaMemcpyAsync(ny + n_old, y, sizeof(double) * n_new, cudaMemcpyHostToDevice, ctx->stream));
+    PGP_CUDA(ctx, cudaMemcpyAsync(m->d_X + n_old * d, X, sizeof(double) * n_new * d, cudaMemcpyHostToDevice, ctx->stream));
+    PGP_CUDA(ctx, cudaMemcpyAsync(m->d_y + n_old, y, sizeof(double) * n_new, cudaMemcpyHostToDevice, ctx->stream));
     PGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    dev_free(ctx, m->d_X);
-    dev_free(ctx, m->d_y);
-    m->d_X = nx;
-    m->d_y = ny;
     m->n = n;
     return 0;
 }
@@ -558,41 +566,62 @@ extern "C" int pgp_exact_append_inc(pgp_model* m, const double* X, const double*
     if (!m->factored) return ctx->fail(PGP_E_STATE, "incremental update before a successful update");
     PGP_TRY(set_device(ctx));
     const int d = m->ndim, np = m->spec.n_parts;
-    const int64_t n_old = m->n, n = n_old + n_new, ld_old = m->ld, ld = lead_dim(n);
+    const int64_t n_old = m->n, n = n_old + n_new, ld_old = m->ld;
     cudaStream_t s = ctx->stream;
-    // new buffers first; the model is only touched once everything is in place
-    double *nF = nullptr, *nZ = nullptr, *nAlpha = nullptr;
+    // The factor buffer has row capacity m->cap (ld = lead_dim(cap)): appends that fit are done IN PLACE
+    // (no reallocation, no copy of the n^2 / 2 factor); otherwise it grows by n / 8 + 256 rows of slack, so a
+    // loop that adds one datum at a time (Bayesian optimisation, SMC) reallocates once in hundreds of steps.
+    const bool inplace = n <= m->cap;
+    const int64_t cap = inplace ? m->cap : round_up(n + n / 8 + 256, 256);
+    const int64_t ld = inplace ? ld_old : lead_dim(cap);
+    double* nF = m->d_F;
     PoolBuf T;                                   // (n_new + 1, ldt) scratch block
     const int64_t ldt = lead_dim(n_new);
     PGP_TRY(T.get(ctx, (size_t)(n_new + 1) * ldt));
-    PGP_TRY(pool_alloc(ctx, &nF, (size_t)(n + 1) * ld));
-    int rc = pool_alloc(ctx, &nZ, (size_t)np * n * d);
-    if (!rc) rc = dev_alloc(ctx, &nAlpha, (size_t)n);
+    if (!inplace) PGP_TRY(pool_alloc(ctx, &nF, (size_t)(cap + 1) * ld));
+    // a failure must leave the model consistent (unfactored, buffers sized for m->n rows): the host
+    // falls back to a full pgp_exact_update
     auto bail = [&](int code) {
         cudaStreamSynchronize(s);
-        pool_free(ctx, nF, (size_t)(n + 1) * ld);
-        pool_free(ctx, nZ, (size_t)np * n * d);
-        dev_free(ctx, nAlpha);
+        if (!inplace && nF != m->d_F) dev_free(ctx, nF);
+        m->factored = false;
+        if (m->n > m->cap) {                     // X, y already grown but F was not: refit the work buffers
+            const int64_t nn = m->n;
+            m->n = n_old;
+            model_free_work(m);
+            m->n = nn;
+            int rc2 = model_alloc_work(m);
+            if (rc2) return rc2;
+        }
         return code;
     };
-    if (rc) return bail(rc);
-    // old factor and a into the wider buffer
-    cudaError_t e = cudaMemcpy2DAsync(nF, ld * 8, m->d_F, ld_old * 8, n_old * 8, n_old, cudaMemcpyDeviceToDevice, s);
+    int rc = 0;
+    // a (row n_old) moves to row n; in place this must precede the new rows (row n_old is the first of them)
+    cudaError_t e = cudaSuccess;
+    if (!inplace)
+        e = cudaMemcpy2DAsync(nF, ld * 8, m->d_F, ld_old * 8, n_old * 8, n_old, cudaMemcpyDeviceToDevice, s);
     if (e == cudaSuccess)
         e = cudaMemcpyAsync(nF + n * ld, m->d_F + n_old * ld_old, n_old * 8, cudaMemcpyDeviceToDevice, s);
     if (e != cudaSuccess) return bail(ctx->cuda_fail(e, "factor copy", __FILE__, __LINE__));
+    const int64_t xcap_old = m->xcap;
     if ((rc = model_upload(m, X, y, n_old, n_new))) return bail(rc);           // X, y grow (m->n = n now)
-    // from here on a failure must leave the model consistent for n rows (unfactored): the caller
-    // falls back to a full pgp_exact_update
-    auto bail_grown = [&](int code) {
-        bail(code);
-        m->n = n_old;
-        model_free_work(m);
-        m->n = n;
-        int rc2 = model_alloc_work(m);
-        return rc2 ? rc2 : code;
-    };
-    if ((rc = launch_scale(ctx, m->d_spec, m->d_X, n, d, np, nZ, 1))) return bail_grown(rc);
+    if (m->xcap != xcap_old) {                                                  // Z, alpha follow the row capacity
+        double *nZ = nullptr, *nAlpha = nullptr;
+        rc = pool_alloc(ctx, &nZ, (size_t)np * m->xcap * d);
+        if (!rc) rc = dev_alloc(ctx, &nAlpha, (size_t)m->xcap);
+        if (rc) {
+            dev_free(ctx, nZ);
+            dev_free(ctx, nAlpha);
+            return bail(rc);
+        }
+        cudaStreamSynchronize(s);
+        dev_free(ctx, m->d_Z);
+        dev_free(ctx, m->d_alpha);
+        m->d_Z = nZ;
+        m->d_alpha = nAlpha;
+    }
+    double* nZ = m->d_Z;
+    if ((rc = launch_scale(ctx, m->d_spec, m->d_X, n, d, np, nZ, 1))) return bail(rc);
     const int st = single_type(&m->spec);
     GramArgs g;                                   // new rows: k(Xnew, Xold)
     g.spec = m->d_spec;
@@ -601,12 +630,12 @@ extern "C" int pgp_exact_append_inc(pgp_model* m, const double* X, const double*
     g.ndim = d; g.n_parts = np;
     g.out = nF + n_old * ld; g.ldo = ld;
     g.single_type = st;
-    if ((rc = launch_gram(ctx, g))) return bail_grown(rc);
+    if ((rc = launch_gram(ctx, g))) return bail(rc);
     Mat F, Bn, Tm;
     F.p = nF; F.ld = ld;
     Bn.p = nF + n_old * ld; Bn.ld = ld;
     Tm.p = T.p; Tm.ld = ldt;
-    if ((rc = trsm_right_lt(ctx, Bn, n_new, F, n_old))) return bail_grown(rc);      // S^T = k(Xnew, X) L^-T
+    if ((rc = trsm_right_lt(ctx, Bn, n_new, F, n_old))) return bail(rc);      // S^T = k(Xnew, X) L^-T
     GramArgs gs;                                  // T = Kss + sn2 I (lower), row n_new = r_new
     gs.spec = m->d_spec;
     gs.Z1 = gs.Z2 = nZ + n_old * d; gs.zs1 = gs.zs2 = n * d; gs.n1 = gs.n2 = n_new;
@@ -614,8 +643,8 @@ extern "C" int pgp_exact_append_inc(pgp_model* m, const double* X, const double*
     gs.out = T.p; gs.ldo = ldt;
     gs.lower_only = 1; gs.add_noise = 1;
     gs.single_type = st;
-    if ((rc = launch_gram(ctx, gs))) return bail_grown(rc);
-    if ((rc = launch_set_residual_at(ctx, Tm, n_new, n_new, m->d_y, n_old, m->d_spec))) return bail_grown(rc);
+    if ((rc = launch_gram(ctx, gs))) return bail(rc);
+    if ((rc = launch_set_residual_at(ctx, Tm, n_new, n_new, m->d_y, n_old, m->d_spec))) return bail(rc);
     {   // T -= [S^T; a] S   (rows: the new rows and the residual row; contraction over the old columns)
         GemmArgs ga;
         ga.A = nF + n_old * ld; ga.lda = ld;
@@ -625,30 +654,35 @@ extern "C" int pgp_exact_append_inc(pgp_model* m, const double* X, const double*
         ga.alpha = -1.0; ga.beta = 1.0;
         ga.tri = 1;
         ga.splitk = 0;
-        if ((rc = launch_gemm(ctx, ga))) return bail_grown(rc);
+        if ((rc = launch_gemm(ctx, ga))) return bail(rc);
     }
-    if ((rc = cudaMemsetAsync(m->d_info, 0, sizeof(int), s) == cudaSuccess ? 0 : PGP_E_CUDA)) return bail_grown(rc);
-    if ((rc = potrf_lower(ctx, Tm, n_new, 1, m->d_info))) return bail_grown(rc);
+    if ((rc = cudaMemsetAsync(m->d_info, 0, sizeof(int), s) == cudaSuccess ? 0 : PGP_E_CUDA)) return bail(rc);
+    if ((rc = potrf_lower(ctx, Tm, n_new, 1, m->d_info))) return bail(rc);
     e = cudaMemcpy2DAsync(nF + n_old * ld + n_old, ld * 8, T.p, ldt * 8, n_new * 8, n_new + 1, cudaMemcpyDeviceToDevice, s);
-    if (e != cudaSuccess) return bail_grown(ctx->cuda_fail(e, "tail copy", __FILE__, __LINE__));
-    if ((rc = launch_loglik(ctx, F, n, m->d_res))) return bail_grown(rc);
+    if (e != cudaSuccess) return bail(ctx->cuda_fail(e, "tail copy", __FILE__, __LINE__));
+    if ((rc = launch_loglik(ctx, F, n, m->d_res))) return bail(rc);
     double* hp = ctx->h_pin;
     e = cudaMemcpyAsync(hp, m->d_res, sizeof(double), cudaMemcpyDeviceToHost, s);
     if (e == cudaSuccess) e = cudaMemcpyAsync(hp + 1, m->d_info, sizeof(int), cudaMemcpyDeviceToHost, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-    if (e != cudaSuccess) return bail_grown(ctx->cuda_fail(e, "incremental update", __FILE__, __LINE__));
-    // swap the work buffers in (model_free_work reads m->n and m->ld for the pool sizes)
+    if (e != cudaSuccess) return bail(ctx->cuda_fail(e, "incremental update", __FILE__, __LINE__));
+    // commit: the gradient / predict scratch is sized by (n, ld) and is rebuilt lazily
     const int info = *reinterpret_cast<int*>(hp + 1);
-    m->n = n_old;
-    model_free_work(m);
-    m->n = n;
-    m->ld = ld;
-    m->d_F = nF;
-    m->d_Z = nZ;
-    m->d_alpha = nAlpha;
+    dev_free(ctx, m->d_G); m->d_G = nullptr;
+    dev_free(ctx, m->d_H); m->d_H = nullptr;
+    dev_free(ctx, m->d_partials); m->d_partials = nullptr;
+    dev_free(ctx, m->d_Bc); m->d_Bc = nullptr;
+    m->bc_rows = 0;
+    if (!inplace) {
+        dev_free(ctx, m->d_F);
+        m->d_F = nF;
+        m->cap = cap;
+        m->ld = ld;
+    }
     m->lZ = hp[0];
     m->info = info ? (int)n_old + info : 0;
     if (info) {
+        m->factored = false;
         char buf[160];
         snprintf(buf, sizeof buf, "%d-th leading minor of the array is not positive definite", m->info);
         ctx->err = buf;
@@ -699,6 +733,7 @@ extern "C" int pgp_model_clone(const pgp_model* src, pgp_model** out) {
     m->info = src->info;
     const int64_t n = src->n;
     const int d = src->ndim;
+    m->xcap = n;                                   // the copy is an exact fit (the source may carry append slack)
     int rc = dev_alloc(ctx, &m->d_X, (size_t)n * d);
     if (!rc) rc = dev_alloc(ctx, &m->d_y, (size_t)n);
     if (!rc) rc = model_alloc_work(m);
@@ -715,7 +750,8 @@ extern "C" int pgp_model_clone(const pgp_model* src, pgp_model** out) {
     if (e == cudaSuccess && src->factored) {
         e = cudaMemcpyAsync(m->d_Z, src->d_Z, sizeof(double) * src->spec.n_parts * n * d, cudaMemcpyDeviceToDevice, s);
         if (e == cudaSuccess)
-            e = cudaMemcpyAsync(m->d_F, src->d_F, sizeof(double) * (n + 1) * src->ld, cudaMemcpyDeviceToDevice, s);
+            e = cudaMemcpy2DAsync(m->d_F, sizeof(double) * m->ld, src->d_F, sizeof(double) * src->ld, sizeof(double) * n,
+                                  n + 1, cudaMemcpyDeviceToDevice, s);
         if (e == cudaSuccess)
             e = cudaMemcpyAsync(m->d_spec, src->d_spec, sizeof(DevSpec), cudaMemcpyDeviceToDevice, s);
     }

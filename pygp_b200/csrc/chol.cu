@@ -401,6 +401,111 @@ int trsm_nt_rec(pgp_ctx* ctx, const Mat& B, int64_t rows, const Mat& L, int64_t 
 
 }  // namespace
 
+// ---------------------------------------------------------------------------
+// TRSM for a FEW rows (incremental update: the one new row of pgp_exact_append_inc,
+// exact.py:57-62).  The GEMM-based recursion computes 64-row tiles whatever the row
+// count -- for one row that is 64 x the flops and ~2 n / 64 launches of 15-20 us.
+// Here: blocks of 128 columns, right-looking:
+//   fewrows_solve_kernel   one CTA: the 128 x 128 diagonal block staged (transposed,
+//                          padded) in shared memory, thread j owns column j of up to
+//                          kFewRows rows; 128 substitution steps, x_k broadcast
+//                          through shared memory;
+//   fewrows_update_kernel  B[:, c] -= sum_k X[:, k] L[c][k] for every later column c:
+//                          one warp per column reads its 1 KB slice of row c of L --
+//                          the whole solve streams the n^2 / 2 entries of L once.
+// ---------------------------------------------------------------------------
+constexpr int kFewRows = 8;
+constexpr int kFewNB = 128;
+
+__global__ void __launch_bounds__(kFewNB) fewrows_solve_kernel(double* B, int64_t ldb, int rows, const double* L,
+                                                               int64_t ldl, int64_t j0, int nb) {
+    extern __shared__ double sm[];
+    constexpr int TP = kFewNB + 1;
+    double* Tt = sm;                          // Tt[k][j] = T[j][k]  (column k of the block contiguous in j)
+    double* xk = Tt + kFewNB * TP;            // [2][kFewRows] broadcast slots
+    const int j = threadIdx.x;
+    const double* T = L + j0 * ldl + j0;
+    for (int idx = threadIdx.x; idx < kFewNB * kFewNB; idx += kFewNB) {
+        int r = idx / kFewNB, c = idx - r * kFewNB;             // coalesced along c
+        double v = (r < nb && c <= r) ? T[(int64_t)r * ldl + c] : (r == c ? 1.0 : 0.0);
+        Tt[c * TP + r] = v;
+    }
+    double b[kFewRows];
+#pragma unroll
+    for (int r = 0; r < kFewRows; ++r) b[r] = (r < rows && j < nb) ? B[(int64_t)r * ldb + j0 + j] : 0.0;
+    __syncthreads();
+    int buf = 0;
+    for (int k = 0; k < nb; ++k) {
+        if (j == k) {
+            const double inv = 1.0 / Tt[k * TP + k];
+#pragma unroll
+            for (int r = 0; r < kFewRows; ++r) {
+                b[r] *= inv;
+                xk[buf * kFewRows + r] = b[r];
+            }
+        }
+        __syncthreads();
+        if (j > k) {
+            const double l = Tt[k * TP + j];
+#pragma unroll
+            for (int r = 0; r < kFewRows; ++r) b[r] -= xk[buf * kFewRows + r] * l;
+        }
+        buf ^= 1;
+    }
+#pragma unroll
+    for (int r = 0; r < kFewRows; ++r)
+        if (r < rows && j < nb) B[(int64_t)r * ldb + j0 + j] = b[r];
+}
+
+__global__ void __launch_bounds__(256) fewrows_update_kernel(double* B, int64_t ldb, int rows, const double* L,
+                                                             int64_t ldl, int64_t j0, int nb, int64_t c0, int64_t n) {
+    __shared__ double xs[kFewRows * kFewNB];
+    for (int idx = threadIdx.x; idx < kFewRows * kFewNB; idx += 256) {
+        int r = idx / kFewNB, k = idx - r * kFewNB;
+        xs[idx] = (r < rows && k < nb) ? B[(int64_t)r * ldb + j0 + k] : 0.0;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = (int64_t)gridDim.x * 8, w0 = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    for (int64_t c = c0 + w0; c < n; c += warps) {
+        const double* Lc = L + c * ldl + j0;
+        double l[kFewNB / 32];
+#pragma unroll
+        for (int q = 0; q < kFewNB / 32; ++q) l[q] = (lane + 32 * q < nb) ? Lc[lane + 32 * q] : 0.0;
+#pragma unroll
+        for (int r = 0; r < kFewRows; ++r) {
+            if (r >= rows) break;
+            double s = 0.0;
+#pragma unroll
+            for (int q = 0; q < kFewNB / 32; ++q) s += l[q] * xs[r * kFewNB + lane + 32 * q];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) B[(int64_t)r * ldb + c] -= s;
+        }
+    }
+}
+
+int trsm_fewrows(pgp_ctx* ctx, const Mat& B, int64_t rows, const Mat& L, int64_t n) {
+    const size_t smem = ((size_t)kFewNB * (kFewNB + 1) + 2 * kFewRows) * sizeof(double);
+    PGP_TRY(ensure_dyn_smem(ctx, fewrows_solve_kernel, smem));
+    for (int64_t j0 = 0; j0 < n; j0 += kFewNB) {
+        const int nb = (int)std::min<int64_t>(kFewNB, n - j0);
+        {
+            Launch Lc(ctx, PC_TRSM, (double)rows * nb * nb);
+            fewrows_solve_kernel<<<1, kFewNB, smem, ctx->stream>>>(B.p, B.ld, (int)rows, L.p, L.ld, j0, nb);
+            PGP_TRY(check_launch(ctx, "fewrows_solve_kernel"));
+        }
+        const int64_t c0 = j0 + nb;
+        if (c0 < n) {
+            Launch Lc(ctx, PC_TRSM, 2.0 * rows * nb * (double)(n - c0));
+            int blocks = (int)std::min<int64_t>(ceil_div(n - c0, 8), (int64_t)ctx->sm_count * 8);
+            fewrows_update_kernel<<<blocks, 256, 0, ctx->stream>>>(B.p, B.ld, (int)rows, L.p, L.ld, j0, nb, c0, n);
+            PGP_TRY(check_launch(ctx, "fewrows_update_kernel"));
+        }
+    }
+    return 0;
+}
+
 int potrf_lower(pgp_ctx* ctx, const Mat& F, int64_t n, int64_t extra, int* d_info) {
     if (n <= 0) return 0;
     static const int la = [] { const char* e = getenv("PGP_CHOL_LOOKAHEAD"); return e ? atoi(e) : 1; }();
@@ -410,6 +515,8 @@ int potrf_lower(pgp_ctx* ctx, const Mat& F, int64_t n, int64_t extra, int* d_inf
 
 int trsm_right_lt(pgp_ctx* ctx, const Mat& B, int64_t rows, const Mat& L, int64_t n) {
     if (n <= 0 || rows <= 0) return 0;
+    static const int few = [] { const char* e = getenv("PGP_TRSM_FEWROWS"); return e ? atoi(e) : 1; }();
+    if (few && rows <= kFewRows && B.batch == 1 && L.batch == 1 && n >= 512) return trsm_fewrows(ctx, B, rows, L, n);
     return trsm_rec(ctx, B, rows, L, 0, n);
 }
 

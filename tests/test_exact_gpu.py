@@ -280,6 +280,9 @@ def test_posterior_input_gradients(name, golden):
     (('se', 1.0, [0.5, 0.6]), 2, 10, [10]),                       # reference tests/test_inference.py:65-79
     (('matern', 1.0, [0.7, 0.8, 0.9], 5), 3, 301, [1, 1, 64, 130, 3]),   # odd sizes, across tile edges
     (('sum', ('se', 1.0, 0.5), ('periodic', 0.5, 1.0, 0.25)), 1, 1000, [24]),
+    # one to eight new rows on n >= 512: the few-rows TRSM (chol.cu: trsm_fewrows), in place after the first growth
+    (('se', 1.0, [0.5, 0.6, 0.7, 0.8]), 4, 700, [1, 1, 5, 8, 1, 2]),
+    (('matern', 1.0, [0.4, 0.5], 3), 2, 1537, [1, 7, 1]),
 ])
 def test_incremental_update_equals_full(spec, d, n0, adds):
     """_updateinc (exact.py:57-62 + mwhutils.linalg.chol_update): growing the
@@ -309,6 +312,9 @@ def test_incremental_update_equals_full(spec, d, n0, adds):
     nt.assert_allclose(mu, mu0, rtol=1e-9, atol=1e-10)
     nt.assert_allclose(s2, s20, rtol=1e-8, atol=1e-11)
     nt.assert_allclose(inc._a, full._a, rtol=1e-8, atol=1e-9)
+    nt.assert_allclose(inc._R, full._R, rtol=1e-8, atol=1e-10)      # factor buffer with append slack (ld != lead_dim(n))
+    cp = inc.copy()                                                  # a clone is an exact fit again
+    nt.assert_allclose(cp.loglikelihood(), lZ0, rtol=1e-10)
     ogp = OExactGP(0.1, make_kernel(spec), 0.1)
     ogp.add_data(X, y)
     nt.assert_allclose(lZ, ogp.loglikelihood(), rtol=1e-10)
