@@ -408,7 +408,11 @@ int launch_gemm(pgp_ctx* ctx, const GemmArgs& a_in) {
     };
     const int64_t tiles128 = count_tiles(128) * a.batch;
     static const int force_tile = [] { const char* e = getenv("PGP_GEMM_TILE"); return e ? atoi(e) : 0; }();
-    const bool small = force_tile ? force_tile == 64 : tiles128 < (int64_t)ctx->sm_count;
+    // ... or when the output is at most 64 wide (K = 64 leaf updates of the recursions, C[M x 64] -= A B^T): a
+    // 128-wide tile would compute half padding
+    static const int narrow64 = [] { const char* e = getenv("PGP_GEMM_NARROW64"); return e ? atoi(e) : 1; }();
+    const bool small = force_tile ? force_tile == 64
+                                  : (tiles128 < (int64_t)ctx->sm_count || (narrow64 && (a.N <= 64 || a.M <= 64)));
     const int BM = small ? 64 : 128, BN = BM;
     int64_t tm = ceil_div(a.M, (int64_t)BM), tn = ceil_div(a.N, (int64_t)BN);
     if (tm * tn > 0x7fffffffLL || a.batch > 65535) return ctx->fail(PGP_E_ARG, "gemm: grid too large");
