@@ -36,14 +36,83 @@ inline int64_t split_point(int64_t n) {
 // ---------------------------------------------------------------------------
 // potrf_base: one CTA factors the n x n (n <= 64) diagonal block at (j0, j0).
 // 16 x 16 threads, each owning a cyclic 4 x 4 register micro-tile (rows
-// ty + 16a, columns tx + 16b), so every thread stays busy as the trailing
-// matrix shrinks.  One barrier per column: the owners of column k publish it
-// (double-buffered), everybody derives 1/sqrt(pivot) redundantly and applies
-// the rank-1 update to its registers with 16 independent FMAs.
+// ty + 16a, columns tx + 16b).  One barrier per column: the owners of column k
+// publish it (double-buffered), everybody derives 1/sqrt(pivot) redundantly and
+// applies the rank-1 update to its registers.
+//
+// This kernel is the critical path of every N <= 16k factorisation (N / 64
+// strictly sequential launches), so it is shaped by its DEPENDENCY CHAIN, measured
+// with tools/potrf_probe.cu (profiles/r01f_potrf_probe.txt): a dependent DFMA is
+// 8 cycles, a shared load 29-36, the barrier itself 9 -- but a rolled column loop
+// with divergent owner blocks spent ~190 of its ~430 cycles per column on control
+// flow.  Hence: the 64 steps are fully unrolled (k is a constant, so the row /
+// column masks of the tiles below the current one fold away and only the live
+// tiles x >= kb, kb <= y <= x are touched), the owners write the finished column
+// to a shared output tile instead of back into their registers (nothing depends
+// on it; the block leaves through one coalesced store), 1/sqrt is one third-order
+// step from the hardware seed (4 dependent FP64 operations, error 2.7e-16), and
+// rows / columns >= n are identity padding, so there is no per-step bound check.
+// 26 -> 14 us per launch on the same box.
 // ---------------------------------------------------------------------------
+constexpr int kPoLd = kNB + 1;
+
+// y (1 + e/2 + 3 e^2/8), e = 1 - d y^2, from the 20-bit seed: relative error (5/16) e^3 < 1e-18 + rounding
+__device__ __forceinline__ double rsqrt_3rd(double d) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    const double t = d * y;
+    const double e = fma(-t, y, 1.0);
+    const double p = fma(0.375, e, 0.5);
+    const double ye = y * e;
+    return fma(ye, p, y);
+}
+
+template <int KB>
+__device__ __forceinline__ void potrf_base_block(double (&a)[4][4], double (*colbuf)[kNB], double* Lout, int tx, int ty,
+                                                 int& bad) {
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+        const int k = KB * 16 + kk;
+        const int buf = kk & 1;
+        if (tx == kk) {
+#pragma unroll
+            for (int x = KB; x < 4; ++x) colbuf[buf][ty + 16 * x] = a[x][KB];
+        }
+        __syncthreads();
+        const double d = colbuf[buf][k];
+        double ci[4], cj[4];
+#pragma unroll
+        for (int x = KB; x < 4; ++x) ci[x] = colbuf[buf][ty + 16 * x];
+#pragma unroll
+        for (int y = KB; y < 4; ++y) cj[y] = colbuf[buf][tx + 16 * y];
+        // not positive definite (or NaN): remember the first failing minor; the NaN / inf that the
+        // seed returns for d <= 0 propagates, as LAPACK's caller would stop here anyway
+        const double inv = rsqrt_3rd(d);
+        if (!(d > 0.0) && bad == 0) bad = k + 1;
+        double li[4], lj[4];
+        li[KB] = ty > kk ? ci[KB] * inv : 0.0;
+        lj[KB] = tx > kk ? cj[KB] * inv : 0.0;
+#pragma unroll
+        for (int x = KB + 1; x < 4; ++x) li[x] = ci[x] * inv;
+#pragma unroll
+        for (int y = KB + 1; y < 4; ++y) lj[y] = cj[y] * inv;
+#pragma unroll
+        for (int x = KB; x < 4; ++x)
+#pragma unroll
+            for (int y = KB; y <= x; ++y) a[x][y] = fma(-li[x], lj[y], a[x][y]);
+        if (tx == kk) {
+            // d * inv = sqrt(d) to ~1 ulp
+            if (ty >= kk) Lout[(ty + 16 * KB) * kPoLd + k] = ty == kk ? d * inv : li[KB];
+#pragma unroll
+            for (int x = KB + 1; x < 4; ++x) Lout[(ty + 16 * x) * kPoLd + k] = li[x];
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) potrf_base_kernel(double* F, int64_t ld, int64_t bstride,
                                                          int64_t j0, int n, int* info) {
     __shared__ double colbuf[2][kNB];
+    __shared__ double Lout[kNB * kPoLd];
     double* Fb = F + (int64_t)blockIdx.x * bstride + j0 * ld + j0;
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
 
@@ -58,55 +127,17 @@ __global__ void __launch_bounds__(256) potrf_base_kernel(double* F, int64_t ld, 
             a[x][y] = v;
         }
 
-    int buf = 0;
-#pragma unroll
-    for (int kb = 0; kb < 4; ++kb) {
-#pragma unroll 1
-        for (int kk = 0; kk < 16; ++kk) {
-            const int k = kb * 16 + kk;
-            if (k >= n) break;
-            if (tx == kk) {
-#pragma unroll
-                for (int x = 0; x < 4; ++x) colbuf[buf][ty + 16 * x] = a[x][kb];
-            }
-            __syncthreads();
-            const double d = colbuf[buf][k];
-            double inv;
-            if (d > 0.0) {
-                inv = rsqrt(d);
-            } else {
-                // not positive definite (or NaN): report the first failing minor
-                if (threadIdx.x == 0) atomicCAS(info + blockIdx.x, 0, (int)(j0 + k + 1));
-                inv = nan("");
-            }
-            double li[4], lj[4];
-#pragma unroll
-            for (int x = 0; x < 4; ++x) li[x] = (ty + 16 * x > k) ? colbuf[buf][ty + 16 * x] * inv : 0.0;
-#pragma unroll
-            for (int y = 0; y < 4; ++y) lj[y] = (tx + 16 * y > k) ? colbuf[buf][tx + 16 * y] * inv : 0.0;
-#pragma unroll
-            for (int x = 0; x < 4; ++x)
-#pragma unroll
-                for (int y = 0; y < 4; ++y) a[x][y] -= li[x] * lj[y];
-            if (tx == kk) {
-#pragma unroll
-                for (int x = 0; x < 4; ++x) {
-                    int r = ty + 16 * x;
-                    if (r > k) a[x][kb] = li[x];
-                    else if (r == k) a[x][kb] = d * inv;   // = sqrt(d) to ~1 ulp (NaN if not PD); a full sqrt() here sits on
-                                                           // the per-column critical path of the whole warp
-                }
-            }
-            buf ^= 1;
-        }
+    int bad = 0;
+    potrf_base_block<0>(a, colbuf, Lout, tx, ty, bad);
+    if (n > 16) potrf_base_block<1>(a, colbuf, Lout, tx, ty, bad);
+    if (n > 32) potrf_base_block<2>(a, colbuf, Lout, tx, ty, bad);
+    if (n > 48) potrf_base_block<3>(a, colbuf, Lout, tx, ty, bad);
+    if (bad && bad <= n && threadIdx.x == 0) atomicCAS(info + blockIdx.x, 0, (int)(j0 + bad));
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < kNB * kNB; idx += 256) {
+        const int r = idx >> 6, c = idx & 63;
+        if (r < n && c <= r) Fb[(int64_t)r * ld + c] = Lout[r * kPoLd + c];
     }
-#pragma unroll
-    for (int x = 0; x < 4; ++x)
-#pragma unroll
-        for (int y = 0; y < 4; ++y) {
-            int r = ty + 16 * x, c = tx + 16 * y;
-            if (r < n && c <= r) Fb[(int64_t)r * ld + c] = a[x][y];
-        }
 }
 
 // ---------------------------------------------------------------------------
@@ -412,8 +443,7 @@ int trsm_nt_rec(pgp_ctx* ctx, const Mat& B, int64_t rows, const Mat& L, int64_t 
 // Here: blocks of 128 columns, right-looking:
 //   fewrows_solve_kernel   one CTA: the 128 x 128 diagonal block staged (transposed,
 //                          padded) in shared memory, thread j owns column j of up to
-//                          kFewRows rows; 128 substitution steps, x_k broadcast
-//                          through shared memory;
+//                          kFewRows rows; 128 substitution steps (see the kernel);
 //   fewrows_update_kernel  B[:, c] -= sum_k X[:, k] L[c][k] for every later column c:
 //                          one warp per column reads its 1 KB slice of row c of L --
 //                          the whole solve streams the n^2 / 2 entries of L once.
@@ -421,43 +451,58 @@ int trsm_nt_rec(pgp_ctx* ctx, const Mat& B, int64_t rows, const Mat& L, int64_t 
 constexpr int kFewRows = 8;
 constexpr int kFewNB = 128;
 
+// The substitution is a chain of dependent steps, so it is organised around its latency: warp w owns
+// columns 32 w .. 32 w + 31 (lane = column).  Inside a warp x_k travels by shuffle (multiply 8 + shuffle ~30
+// + FMA 8 cycles per step, no barrier); between warps one barrier per 32 columns, after which the later
+// warps apply the 32 finished x_k from shared memory.  Reciprocals of the diagonal are taken while the
+// block is staged (a division in the chain costs more than the step itself).
+template <int ROWS>
 __global__ void __launch_bounds__(kFewNB) fewrows_solve_kernel(double* B, int64_t ldb, int rows, const double* L,
                                                                int64_t ldl, int64_t j0, int nb) {
     extern __shared__ double sm[];
     constexpr int TP = kFewNB + 1;
     double* Tt = sm;                          // Tt[k][j] = T[j][k]  (column k of the block contiguous in j)
-    double* xk = Tt + kFewNB * TP;            // [2][kFewRows] broadcast slots
-    const int j = threadIdx.x;
+    double* xs = Tt + kFewNB * TP;            // [ROWS][128] finished x of the block
+    const int j = threadIdx.x, w = j >> 5, lane = j & 31;
     const double* T = L + j0 * ldl + j0;
     for (int idx = threadIdx.x; idx < kFewNB * kFewNB; idx += kFewNB) {
         int r = idx / kFewNB, c = idx - r * kFewNB;             // coalesced along c
-        double v = (r < nb && c <= r) ? T[(int64_t)r * ldl + c] : (r == c ? 1.0 : 0.0);
+        double v = (r < nb && c <= r) ? T[(int64_t)r * ldl + c] : (r == c ? 1.0 : 0.0);   // identity padding
         Tt[c * TP + r] = v;
     }
-    double b[kFewRows];
+    double b[ROWS];
 #pragma unroll
-    for (int r = 0; r < kFewRows; ++r) b[r] = (r < rows && j < nb) ? B[(int64_t)r * ldb + j0 + j] : 0.0;
+    for (int r = 0; r < ROWS; ++r) b[r] = (r < rows && j < nb) ? B[(int64_t)r * ldb + j0 + j] : 0.0;
+    const double rinv = j < nb ? 1.0 / T[(int64_t)j * ldl + j] : 1.0;
     __syncthreads();
-    int buf = 0;
-    for (int k = 0; k < nb; ++k) {
-        if (j == k) {
-            const double inv = 1.0 / Tt[k * TP + k];
 #pragma unroll
-            for (int r = 0; r < kFewRows; ++r) {
-                b[r] *= inv;
-                xk[buf * kFewRows + r] = b[r];
+    for (int s = 0; s < kFewNB / 32; ++s) {
+        if (w == s) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+                const double l = Tt[(32 * s + k) * TP + j];        // T[j][32 s + k]
+#pragma unroll
+                for (int r = 0; r < ROWS; ++r) {
+                    const double xk = __shfl_sync(0xffffffffu, b[r] * rinv, k);
+                    if (lane == k) b[r] = xk;
+                    else if (lane > k) b[r] = fma(-xk, l, b[r]);
+                }
             }
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r) xs[r * kFewNB + j] = b[r];
         }
         __syncthreads();
-        if (j > k) {
-            const double l = Tt[k * TP + j];
+        if (w > s) {
+#pragma unroll 8
+            for (int k = 0; k < 32; ++k) {
+                const double l = Tt[(32 * s + k) * TP + j];
 #pragma unroll
-            for (int r = 0; r < kFewRows; ++r) b[r] -= xk[buf * kFewRows + r] * l;
+                for (int r = 0; r < ROWS; ++r) b[r] = fma(-xs[r * kFewNB + 32 * s + k], l, b[r]);
+            }
         }
-        buf ^= 1;
     }
 #pragma unroll
-    for (int r = 0; r < kFewRows; ++r)
+    for (int r = 0; r < ROWS; ++r)
         if (r < rows && j < nb) B[(int64_t)r * ldb + j0 + j] = b[r];
 }
 
@@ -490,13 +535,15 @@ __global__ void __launch_bounds__(256) fewrows_update_kernel(double* B, int64_t 
 }
 
 int trsm_fewrows(pgp_ctx* ctx, const Mat& B, int64_t rows, const Mat& L, int64_t n) {
-    const size_t smem = ((size_t)kFewNB * (kFewNB + 1) + 2 * kFewRows) * sizeof(double);
-    PGP_TRY(ensure_dyn_smem(ctx, fewrows_solve_kernel, smem));
+    const size_t smem = ((size_t)kFewNB * (kFewNB + 1) + (size_t)kFewRows * kFewNB) * sizeof(double);
+    auto solve = rows == 1 ? fewrows_solve_kernel<1> : rows == 2 ? fewrows_solve_kernel<2>
+               : rows <= 4 ? fewrows_solve_kernel<4> : fewrows_solve_kernel<8>;
+    PGP_TRY(ensure_dyn_smem(ctx, solve, smem));
     for (int64_t j0 = 0; j0 < n; j0 += kFewNB) {
         const int nb = (int)std::min<int64_t>(kFewNB, n - j0);
         {
             Launch Lc(ctx, PC_TRSM, (double)rows * nb * nb);
-            fewrows_solve_kernel<<<1, kFewNB, smem, ctx->stream>>>(B.p, B.ld, (int)rows, L.p, L.ld, j0, nb);
+            solve<<<1, kFewNB, smem, ctx->stream>>>(B.p, B.ld, (int)rows, L.p, L.ld, j0, nb);
             PGP_TRY(check_launch(ctx, "fewrows_solve_kernel"));
         }
         const int64_t c0 = j0 + nb;

@@ -161,6 +161,254 @@ __global__ void __launch_bounds__(256) v0_kernel(double* F, int64_t ld, int n, i
         }
 }
 
+// ---- V2: V0 without the dead work ---------------------------------------------------------------
+// In column block kb (16 columns) the micro-tile rows x < kb and columns y < kb are finished and the
+// tiles y > x lie above the diagonal: only x >= kb, kb <= y <= x are updated (10 / 6 / 3 / 1 of the 16
+// register entries), the column values are fetched before the pivot's rsqrt so that their latency
+// overlaps it, and 1/sqrt is one third-order step from the hardware seed (4 dependent FP64 operations).
+template <int KB>
+__device__ __forceinline__ void v2_block(double (&a)[4][4], double (*colbuf)[NB], int& buf, int n, int tx, int ty, int* info) {
+#pragma unroll 1
+    for (int kk = 0; kk < 16; ++kk) {
+        const int k = KB * 16 + kk;
+        if (k >= n) break;
+        if (tx == kk) {
+#pragma unroll
+            for (int x = KB; x < 4; ++x) colbuf[buf][ty + 16 * x] = a[x][KB];
+        }
+        __syncthreads();
+        const double d = colbuf[buf][k];
+        double ci[4], cj[4];
+#pragma unroll
+        for (int x = KB; x < 4; ++x) ci[x] = colbuf[buf][ty + 16 * x];
+#pragma unroll
+        for (int y = KB; y < 4; ++y) cj[y] = colbuf[buf][tx + 16 * y];
+        double inv;
+        if (d > 0.0) {
+            inv = rsqrt3(d);
+        } else {
+            if (threadIdx.x == 0) atomicCAS(info, 0, k + 1);
+            inv = nan("");
+        }
+        double li[4], lj[4];
+#pragma unroll
+        for (int x = KB; x < 4; ++x) li[x] = (ty + 16 * x > k) ? ci[x] * inv : 0.0;
+#pragma unroll
+        for (int y = KB; y < 4; ++y) lj[y] = (tx + 16 * y > k) ? cj[y] * inv : 0.0;
+#pragma unroll
+        for (int x = KB; x < 4; ++x)
+#pragma unroll
+            for (int y = KB; y <= x; ++y) a[x][y] -= li[x] * lj[y];
+        if (tx == kk) {
+#pragma unroll
+            for (int x = KB; x < 4; ++x) {
+                int r = ty + 16 * x;
+                if (r > k) a[x][KB] = li[x];
+                else if (r == k) a[x][KB] = d * inv;
+            }
+        }
+        buf ^= 1;
+    }
+}
+
+__global__ void __launch_bounds__(256) v2_kernel(double* F, int64_t ld, int n, int* info, long long* clk) {
+    __shared__ double colbuf[2][NB];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    double a[4][4];
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y) {
+            int r = ty + 16 * x, c = tx + 16 * y;
+            double v = (r == c) ? 1.0 : 0.0;
+            if (r < n && c <= r) v = F[(int64_t)r * ld + c];
+            a[x][y] = v;
+        }
+    int buf = 0;
+    v2_block<0>(a, colbuf, buf, n, tx, ty, info);
+    v2_block<1>(a, colbuf, buf, n, tx, ty, info);
+    v2_block<2>(a, colbuf, buf, n, tx, ty, info);
+    v2_block<3>(a, colbuf, buf, n, tx, ty, info);
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y) {
+            int r = ty + 16 * x, c = tx + 16 * y;
+            if (r < n && c <= r) F[(int64_t)r * ld + c] = a[x][y];
+        }
+}
+
+// ---- V2 instrumented at fine grain (32-bit clock, thread `who`; the cost of a back-to-back clock pair is
+// reported so it can be subtracted) ------------------------------------------------------------------
+#define TICK(i) { unsigned t_ = clock(); acc[i] += t_ - last; last = t_; }
+template <int KB>
+__device__ __forceinline__ void v2i_block(double (&a)[4][4], double (*colbuf)[NB], int& buf, int n, int tx, int ty,
+                                          unsigned (&acc)[10], unsigned& last) {
+#pragma unroll 1
+    for (int kk = 0; kk < 16; ++kk) {
+        const int k = KB * 16 + kk;
+        if (k >= n) break;
+        TICK(0)                                   // loop overhead
+        if (tx == kk) {
+#pragma unroll
+            for (int x = KB; x < 4; ++x) colbuf[buf][ty + 16 * x] = a[x][KB];
+        }
+        TICK(1)                                   // owner store
+        __syncthreads();
+        TICK(2)                                   // barrier
+        const double d = colbuf[buf][k];
+        asm volatile("" ::"d"(d));
+        TICK(3)                                   // pivot load
+        double ci[4], cj[4];
+#pragma unroll
+        for (int x = KB; x < 4; ++x) ci[x] = colbuf[buf][ty + 16 * x];
+#pragma unroll
+        for (int y = KB; y < 4; ++y) cj[y] = colbuf[buf][tx + 16 * y];
+        asm volatile("" ::"d"(ci[3]), "d"(cj[3]));
+        TICK(4)                                   // column loads
+        double inv = d > 0.0 ? rsqrt3(d) : nan("");
+        asm volatile("" ::"d"(inv));
+        TICK(5)                                   // rsqrt
+        double li[4], lj[4];
+#pragma unroll
+        for (int x = KB; x < 4; ++x) li[x] = (ty + 16 * x > k) ? ci[x] * inv : 0.0;
+#pragma unroll
+        for (int y = KB; y < 4; ++y) lj[y] = (tx + 16 * y > k) ? cj[y] * inv : 0.0;
+        asm volatile("" ::"d"(li[3]), "d"(lj[3]));
+        TICK(6)                                   // scaling
+#pragma unroll
+        for (int x = KB; x < 4; ++x)
+#pragma unroll
+            for (int y = KB; y <= x; ++y) a[x][y] -= li[x] * lj[y];
+        asm volatile("" ::"d"(a[3][3]), "d"(a[3][KB]));
+        TICK(7)                                   // rank-1 update
+        if (tx == kk) {
+#pragma unroll
+            for (int x = KB; x < 4; ++x) {
+                int r = ty + 16 * x;
+                if (r > k) a[x][KB] = li[x];
+                else if (r == k) a[x][KB] = d * inv;
+            }
+        }
+        asm volatile("" ::"d"(a[3][KB]));
+        TICK(8)                                   // owner write-back to registers
+        buf ^= 1;
+    }
+}
+
+__global__ void __launch_bounds__(256) v2i_kernel(double* F, int64_t ld, int n, int who, unsigned* out) {
+    __shared__ double colbuf[2][NB];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    double a[4][4];
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y) {
+            int r = ty + 16 * x, c = tx + 16 * y;
+            double v = (r == c) ? 1.0 : 0.0;
+            if (r < n && c <= r) v = F[(int64_t)r * ld + c];
+            a[x][y] = v;
+        }
+    unsigned acc[10];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) acc[i] = 0;
+    unsigned last = clock();
+    {   // calibration: 64 back-to-back pairs
+        unsigned t0 = clock();
+#pragma unroll 1
+        for (int i = 0; i < 64; ++i) { unsigned t_ = clock(); acc[9] += t_ - t0; t0 = t_; }
+        last = clock();
+    }
+    int buf = 0;
+    v2i_block<0>(a, colbuf, buf, n, tx, ty, acc, last);
+    v2i_block<1>(a, colbuf, buf, n, tx, ty, acc, last);
+    v2i_block<2>(a, colbuf, buf, n, tx, ty, acc, last);
+    v2i_block<3>(a, colbuf, buf, n, tx, ty, acc, last);
+    if (threadIdx.x == who)
+        for (int i = 0; i < 10; ++i) out[i] = acc[i];
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y) {
+            int r = ty + 16 * x, c = tx + 16 * y;
+            if (r < n && c <= r) F[(int64_t)r * ld + c] = a[x][y];
+        }
+}
+
+// ---- V3: V2 with the control flow taken off the dependency chain -------------------------------
+// Fine-grain clocks of V2 (above): of ~430 cycles per column only ~210 are the dependency chain
+// (pivot load 36, 1/sqrt 95, scale 8, update 8, store -> barrier -> load ~60); the rest is the rolled
+// loop (46), the divergent owner blocks (56 + 84) and per-entry predicates.  Here the 64 steps are
+// fully unrolled (k is a constant: the row/column masks of the tiles x > KB disappear), the owners
+// write the finished column to a shared output tile instead of back into their registers (nothing
+// depends on it), and the block leaves through one coalesced store.  Rows / columns >= n are identity
+// padding, so there is no per-step bound check.
+constexpr int LDO = NB + 1;
+template <int KB>
+__device__ __forceinline__ void v3_block(double (&a)[4][4], double (*colbuf)[NB], double* Lout, int tx, int ty, int& bad) {
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+        const int k = KB * 16 + kk;
+        const int buf = kk & 1;
+        if (tx == kk) {
+#pragma unroll
+            for (int x = KB; x < 4; ++x) colbuf[buf][ty + 16 * x] = a[x][KB];
+        }
+        __syncthreads();
+        const double d = colbuf[buf][k];
+        double ci[4], cj[4];
+#pragma unroll
+        for (int x = KB; x < 4; ++x) ci[x] = colbuf[buf][ty + 16 * x];
+#pragma unroll
+        for (int y = KB; y < 4; ++y) cj[y] = colbuf[buf][tx + 16 * y];
+        const double inv = rsqrt3(d);
+        if (!(d > 0.0) && bad == 0) bad = k + 1;
+        double li[4], lj[4];
+        li[KB] = ty > kk ? ci[KB] * inv : 0.0;
+        lj[KB] = tx > kk ? cj[KB] * inv : 0.0;
+#pragma unroll
+        for (int x = KB + 1; x < 4; ++x) li[x] = ci[x] * inv;
+#pragma unroll
+        for (int y = KB + 1; y < 4; ++y) lj[y] = cj[y] * inv;
+#pragma unroll
+        for (int x = KB; x < 4; ++x)
+#pragma unroll
+            for (int y = KB; y <= x; ++y) a[x][y] = fma(-li[x], lj[y], a[x][y]);
+        if (tx == kk) {
+            if (ty >= kk) Lout[(ty + 16 * KB) * LDO + k] = ty == kk ? d * inv : li[KB];
+#pragma unroll
+            for (int x = KB + 1; x < 4; ++x) Lout[(ty + 16 * x) * LDO + k] = li[x];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) v3_kernel(double* F, int64_t ld, int n, int* info, long long* clk) {
+    __shared__ double colbuf[2][NB];
+    __shared__ double Lout[NB * LDO];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    double a[4][4];
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y) {
+            int r = ty + 16 * x, c = tx + 16 * y;
+            double v = (r == c) ? 1.0 : 0.0;
+            if (r < n && c <= r) v = F[(int64_t)r * ld + c];
+            a[x][y] = v;
+        }
+    int bad = 0;
+    v3_block<0>(a, colbuf, Lout, tx, ty, bad);
+    if (n > 16) v3_block<1>(a, colbuf, Lout, tx, ty, bad);
+    if (n > 32) v3_block<2>(a, colbuf, Lout, tx, ty, bad);
+    if (n > 48) v3_block<3>(a, colbuf, Lout, tx, ty, bad);
+    if (bad && bad <= n && threadIdx.x == 0) atomicCAS(info, 0, bad);
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < NB * NB; idx += 256) {
+        const int r = idx >> 6, c = idx & 63;
+        if (r < n && c <= r) F[(int64_t)r * ld + c] = Lout[r * LDO + c];
+    }
+}
+
 // ---- V1: ONE warp, the whole block in registers ----------------------------------------------
 // Lane l owns rows l and l + 32:  A[c] = a[l][c] (c < 32), S[c] = a[l+32][c] (c < 32),
 // T[c] = a[l+32][32+c].  Fully unrolled right-looking factorisation: per column the
@@ -256,6 +504,39 @@ __global__ void __launch_bounds__(32) v1_kernel(double* __restrict__ F, int64_t 
     }
 }
 
+// FP64 issue rate seen by ONE CTA: W warps, each thread 16 independent DFMA chains, ITER rounds.
+__global__ void dp_rate_kernel(double* out, long long* clk, int iters) {
+    double a[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = threadIdx.x * 1e-3 + i;
+    const double m = 1.0000001, c = 1e-9;
+    __syncthreads();
+    long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) a[i] = fma(a[i], m, c);
+    }
+    long long t1 = clock64();
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += a[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    if (threadIdx.x == 0 && blockIdx.x == 0) clk[6] = t1 - t0;
+}
+// dependent chain: latency of one DFMA
+__global__ void dp_lat_kernel(double* out, long long* clk, int iters) {
+    double a = threadIdx.x * 1e-3;
+    const double m = 1.0000001, c = 1e-9;
+    long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) a = fma(a, m, c);
+    }
+    long long t1 = clock64();
+    out[threadIdx.x] = a;
+    if (threadIdx.x == 0) clk[7] = t1 - t0;
+}
+
 static void host_chol(std::vector<double>& a, int n, int ld) {
     for (int k = 0; k < n; ++k) {
         double d = std::sqrt(a[(size_t)k * ld + k]);
@@ -322,6 +603,8 @@ int main(int argc, char** argv) {
     run("v0_no_rsqrt(timing only)", [&] { v0_kernel<2><<<1, 256>>>(dF, ld, n, dinfo, dclk); }, false);
     run("v0_fast_rsqrt", [&] { v0_kernel<3><<<1, 256>>>(dF, ld, n, dinfo, dclk); }, true);
     run("v0_instrumented", [&] { v0_kernel<1><<<1, 256>>>(dF, ld, n, dinfo, dclk); }, true);
+    run("v2_no_dead_work", [&] { v2_kernel<<<1, 256>>>(dF, ld, n, dinfo, dclk); }, true);
+    run("v3_unrolled_no_branches", [&] { v3_kernel<<<1, 256>>>(dF, ld, n, dinfo, dclk); }, true);
     run("v1_one_warp", [&] { v1_kernel<0><<<1, 32>>>(dF, ld, n, dinfo, dclk); }, true);
     run("v1_one_warp_fast_rsqrt", [&] { v1_kernel<1><<<1, 32>>>(dF, ld, n, dinfo, dclk); }, true);
     run("v1_one_warp_rsqrt3", [&] { v1_kernel<2><<<1, 32>>>(dF, ld, n, dinfo, dclk); }, true);
@@ -334,7 +617,40 @@ int main(int argc, char** argv) {
         CK(cudaMemcpy(hm, dm, sizeof hm, cudaMemcpyDeviceToHost));
         printf("{\"rsqrt_max_rel_err\": {\"seed\": %.3e, \"two_newton\": %.3e, \"third_order\": %.3e}}\n", hm[0], hm[1], hm[2]);
     }
+    // the same production kernel with 148 CTAs (every CTA factors the same block into its own copy? no: all write
+    // the same values to the same block -- benign for timing): does a full-chip grid change the per-launch time?
+    run("v0_production_grid148(timing only)", [&] { v0_kernel<0><<<148, 256>>>(dF, ld, n, dinfo, dclk); }, false);
+    for (int who : {0, 37, 255}) {
+        unsigned* dacc;
+        CK(cudaMalloc(&dacc, 10 * sizeof(unsigned)));
+        CK(cudaMemcpy(dF, dK, sizeof(double) * NB * ld, cudaMemcpyDeviceToDevice));
+        v2i_kernel<<<1, 256>>>(dF, ld, n, who, dacc);
+        CK(cudaDeviceSynchronize());
+        unsigned h[10];
+        CK(cudaMemcpy(h, dacc, sizeof h, cudaMemcpyDeviceToHost));
+        printf("{\"v2_fine_cycles_per_column\": {\"thread\": %d, \"loop\": %.1f, \"owner_store\": %.1f, \"barrier\": %.1f, \"pivot_lds\": %.1f, "
+               "\"column_lds\": %.1f, \"rsqrt\": %.1f, \"scale\": %.1f, \"update\": %.1f, \"owner_writeback\": %.1f, \"clock_pair_overhead\": %.1f}}\n",
+               who, h[0] / (double)n, h[1] / (double)n, h[2] / (double)n, h[3] / (double)n, h[4] / (double)n, h[5] / (double)n,
+               h[6] / (double)n, h[7] / (double)n, h[8] / (double)n, h[9] / 64.0);
+    }
     long long clk[8];
+    {
+        double* dout;
+        CK(cudaMalloc(&dout, sizeof(double) * 148 * 1024));
+        for (int warps : {1, 2, 4, 8, 16}) {
+            for (int grid : {1, 148}) {
+                dp_rate_kernel<<<grid, warps * 32>>>(dout, dclk, 1000);
+                CK(cudaDeviceSynchronize());
+                CK(cudaMemcpy(clk, dclk, sizeof clk, cudaMemcpyDeviceToHost));
+                printf("{\"dp_rate\": {\"grid\": %d, \"warps\": %d, \"cycles_per_warp_dfma\": %.3f, \"fma_per_clk_per_sm\": %.1f}}\n", grid, warps,
+                       clk[6] / (1000.0 * 16), warps * 32 * 16 * 1000.0 / clk[6]);
+            }
+        }
+        dp_lat_kernel<<<1, 32>>>(dout, dclk, 1000);
+        CK(cudaDeviceSynchronize());
+        CK(cudaMemcpy(clk, dclk, sizeof clk, cudaMemcpyDeviceToHost));
+        printf("{\"dfma_dependent_latency_cycles\": %.2f}\n", clk[7] / (1000.0 * 16));
+    }
     CK(cudaMemcpy(clk, dclk, sizeof clk, cudaMemcpyDeviceToHost));
     printf("{\"v0_cycles_per_column\": {\"store+barrier\": %.1f, \"pivot_lds\": %.1f, \"rsqrt\": %.1f, \"scale+update\": %.1f, "
            "\"loop_total\": %.1f}, \"v1_loop_cycles_per_column\": %.1f}\n",
