@@ -389,9 +389,13 @@ def run_ours(args):
     if rank == 0:
         g_l, g_ms, g_work = prof['gemm']
         achieved = g_work/(g_ms*1e-3)/1e12 if g_ms > 0 else 0.0
-        traffic = None
+        # roofline.traffic: DRAM bytes of ONE launch of the dominant kernel from the committed ncu --set full
+        # capture (an 8192^3 launch; the launches of a step have many shapes, so the capture's own algorithmic
+        # bytes are given beside it in traffic_detail)
+        traffic, traffic_detail = None, None
         try:
-            traffic = json.load(open(os.path.join(ROOT, 'profiles', 'gemm_traffic.json')))
+            traffic_detail = json.load(open(os.path.join(ROOT, 'profiles', 'gemm_traffic.json')))
+            traffic = traffic_detail['dram_bytes_per_launch']
         except Exception:
             pass
         line = {
@@ -407,7 +411,7 @@ def run_ours(args):
             'wall_s': wall, 'device_s': dev_s,
             'roofline': {'bound': 'tensor', 'kernel': 'gemm_nt_kernel (FP64 DMMA)', 'achieved': achieved,
                          'peak': fp64_peak, 'unit': 'TFLOP/s', 'frac': achieved/fp64_peak if fp64_peak else None,
-                         'traffic': traffic, 'launches': g_l, 'avg_launch_ms': g_ms/max(g_l, 1),
+                         'traffic': traffic, 'traffic_detail': traffic_detail, 'launches': g_l, 'avg_launch_ms': g_ms/max(g_l, 1),
                          'share_of_step': g_ms*1e-3/dev_s,
                          'peak_source': 'cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 '
                                         'entry; nominal 37 TFLOP/s); HBM %s' % hbm_src},
