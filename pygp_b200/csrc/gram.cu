@@ -30,19 +30,21 @@ struct Tile {
     __device__ int col(int b) const { return 2 * tx + 32 * (b >> 1) + (b & 1); }
 };
 
-// stage `rows` x ndim doubles of every leaf's scaled inputs, transposed
+// stage `rows` x ndim doubles of every leaf's scaled inputs, transposed to [k][row].
+// Lanes run along the ROW index: the shared stores are conflict-free and the index split is a shift (the
+// earlier k-fastest mapping cost two runtime integer divisions per element and 16-way conflicted stores --
+// 11-way on average over all shared stores of the kernel in ncu).  The global reads are then strided by
+// ndim doubles, but the 32-byte sectors they touch are reused by the next k through L1.
 __device__ __forceinline__ void stage_tile(double* dst, const double* Z, int64_t zstride, int64_t n,
                                            int64_t r0, int ndim, int n_parts) {
-    const int per_part = kTile * ndim;
-    for (int idx = threadIdx.x; idx < n_parts * per_part; idx += kThreads) {
-        int p = idx / per_part;
-        int rem = idx - p * per_part;
-        int r = rem / ndim;
-        int k = rem - r * ndim;
-        int64_t gr = r0 + r;
-        double v = 0.0;
-        if (gr < n) v = Z[p * zstride + gr * ndim + k];
-        dst[(p * ndim + k) * kTile + r] = v;
+    for (int p = 0; p < n_parts; ++p) {
+        const double* Zp = Z + p * zstride;
+        double* dp = dst + p * ndim * kTile;
+        for (int idx = threadIdx.x; idx < ndim * kTile; idx += kThreads) {
+            const int k = idx / kTile, r = idx % kTile;      // kTile = 64: shifts
+            const int64_t gr = r0 + r;
+            dp[idx] = gr < n ? Zp[gr * ndim + k] : 0.0;
+        }
     }
 }
 
