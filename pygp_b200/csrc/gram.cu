@@ -200,8 +200,10 @@ int launch_scale(pgp_ctx* ctx, const DevSpec* d_spec, const double* d_X, int64_t
 //   PTYPE >= 0: single leaf of that type (register micro-tile fast path)
 //   PTYPE <  0: composite, one entry at a time through the tree
 // ---------------------------------------------------------------------------
+// Matern values: capped at 64 registers (4 CTAs / SM; a few spilled bytes): the kernel is latency-bound, and the
+// fourth resident CTA is worth +6 % (2.33 -> 2.48 TB/s at d = 16); SE is 2 % faster without the cap.
 template <int PTYPE, int MODE>
-__global__ void __launch_bounds__(kThreads) gram_kernel(GramArgs a) {
+__global__ void __launch_bounds__(kThreads, (MODE == 0 && PTYPE >= PGP_MATERN1 && PTYPE <= PGP_MATERN5) ? 4 : 0) gram_kernel(GramArgs a) {
     constexpr bool GRAD1 = MODE == 1;
     constexpr bool GRADX = MODE == 2;
     constexpr bool GRADXY = MODE == 3;      // composite path only (PTYPE < 0)
