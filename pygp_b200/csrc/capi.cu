@@ -569,10 +569,12 @@ extern "C" int pgp_exact_append_inc(pgp_model* m, const double* X, const double*
     const int64_t n_old = m->n, n = n_old + n_new, ld_old = m->ld;
     cudaStream_t s = ctx->stream;
     // The factor buffer has row capacity m->cap (ld = lead_dim(cap)): appends that fit are done IN PLACE
-    // (no reallocation, no copy of the n^2 / 2 factor); otherwise it grows by n / 8 + 256 rows of slack, so a
+    // (no reallocation, no copy of the n^2 / 2 factor); otherwise it grows with n / 8 + 256 rows of slack (capped at ~1 GiB), so a
     // loop that adds one datum at a time (Bayesian optimisation, SMC) reallocates once in hundreds of steps.
     const bool inplace = n <= m->cap;
-    const int64_t cap = inplace ? m->cap : round_up(n + n / 8 + 256, 256);
+    // slack: n / 8 + 256 rows, but at most ~1 GiB of extra factor rows (large n: 2^27 / n rows), at least 256
+    const int64_t slack = std::min<int64_t>(n / 8 + 256, std::max<int64_t>(256, ((int64_t)1 << 27) / n));
+    const int64_t cap = inplace ? m->cap : round_up(n + slack, 256);
     const int64_t ld = inplace ? ld_old : lead_dim(cap);
     double* nF = m->d_F;
     PoolBuf T;                                   // (n_new + 1, ldt) scratch block
