@@ -4,7 +4,7 @@
 // other and checks them against a naive kernel.  Written at the end of round 1 from the ncu
 // capture of the production kernel (latency-bound at 25-37 % occupancy: every CTA runs
 // stage -> barrier -> distances -> epilogue -> store -> barrier -> mirror with nothing overlapped);
-// it had no GPU time left to run, so its first run is the first thing to do in round 2.
+// first run: profiles/r01g_gram_probe.txt (v0 2.63 TB/s, v1 2.38-2.45, v2 2.65-2.72 at d = 16, N = 32768).
 //
 //   v0  the production structure: one CTA per lower tile, inputs staged [k][row] by plain loads
 //   v1  persistent CTAs walking the lower tiles row by row; the inputs come from a
