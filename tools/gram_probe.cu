@@ -13,6 +13,8 @@
 //       previous tile computes; the row operand is reused along a tile row
 //   v2  v1 with the epilogue's exp as one polynomial per entry on constants held in constant
 //       memory (no library call; see profiles/r01f_gram_batched_epilogue_experiment.txt)
+//   v3  v2 with 8 x 4 register tiles (128 threads per tile): 8 + 2 shared loads per 64 FP64
+//       operations instead of 4 + 2 per 32 -- NOT YET RUN (added after the GPU budget of round 1 ended)
 //
 //   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -o bin/gram_probe gram_probe.cu
 //   bin/gram_probe [N=32768] [d=16]
@@ -63,11 +65,13 @@ __device__ __forceinline__ void tri_decode(int64_t idx, int* ti, int* tj) {
     *tj = (int)(idx - (int64_t)i * (i + 1) / 2);
 }
 
-// the 4 x 4 micro-tile of a thread: rows ty + 16 a, columns 2 tx + 32 (b >> 1) + (b & 1)
+// the RA x 4 micro-tile of a thread (RA = 4: 256 threads, RA = 8: 128 threads per tile):
+// rows ty + (64 / RA) a, columns 2 tx + 32 (b >> 1) + (b & 1)
+template <int RA>
 struct Map {
     int tx, ty;
     __device__ Map() : tx(threadIdx.x & 15), ty(threadIdx.x >> 4) {}
-    __device__ int row(int a) const { return ty + 16 * a; }
+    __device__ int row(int a) const { return ty + (T / RA) * a; }
     __device__ int col(int b) const { return 2 * tx + 32 * (b >> 1) + (b & 1); }
 };
 
@@ -103,38 +107,38 @@ __device__ __forceinline__ double value<true>(double D, double two_logsf) {
 }
 
 // distances + epilogue + stores of one tile from staged inputs Zs1 / Zs2 ([k][T] each); Tm = mirror scratch
-template <bool POLY>
+template <bool POLY, int RA = 4>
 __device__ __forceinline__ void tile_compute(const double* Zs1, const double* Zs2, double* Tm, int d, double two_logsf,
                                              double* out, int64_t ld, int64_t n, int ti, int tj) {
-    Map t;
-    double D[4][4];
+    Map<RA> t;
+    double D[RA][4];
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int a = 0; a < RA; ++a)
 #pragma unroll
         for (int b = 0; b < 4; ++b) D[a][b] = 0.0;
     for (int k = 0; k < d; ++k) {
-        double zi[4], zj[4];
+        double zi[RA], zj[4];
 #pragma unroll
-        for (int a = 0; a < 4; ++a) zi[a] = Zs1[k * T + t.row(a)];
+        for (int a = 0; a < RA; ++a) zi[a] = Zs1[k * T + t.row(a)];
         const double2 q0 = *reinterpret_cast<const double2*>(&Zs2[k * T + 2 * t.tx]);
         const double2 q1 = *reinterpret_cast<const double2*>(&Zs2[k * T + 2 * t.tx + 32]);
         zj[0] = q0.x; zj[1] = q0.y; zj[2] = q1.x; zj[3] = q1.y;
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
+        for (int a = 0; a < RA; ++a)
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
                 const double df = zi[a] - zj[b];
                 D[a][b] += df * df;
             }
     }
-    double res[4][4];
+    double res[RA][4];
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int a = 0; a < RA; ++a)
 #pragma unroll
         for (int b = 0; b < 4; ++b) res[a][b] = value<POLY>(D[a][b], two_logsf);
     const int64_t i0 = (int64_t)ti * T, j0 = (int64_t)tj * T;
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
+    for (int a = 0; a < RA; ++a) {
         const int64_t gi = i0 + t.row(a);
         if (gi >= n) continue;
 #pragma unroll
@@ -148,12 +152,12 @@ __device__ __forceinline__ void tile_compute(const double* Zs1, const double* Zs
     if (ti != tj) {   // mirrored tile through a shared transpose
         constexpr int TP = T + 1;
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
+        for (int a = 0; a < RA; ++a)
 #pragma unroll
             for (int b = 0; b < 4; ++b) Tm[t.row(a) * TP + t.col(b)] = res[a][b];
         __syncthreads();
 #pragma unroll
-        for (int a = 0; a < 4; ++a) {
+        for (int a = 0; a < RA; ++a) {
             const int64_t gi = j0 + t.row(a);
             if (gi >= n) continue;
 #pragma unroll
@@ -196,14 +200,14 @@ __device__ __forceinline__ void cp16(double* sdst, const double* gsrc, int bytes
 
 // stage rows [r0, r0 + T) of every dimension of Zt ([d][npad], npad a multiple of T and of 2) into dst [k][T]
 __device__ __forceinline__ void stage_async(double* dst, const double* Zt, int64_t npad, int64_t r0, int d) {
-    for (int idx = threadIdx.x; idx < d * (T / 2); idx += THREADS) {
+    for (int idx = threadIdx.x; idx < d * (T / 2); idx += blockDim.x) {
         const int k = idx / (T / 2), c = (idx % (T / 2)) * 2;
         cp16(dst + k * T + c, Zt + (int64_t)k * npad + r0 + c, 16);
     }
 }
 
-template <bool POLY>
-__global__ void __launch_bounds__(THREADS) v1_kernel(const double* Zt, int64_t n, int64_t npad, int d, double two_logsf,
+template <bool POLY, int RA = 4>
+__global__ void __launch_bounds__(16 * (T / RA)) v1_kernel(const double* Zt, int64_t n, int64_t npad, int d, double two_logsf,
                                                      double* out, int64_t ld, int64_t ntiles) {
     extern __shared__ __align__(16) double sm[];
     // [2] x (Zs1, Zs2) + mirror scratch
@@ -228,7 +232,7 @@ __global__ void __launch_bounds__(THREADS) v1_kernel(const double* Zt, int64_t n
         asm volatile("cp.async.commit_group;\n" ::);
         asm volatile("cp.async.wait_group 1;\n" ::);    // the current tile's inputs have landed
         __syncthreads();
-        tile_compute<POLY>(buf[cur], buf[cur] + d * T, Tm, d, two_logsf, out, ld, n, ti, tj);
+        tile_compute<POLY, RA>(buf[cur], buf[cur] + d * T, Tm, d, two_logsf, out, ld, n, ti, tj);
         __syncthreads();                                // everybody is done with buf[cur] and Tm
         if (next >= ntiles) break;
         tile = next; ti = ni; tj = nj;
@@ -304,6 +308,14 @@ int main(int argc, char** argv) {
         CK(cudaFuncSetAttribute(v1_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         snprintf(name, sizeof name, "v2_persistent_poly_exp_%d_per_sm", per_sm);
         run(name, [&] { v1_kernel<true><<<grid, THREADS, smem>>>(dZt, n, npad, d, two_logsf, dOut, ld, ntiles); });
+    }
+    for (int per_sm : {3, 4, 6}) {      // v3: 8 x 4 register tiles, 128 threads
+        const size_t smem = ((size_t)4 * d * T + T * (T + 1)) * 8;
+        const unsigned grid = (unsigned)std::min<int64_t>(ntiles, (int64_t)sms * per_sm);
+        char name[96];
+        CK(cudaFuncSetAttribute(v1_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        snprintf(name, sizeof name, "v3_persistent_poly_exp_8x4_%d_per_sm", per_sm);
+        run(name, [&] { v1_kernel<true, 8><<<grid, 128, smem>>>(dZt, n, npad, d, two_logsf, dOut, ld, ntiles); });
     }
     return 0;
 }
