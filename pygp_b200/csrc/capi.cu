@@ -587,6 +587,13 @@ extern "C" int pgp_exact_append_inc(pgp_model* m, const double* X, const double*
         cudaStreamSynchronize(s);
         if (!inplace && nF != m->d_F) dev_free(ctx, nF);
         m->factored = false;
+        // the gradient / predict scratch is sized by (n, ld): once m->n may have changed it must not be
+        // reused by the documented fallback (pgp_exact_update, then loglike(grad) / predict)
+        dev_free(ctx, m->d_G); m->d_G = nullptr;
+        dev_free(ctx, m->d_H); m->d_H = nullptr;
+        dev_free(ctx, m->d_partials); m->d_partials = nullptr;
+        dev_free(ctx, m->d_Bc); m->d_Bc = nullptr;
+        m->bc_rows = 0;
         if (m->n > m->cap) {                     // X, y already grown but F was not: refit the work buffers
             const int64_t nn = m->n;
             m->n = n_old;

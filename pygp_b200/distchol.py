@@ -42,7 +42,7 @@ def block_columns(n, nb):
     return [(j0, min(nb, n - j0)) for j0 in range(0, n, nb)]
 
 
-def distributed_factor(be, n, nb, rank, size, bcast, group=1):
+def distributed_factor(be, n, nb, rank, size, bcast, group=1, allreduce_min=None):
     """Run the schedule.  `be` provides the arithmetic on this rank's buffers:
 
         be.build_panel(j0, w)          -> panel ((n - j0) + 1, w): K[j0:, j0:j0+w] + noise, last row r[j0:j0+w]
@@ -63,7 +63,11 @@ def distributed_factor(be, n, nb, rank, size, bcast, group=1):
     N = 65536, nb = 512 this is SLOWER (0.58 s for 2, 0.60 s for 4, against 0.51 s
     for 1): the per-rank GEMM work is already hidden behind the panel chain
     (factor + broadcast), and deferring it only makes it arrive in bursts.
-    Returns info (> 0: order of the first non positive-definite leading minor)."""
+    `allreduce_min(int) -> int` makes the potrf `info` GLOBAL: it is only known on the
+    rank that owns the failing panel (receivers see a NaN-filled panel, not an info), and
+    ranks that disagree about success diverge in the caller's error handling and deadlock
+    in the next collective.  Returns info (> 0: order of the first non positive-definite
+    leading minor), the same value on every rank."""
     cols = block_columns(n, nb)
     nblk = len(cols)
     mine = {j: be.build_panel(*cols[j]) for j in range(nblk) if j % size == rank}
@@ -109,6 +113,10 @@ def distributed_factor(be, n, nb, rank, size, bcast, group=1):
         if nxt is not None:
             cur, handle = nxt[0], nxt[1]
     be.sync()
+    if allreduce_min is not None and size > 1:
+        big = 1 << 62
+        info = allreduce_min(info if info else big)
+        info = 0 if info == big else info
     return info
 
 
@@ -215,8 +223,13 @@ def distributed_update(gp, nb=512, group=None, panels_per_update=1):
             src_global = dist.get_global_rank(group, src) if group is not None else src
             return _Handle(dist.broadcast(buf, src=src_global, group=group, async_op=True))
 
+    def allreduce_min(v):
+        t = torch.tensor([v], dtype=torch.int64, device=be.dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+        return int(t.item())
+
     with torch.cuda.stream(be.stream):
-        info = distributed_factor(be, gp.ndata, nb, rank, size, bcast, panels_per_update)
+        info = distributed_factor(be, gp.ndata, nb, rank, size, bcast, panels_per_update, allreduce_min)
     if info:
         raise np.linalg.LinAlgError('%d-th leading minor of the array is not positive definite' % info)
     _lib.check(be.ctx, _lib.lib().pgp_exact_adopt_factor(gp._dev.handle, _lib.ptr(hyp)))

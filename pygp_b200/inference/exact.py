@@ -113,7 +113,15 @@ class ExactGP(GP):
             raise
         self._ndev += len(Xn)
 
+    def _ensure_dev(self):
+        """Rebuild the device state from the host data if it was dropped (a failed
+        incremental update): the reference keeps working from its old factor, here the
+        model is refactored on next use."""
+        if self._dev is None and self.ndata > 0:
+            self._update()
+
     def _factor(self):
+        self._ensure_dev()
         n = self.ndata
         R, a = np.empty((n, n)), np.empty(n)
         _lib.check(self._dev.ctx, _lib.lib().pgp_exact_get_factor(self._dev.handle, _lib.ptr(R), _lib.ptr(a)))
@@ -130,6 +138,7 @@ class ExactGP(GP):
 
     # -- GP interface ------------------------------------------------------------
     def loglikelihood(self, grad=False):
+        self._ensure_dev()
         lZ = C.c_double()
         dlZ = np.empty(self.nhyper) if grad else None
         _lib.check(self._dev.ctx, _lib.lib().pgp_exact_loglike(
@@ -141,6 +150,7 @@ class ExactGP(GP):
         X = _lib.as_f64(X, 2)
         if self._X is None:
             return np.full(X.shape[0], self._mean), self._kernel.get(X)
+        self._ensure_dev()
         mu, Sigma = np.empty(len(X)), np.empty((len(X), len(X)))
         _lib.check(self._dev.ctx, _lib.lib().pgp_exact_full_posterior(
             self._dev.handle, _lib.ptr(X), len(X), _lib.ptr(mu), _lib.ptr(Sigma)))
@@ -154,6 +164,7 @@ class ExactGP(GP):
             return out + (np.zeros_like(X), np.zeros_like(X)) if grad else out
         if X.shape[1] != self._kernel.ndim:
             raise ValueError('test inputs have the wrong number of columns')
+        self._ensure_dev()
         mu, s2 = np.empty(len(X)), np.empty(len(X))
         if not grad:
             _lib.check(self._dev.ctx, _lib.lib().pgp_exact_predict(

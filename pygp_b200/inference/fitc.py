@@ -20,7 +20,8 @@ __all__ = ['FITC']
 
 class _DeviceFITC(object):
     """Owner of a `pgp_fitc*`.  A deep copy (Parameterized.copy) starts without
-    device state; the copy's next `_update` uploads its own."""
+    device state; the copy rebuilds its own lazily (`FITC._ensure_dev`) the first
+    time it is evaluated, so `gp.copy().posterior(X)` works as in the reference."""
 
     def __init__(self, ctx, handle):
         self.ctx, self.handle = ctx, handle
@@ -96,7 +97,14 @@ class FITC(GP):
         hyp = _lib.as_f64(self.get_hyper())
         _lib.check(self._dev.ctx, _lib.lib().pgp_fitc_update(self._dev.handle, _lib.ptr(hyp)))
 
+    def _ensure_dev(self):
+        """Device state of a copy made without a hyper argument (utils/models.py:47-55):
+        rebuilt on first use from the host data the copy carries."""
+        if self._dev is None and self.ndata > 0:
+            self._update()
+
     def loglikelihood(self, grad=False):
+        self._ensure_dev()
         lZ = C.c_double()
         dlZ = np.empty(self.nhyper) if grad else None
         _lib.check(self._dev.ctx, _lib.lib().pgp_fitc_loglike(
@@ -108,6 +116,7 @@ class FITC(GP):
         X = _lib.as_f64(X, 2)
         if self._X is None:
             return np.full(X.shape[0], self._mean), self._kernel.get(X)
+        self._ensure_dev()
         mu, Sigma = np.empty(len(X)), np.empty((len(X), len(X)))
         _lib.check(self._dev.ctx, _lib.lib().pgp_fitc_full_posterior(
             self._dev.handle, _lib.ptr(X), len(X), _lib.ptr(mu), _lib.ptr(Sigma)))
@@ -120,6 +129,7 @@ class FITC(GP):
             return out + (np.zeros_like(X), np.zeros_like(X)) if grad else out
         if X.shape[1] != self._kernel.ndim:
             raise ValueError('test inputs have the wrong number of columns')
+        self._ensure_dev()
         mu, s2 = np.empty(len(X)), np.empty(len(X))
         if not grad:
             _lib.check(self._dev.ctx, _lib.lib().pgp_fitc_predict(

@@ -21,6 +21,13 @@ __all__ = ['MCMC']
 
 
 class MCMC(object):
+    # Opt-in multi-GPU mixture: set `sharded = True` (or a process group)
+    # in a one-process-per-GPU job where EVERY rank holds the same chain (same data, same
+    # rng seed) and calls `posterior` in lockstep; the n sampled models are then split
+    # across the ranks.  Never inferred from the world size: a call on a subset of ranks,
+    # or chains that differ per rank (rng=None), would hang or mix different posteriors.
+    sharded = False
+
     def __init__(self, model, prior, n=100, burn=100, rng=None):
         self._model = model.copy()
         self._prior = prior
@@ -96,11 +103,12 @@ class MCMC(object):
             return mu, s2, dmu, ds2
         from .. import sharding
         model = self._model
-        if (sharding.world()[1] > 1 and isinstance(model, ExactGP) and model.ndata > 0
+        group = None if self.sharded is True else self.sharded
+        if (self.sharded and sharding.world(group)[1] > 1 and isinstance(model, ExactGP) and model.ndata > 0
                 and len(self._hypers) > 0):
             # one process per GPU, identical chains (same rng) on every rank: the
             # n sampled models are split across the ranks
-            return sharding.sharded_mixture_posterior(model, self._hypers, model._kernel.transform(X))
+            return sharding.sharded_mixture_posterior(model, self._hypers, model._kernel.transform(X), group)
         mu_, s2_ = self._component_posteriors(X)
         mu = np.mean(mu_, axis=0)
         s2 = np.mean(s2_ + (mu_ - mu)**2, axis=0)

@@ -22,7 +22,7 @@ NCCL, host for gloo -- which is how tests/test_sharding.py runs on CPU).
 
 import numpy as np
 
-__all__ = ['shard_range', 'world', 'all_gather_rows', 'all_reduce_sum', 'sharded_posterior',
+__all__ = ['shard_range', 'world', 'all_gather_rows', 'all_reduce_sum', 'sharded_posterior', '_raise_together',
            'sharded_batched_loglike', 'sharded_mixture_posterior']
 
 
@@ -49,7 +49,12 @@ def _device_for(group):
     import torch
     import torch.distributed as dist
     backend = dist.get_backend(group)
-    return torch.device('cuda', torch.cuda.current_device()) if 'nccl' in str(backend) else torch.device('cpu')
+    if 'nccl' not in str(backend):
+        return torch.device('cpu')
+    # the device the library context computes on (LOCAL_RANK / PYGP_B200_DEVICE), not torch's current
+    # device: collectives and compute must share one GPU even if the caller never called set_device
+    from . import _lib
+    return torch.device('cuda', _lib.context().device)
 
 
 def all_gather_rows(local, total, group=None):
@@ -86,6 +91,27 @@ def all_reduce_sum(x, group=None):
     return t.cpu().numpy()
 
 
+def _raise_together(err, group=None):
+    """Make a rank-local failure global: all-reduce an error flag (MAX) and raise the
+    same exception class on every rank, so that nobody is left waiting in the next
+    collective.  `err` is None or the exception caught on this rank."""
+    rank, size = world(group)
+    code = 0 if err is None else (1 if isinstance(err, np.linalg.LinAlgError) else 2)
+    if size > 1:
+        import torch
+        import torch.distributed as dist
+        t = torch.tensor([float(code)], dtype=torch.float64, device=_device_for(group))
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+        code = int(t.item())
+    if code == 0:
+        return
+    if err is not None:
+        raise err
+    if code == 1:
+        raise np.linalg.LinAlgError('another rank: kernel matrix not positive definite')
+    raise RuntimeError('another rank failed in a sharded evaluation')
+
+
 def sharded_posterior(gp, X, group=None):
     """`gp.posterior(X)` (exact.py:81-97 / fitc.py:122-142) with the rows of X
     split across the ranks; every rank holds an identical model (same data,
@@ -93,10 +119,13 @@ def sharded_posterior(gp, X, group=None):
     rank, size = world(group)
     X = np.array(X, ndmin=2, dtype=float)
     lo, hi = shard_range(len(X), rank, size)
-    if hi > lo:
-        mu, s2 = gp.posterior(X[lo:hi])
-    else:
-        mu, s2 = np.empty(0), np.empty(0)
+    err, mu, s2 = None, np.empty(0), np.empty(0)
+    try:
+        if hi > lo:
+            mu, s2 = gp.posterior(X[lo:hi])
+    except Exception as e:                # noqa: BLE001 -- re-raised on every rank below
+        err = e
+    _raise_together(err, group)
     out = all_gather_rows(np.stack([mu, s2], 1), len(X), group)
     return out[:, 0].copy(), out[:, 1].copy()
 
@@ -135,7 +164,13 @@ def sharded_batched_loglike(gp, hypers, group=None, local_fn=None):
     hypers = np.array(hypers, ndmin=2, dtype=float)
     lo, hi = shard_range(len(hypers), rank, size)
     fn = local_fn or (lambda h: _batched('loglike', gp, h, None))
-    mine = fn(hypers[lo:hi]) if hi > lo else np.empty(0)
+    err, mine = None, np.empty(0)
+    try:
+        if hi > lo:
+            mine = fn(hypers[lo:hi])
+    except Exception as e:                # noqa: BLE001
+        err = e
+    _raise_together(err, group)
     return all_gather_rows(np.asarray(mine, dtype=float), len(hypers), group)
 
 
@@ -149,10 +184,13 @@ def sharded_mixture_posterior(gp, hypers, X, group=None, local_fn=None):
     B, m = len(hypers), len(X)
     lo, hi = shard_range(B, rank, size)
     fn = local_fn or (lambda h, x: _batched('predict', gp, h, x))
-    if hi > lo:
-        mu_, s2_ = fn(hypers[lo:hi], X)
-    else:
-        mu_, s2_ = np.empty((0, m)), np.empty((0, m))
+    err, mu_, s2_ = None, np.empty((0, m)), np.empty((0, m))
+    try:
+        if hi > lo:
+            mu_, s2_ = fn(hypers[lo:hi], X)
+    except Exception as e:                # noqa: BLE001 -- e.g. LinAlgError on the one rank whose slice is non-PD
+        err = e
+    _raise_together(err, group)           # before the all-reduces: every rank raises, nobody deadlocks
     mu = all_reduce_sum(np.sum(mu_, axis=0), group)/B
     s2 = all_reduce_sum(np.sum(s2_ + (mu_ - mu)**2, axis=0), group)/B
     return mu, s2

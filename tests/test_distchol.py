@@ -120,6 +120,23 @@ def _worker(rank, size, port, q):
             # every rank ends with the complete factor (the broadcasts are the all-gather)
             nt.assert_allclose(be.F[:n][low], L[low], rtol=1e-11, atol=1e-12)
             nt.assert_allclose(be.F[n], sla.solve_triangular(L, r, lower=True), rtol=1e-10, atol=1e-12)
+
+        # not positive definite: `info` is found by the owner of the failing panel only; with the
+        # MIN all-reduce every rank reports the same first failing minor (distchol.py:90)
+        def allreduce_min(v):
+            t = torch.tensor([v], dtype=torch.int64)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            return int(t.item())
+        K, r = _problem(300, seed=5)
+        K[150, 150] = -1.0                      # block column 2 (nb = 64) -> owned by rank 0 of 2
+        with np.errstate(all='ignore'):
+            info = distributed_factor(NumpyBackend(K, r, 64), 300, 64, rank, size, bcast, 1, allreduce_min)
+        assert 128 < info <= 192, info
+        K[150, 150] = K[149, 149]
+        K[100, 100] = -1.0                      # block column 1 -> owned by rank 1
+        with np.errstate(all='ignore'):
+            info = distributed_factor(NumpyBackend(K, r, 64), 300, 64, rank, size, bcast, 1, allreduce_min)
+        assert 64 < info <= 128, info
         q.put((rank, 'ok'))
     except Exception:      # pragma: no cover
         import traceback

@@ -89,3 +89,11 @@ def test_reference_interface():
     f = pygp.inference.FITC.from_gp(gp)             # a different approximation: a different likelihood
     assert abs(f.loglikelihood() - gp.loglikelihood()) > 1e-6
     assert gp.sample(Xs, 2, rng=0).shape == (2, len(Xs))
+
+
+def test_copy_without_hyper_is_usable():
+    """`DTC.copy()` (utils/models.py:47-55) gives a model whose posterior / likelihood work at once."""
+    gp, Xs = build(sorted(DTC_CASES)[0])
+    g2 = gp.copy()
+    nt.assert_allclose(g2.posterior(Xs)[0], gp.posterior(Xs)[0], rtol=1e-12)
+    nt.assert_allclose(g2.loglikelihood(), gp.loglikelihood(), rtol=1e-12)

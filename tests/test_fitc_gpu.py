@@ -117,6 +117,13 @@ def test_reference_interface():
     g4.add_data(X, y)
     nt.assert_allclose(g3.loglikelihood(), g4.loglikelihood(), rtol=1e-12)
     nt.assert_allclose(gp.get_hyper(), mk().get_hyper())          # original untouched
+    # copy() WITHOUT a hyper argument is fully usable (utils/models.py:47-55): the copy has the
+    # data but rebuilds its own device state on first use
+    g7 = gp.copy()
+    nt.assert_allclose(g7.posterior(Xs)[0], gp.posterior(Xs)[0], rtol=1e-12)
+    nt.assert_allclose(g7.posterior(Xs)[1], gp.posterior(Xs)[1], rtol=1e-12)
+    nt.assert_allclose(gp.copy().loglikelihood(True)[1], gp.loglikelihood(True)[1], rtol=1e-12)
+    assert gp.copy().sample(Xs[:3], rng=0).shape == (3,)
     # from_gp (fitc.py:53-64)
     g5 = pygp.inference.FITC.from_gp(gp)
     nt.assert_allclose(g5.loglikelihood(), gp.loglikelihood(), rtol=1e-12)

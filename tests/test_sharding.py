@@ -89,6 +89,21 @@ def _worker(rank, size, port, q):
         # a rank with no work (1 sample, 2 ranks) still takes part in the collectives
         got = sharding.sharded_batched_loglike(gp, H[:1], local_fn=lz)
         nt.assert_array_equal(got, lz(H[:1]))
+
+        # a failure on ONE rank (non-PD hyper slice) must surface on EVERY rank before the
+        # all-reduces, as the same exception class, instead of leaving the others waiting
+        def pred_bad(hs, x):
+            if rank == 1:
+                raise np.linalg.LinAlgError('not positive definite (rank 1 only)')
+            return pred(hs, x)
+        try:
+            sharding.sharded_mixture_posterior(gp, H, Xs, local_fn=pred_bad)
+            raise AssertionError('expected LinAlgError on every rank')
+        except np.linalg.LinAlgError:
+            pass
+        # ... and the group is still usable afterwards
+        got = sharding.sharded_batched_loglike(gp, H, local_fn=lz)
+        nt.assert_array_equal(got, lz(H))
         q.put((rank, 'ok'))
     except Exception as e:      # pragma: no cover
         import traceback
