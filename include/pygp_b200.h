@@ -244,6 +244,11 @@ int pgp_dev_copy2d(pgp_ctx* ctx, void* d_dst, int64_t dpitch, const void* d_src,
  * further rows below it that receive the same right-solves (row n = r -> a). */
 int pgp_dev_potrf(pgp_ctx* ctx, double* d_F, int64_t n, int64_t ld, int64_t extra);
 
+/* the short FP64 elementary functions of the covariance epilogues (csrc/fastmath.cuh),
+ * elementwise on host arrays, for their accuracy sweep against libm
+ * (tests/test_fastmath_gpu.py).  which: 0 exp, 1 sqrt, 2 exp clamped at -708. */
+int pgp_dev_fastmath(pgp_ctx* ctx, int which, const double* x, int64_t n, double* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -99,6 +99,7 @@ SIGNATURES = {
     'pgp_dev_trsm': (C.c_int, [_vp, _vp, _i64, _i64, _vp, _i64, _i64, C.c_int]),
     'pgp_dev_copy2d': (C.c_int, [_vp, _vp, _i64, _vp, _i64, _i64, _i64]),
     'pgp_dev_potrf': (C.c_int, [_vp, _vp, _i64, _i64, _i64]),
+    'pgp_dev_fastmath': (C.c_int, [_vp, C.c_int, _dp, _i64, _dp]),
 }
 
 _lib = None

@@ -207,11 +207,11 @@ int gram_device(pgp_ctx* ctx, const pgp_kernel_spec* spec, const double* hyp, co
     PGP_TRY(alloc<DevSpec>(ctx, dspec, 1));
     PGP_TRY(upload_spec(ctx, hs, dspec.as<DevSpec>()));
     const int d = spec->ndim, np = spec->n_parts;
-    PGP_TRY(alloc<double>(ctx, z1, (size_t)np * n1 * d));
+    PGP_TRY(alloc<double>(ctx, z1, z_doubles(np, d, n1)));
     PGP_TRY(launch_scale(ctx, dspec.as<DevSpec>(), d_X1, n1, d, np, z1.as<double>(), 1));
     const double* Z2 = z1.as<double>();
     if (d_X2) {
-        PGP_TRY(alloc<double>(ctx, z2, (size_t)np * n2 * d));
+        PGP_TRY(alloc<double>(ctx, z2, z_doubles(np, d, n2)));
         PGP_TRY(launch_scale(ctx, dspec.as<DevSpec>(), d_X2, n2, d, np, z2.as<double>(), 1));
         Z2 = z2.as<double>();
     }
@@ -306,13 +306,13 @@ extern "C" int pgp_gram_gradx(pgp_ctx* ctx, const pgp_kernel_spec* spec, const d
     PGP_TRY(upload_spec(ctx, hs, dspec.as<DevSpec>()));
     PGP_TRY(alloc<double>(ctx, x1, (size_t)n1 * d));
     PGP_CUDA(ctx, cudaMemcpyAsync(x1.p, X1, sizeof(double) * n1 * d, cudaMemcpyHostToDevice, ctx->stream));
-    PGP_TRY(alloc<double>(ctx, z1, (size_t)np * n1 * d));
+    PGP_TRY(alloc<double>(ctx, z1, z_doubles(np, d, n1)));
     PGP_TRY(launch_scale(ctx, dspec.as<DevSpec>(), x1.as<double>(), n1, d, np, z1.as<double>(), 1));
     const double* Z2 = z1.as<double>();
     if (X2) {
         PGP_TRY(alloc<double>(ctx, x2, (size_t)n2 * d));
         PGP_CUDA(ctx, cudaMemcpyAsync(x2.p, X2, sizeof(double) * n2 * d, cudaMemcpyHostToDevice, ctx->stream));
-        PGP_TRY(alloc<double>(ctx, z2, (size_t)np * n2 * d));
+        PGP_TRY(alloc<double>(ctx, z2, z_doubles(np, d, n2)));
         PGP_TRY(launch_scale(ctx, dspec.as<DevSpec>(), x2.as<double>(), n2, d, np, z2.as<double>(), 1));
         Z2 = z2.as<double>();
     }
@@ -359,13 +359,13 @@ extern "C" int pgp_gram_gradxy(pgp_ctx* ctx, const pgp_kernel_spec* spec, const 
     PGP_TRY(upload_spec(ctx, hs, dspec.as<DevSpec>()));
     PGP_TRY(alloc<double>(ctx, x1, (size_t)n1 * d));
     PGP_CUDA(ctx, cudaMemcpyAsync(x1.p, X1, sizeof(double) * n1 * d, cudaMemcpyHostToDevice, ctx->stream));
-    PGP_TRY(alloc<double>(ctx, z1, (size_t)np * n1 * d));
+    PGP_TRY(alloc<double>(ctx, z1, z_doubles(np, d, n1)));
     PGP_TRY(launch_scale(ctx, dspec.as<DevSpec>(), x1.as<double>(), n1, d, np, z1.as<double>(), 1));
     const double* Z2 = z1.as<double>();
     if (X2) {
         PGP_TRY(alloc<double>(ctx, x2, (size_t)n2 * d));
         PGP_CUDA(ctx, cudaMemcpyAsync(x2.p, X2, sizeof(double) * n2 * d, cudaMemcpyHostToDevice, ctx->stream));
-        PGP_TRY(alloc<double>(ctx, z2, (size_t)np * n2 * d));
+        PGP_TRY(alloc<double>(ctx, z2, z_doubles(np, d, n2)));
         PGP_TRY(launch_scale(ctx, dspec.as<DevSpec>(), x2.as<double>(), n2, d, np, z2.as<double>(), 1));
         Z2 = z2.as<double>();
     }
@@ -475,7 +475,7 @@ int model_alloc_work(pgp_model* m) {
     pgp_ctx* ctx = m->ctx;
     m->cap = m->n;                       // exact fit; pgp_exact_append_inc adds slack when it has to grow
     m->ld = lead_dim(m->cap);
-    PGP_TRY(pool_alloc(ctx, &m->d_Z, (size_t)m->spec.n_parts * m->xcap * m->ndim));
+    PGP_TRY(pool_alloc(ctx, &m->d_Z, z_doubles(m->spec.n_parts, m->ndim, m->xcap)));
     PGP_TRY(pool_alloc(ctx, &m->d_F, (size_t)(m->cap + 1) * m->ld));
     PGP_TRY(dev_alloc(ctx, &m->d_alpha, (size_t)m->xcap));
     return 0;
@@ -616,7 +616,7 @@ extern "C" int pgp_exact_append_inc(pgp_model* m, const double* X, const double*
     if ((rc = model_upload(m, X, y, n_old, n_new))) return bail(rc);           // X, y grow (m->n = n now)
     if (m->xcap != xcap_old) {                                                  // Z, alpha follow the row capacity
         double *nZ = nullptr, *nAlpha = nullptr;
-        rc = pool_alloc(ctx, &nZ, (size_t)np * m->xcap * d);
+        rc = pool_alloc(ctx, &nZ, z_doubles(np, d, m->xcap));
         if (!rc) rc = dev_alloc(ctx, &nAlpha, (size_t)m->xcap);
         if (rc) {
             dev_free(ctx, nZ);
@@ -634,8 +634,8 @@ extern "C" int pgp_exact_append_inc(pgp_model* m, const double* X, const double*
     const int st = single_type(&m->spec);
     GramArgs g;                                   // new rows: k(Xnew, Xold)
     g.spec = m->d_spec;
-    g.Z1 = nZ + n_old * d; g.zs1 = n * d; g.n1 = n_new;
-    g.Z2 = nZ; g.zs2 = n * d; g.n2 = n_old;
+    g.Z1 = nZ + n_old; g.zd1 = z_stride(n); g.n1 = n_new;      // row windows of the scaled array of all n rows
+    g.Z2 = nZ; g.zd2 = z_stride(n); g.n2 = n_old;
     g.ndim = d; g.n_parts = np;
     g.out = nF + n_old * ld; g.ldo = ld;
     g.single_type = st;
@@ -647,7 +647,7 @@ extern "C" int pgp_exact_append_inc(pgp_model* m, const double* X, const double*
     if ((rc = trsm_right_lt(ctx, Bn, n_new, F, n_old))) return bail(rc);      // S^T = k(Xnew, X) L^-T
     GramArgs gs;                                  // T = Kss + sn2 I (lower), row n_new = r_new
     gs.spec = m->d_spec;
-    gs.Z1 = gs.Z2 = nZ + n_old * d; gs.zs1 = gs.zs2 = n * d; gs.n1 = gs.n2 = n_new;
+    gs.Z1 = gs.Z2 = nZ + n_old; gs.zd1 = gs.zd2 = z_stride(n); gs.n1 = gs.n2 = n_new;
     gs.ndim = d; gs.n_parts = np;
     gs.out = T.p; gs.ldo = ldt;
     gs.lower_only = 1; gs.add_noise = 1;
@@ -757,7 +757,7 @@ extern "C" int pgp_model_clone(const pgp_model* src, pgp_model** out) {
     cudaError_t e = cudaMemcpyAsync(m->d_X, src->d_X, sizeof(double) * n * d, cudaMemcpyDeviceToDevice, s);
     if (e == cudaSuccess) e = cudaMemcpyAsync(m->d_y, src->d_y, sizeof(double) * n, cudaMemcpyDeviceToDevice, s);
     if (e == cudaSuccess && src->factored) {
-        e = cudaMemcpyAsync(m->d_Z, src->d_Z, sizeof(double) * src->spec.n_parts * n * d, cudaMemcpyDeviceToDevice, s);
+        e = cudaMemcpyAsync(m->d_Z, src->d_Z, sizeof(double) * z_doubles(src->spec.n_parts, d, n), cudaMemcpyDeviceToDevice, s);
         if (e == cudaSuccess)
             e = cudaMemcpy2DAsync(m->d_F, sizeof(double) * m->ld, src->d_F, sizeof(double) * src->ld, sizeof(double) * n,
                                   n + 1, cudaMemcpyDeviceToDevice, s);
@@ -924,7 +924,7 @@ int predict_chunked(pgp_model* m, const double* Xs, bool xs_on_device, int64_t m
     }
     DevBuf xs, zs, o;
     if (!xs_on_device) PGP_TRY(alloc<double>(ctx, xs, (size_t)chunk * d));
-    PGP_TRY(alloc<double>(ctx, zs, (size_t)np * chunk * d));
+    PGP_TRY(alloc<double>(ctx, zs, z_doubles(np, d, chunk)));
     if (!out_on_device) PGP_TRY(alloc<double>(ctx, o, (size_t)2 * chunk * rpp));
     Mat B, F;
     B.p = m->d_Bc; B.ld = ld;
@@ -1017,7 +1017,7 @@ extern "C" int pgp_exact_full_posterior(pgp_model* m, const double* Xs, int64_t 
     PGP_TRY(B.get(ctx, (size_t)ms * ld));
     PGP_TRY(S.get(ctx, (size_t)ms * lds));
     PGP_TRY(alloc<double>(ctx, xs, (size_t)ms * d));
-    PGP_TRY(alloc<double>(ctx, zs, (size_t)np * ms * d));
+    PGP_TRY(alloc<double>(ctx, zs, z_doubles(np, d, ms)));
     PGP_TRY(alloc<double>(ctx, o, (size_t)2 * ms));
     cudaStream_t st = ctx->stream;
     PGP_CUDA(ctx, cudaMemcpyAsync(xs.p, Xs, sizeof(double) * ms * d, cudaMemcpyHostToDevice, st));
@@ -1141,8 +1141,8 @@ static int batched_impl(pgp_ctx* ctx, const pgp_kernel_spec* spec, const double*
     const int64_t ld = lead_dim(n);
     const bool pred = Xs != nullptr && ms > 0;
     // per-problem device footprint -> chunk of the batch that fits a 24 GiB budget
-    size_t per = sizeof(double) * ((size_t)(n + 1) * ld + (size_t)np * n * d) + sizeof(DevSpec);
-    if (pred) per += sizeof(double) * ((size_t)ms * ld + (size_t)np * ms * d + 2 * ms);
+    size_t per = sizeof(double) * ((size_t)(n + 1) * ld + z_doubles(np, d, n)) + sizeof(DevSpec);
+    if (pred) per += sizeof(double) * ((size_t)ms * ld + z_doubles(np, d, ms) + 2 * ms);
     size_t free_b = 0, total_b = 0;
     PGP_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
     size_t budget = std::min<size_t>((size_t)24 << 30, free_b / 2);
@@ -1155,14 +1155,14 @@ static int batched_impl(pgp_ctx* ctx, const pgp_kernel_spec* spec, const double*
     PGP_CUDA(ctx, cudaMemcpyAsync(dX.p, X, sizeof(double) * n * d, cudaMemcpyHostToDevice, ctx->stream));
     PGP_CUDA(ctx, cudaMemcpyAsync(dy.p, y, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
     PGP_TRY(alloc<DevSpec>(ctx, dspec, chunk));
-    PGP_TRY(alloc<double>(ctx, dZ, (size_t)chunk * np * n * d));
+    PGP_TRY(alloc<double>(ctx, dZ, (size_t)chunk * z_doubles(np, d, n)));
     PGP_TRY(dF.get(ctx, (size_t)chunk * (n + 1) * ld));
     PGP_TRY(alloc<double>(ctx, dres, (size_t)chunk));
     PGP_TRY(alloc<int>(ctx, dinfo, (size_t)chunk));
     if (pred) {
         PGP_TRY(alloc<double>(ctx, dXs, (size_t)ms * d));
         PGP_CUDA(ctx, cudaMemcpyAsync(dXs.p, Xs, sizeof(double) * ms * d, cudaMemcpyHostToDevice, ctx->stream));
-        PGP_TRY(alloc<double>(ctx, dZs, (size_t)chunk * np * ms * d));
+        PGP_TRY(alloc<double>(ctx, dZs, (size_t)chunk * z_doubles(np, d, ms)));
         PGP_TRY(dB.get(ctx, (size_t)chunk * ms * ld));
         PGP_TRY(alloc<double>(ctx, dout, (size_t)chunk * 2 * ms));
     }
@@ -1329,4 +1329,19 @@ extern "C" int pgp_dev_potrf(pgp_ctx* ctx, double* d_F, int64_t n, int64_t ld, i
     PGP_CUDA(ctx, cudaMemcpyAsync(&h, info.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     PGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return h;
+}
+
+extern "C" int pgp_dev_fastmath(pgp_ctx* ctx, int which, const double* x, int64_t n, double* out) {
+    if (!ctx) return PGP_E_ARG;
+    if (!x || !out || n < 0 || which < 0 || which > 2) return ctx->fail(PGP_E_ARG, "bad argument");
+    if (n == 0) return 0;
+    PGP_TRY(set_device(ctx));
+    DevBuf dx, dout;
+    PGP_TRY(alloc<double>(ctx, dx, (size_t)n));
+    PGP_TRY(alloc<double>(ctx, dout, (size_t)n));
+    PGP_CUDA(ctx, cudaMemcpyAsync(dx.p, x, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+    PGP_TRY(launch_fastmath(ctx, which, dx.as<double>(), n, dout.as<double>()));
+    PGP_CUDA(ctx, cudaMemcpyAsync(out, dout.p, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    PGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
 }

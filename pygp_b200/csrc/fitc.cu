@@ -491,7 +491,7 @@ extern "C" int pgp_fitc_create(pgp_ctx* ctx, const pgp_kernel_spec* spec, const 
     int rc = 0;
     auto A = [&](double** q, size_t cnt) { if (!rc) rc = dev_alloc(ctx, q, cnt); };
     A(&f->d_X, (size_t)n * d); A(&f->d_y, n); A(&f->d_U, (size_t)p * d);
-    A(&f->d_ZX, (size_t)np * n * d); A(&f->d_ZU, (size_t)np * p * d);
+    A(&f->d_ZX, z_doubles(np, d, n)); A(&f->d_ZU, z_doubles(np, d, p));
     A(&f->d_L, (size_t)p * ldp); A(&f->d_A, (size_t)(p + 1) * ldp); A(&f->d_R, (size_t)(p + 1) * ldp);
     A(&f->d_ell, n); A(&f->d_rs, n); A(&f->d_c, n); A(&f->d_alpha, n);
     A(&f->d_a, ldp); A(&f->d_b, ldp); A(&f->d_t, ldp); A(&f->d_w, ldp);
@@ -601,8 +601,8 @@ extern "C" int pgp_fitc_update(pgp_fitc* f, const double* hyp) {
     for (int64_t r0 = 0; !f->dtc && r0 < n; r0 += f->kc_rows) {
         const int64_t rows = std::min(f->kc_rows, n - r0);
         GramArgs gc = gx;
-        gc.Z1 = f->d_ZX + r0 * d;
-        gc.zs1 = n * d;
+        gc.Z1 = f->d_ZX + r0;          // row window of the scaled inputs
+        gc.zd1 = z_stride(n);
         gc.n1 = rows;
         gc.out = f->d_Kc;
         PGP_TRY(launch_gram(ctx, gc));
@@ -786,7 +786,7 @@ static int fitc_predict_impl(pgp_fitc* f, const double* Xs, int64_t ms, double* 
     }
     double *dxs = nullptr, *dzs = nullptr, *dout = nullptr;
     int rc = dev_alloc(ctx, &dxs, (size_t)chunk * d);
-    if (!rc) rc = dev_alloc(ctx, &dzs, (size_t)np * chunk * d);
+    if (!rc) rc = dev_alloc(ctx, &dzs, z_doubles(np, d, chunk));
     if (!rc) rc = dev_alloc(ctx, &dout, (size_t)2 * chunk * rpp);
     Mat L; L.p = f->d_L; L.ld = ldp;
     Mat R; R.p = f->d_R; R.ld = ldp;
@@ -875,7 +875,7 @@ extern "C" int pgp_fitc_full_posterior(pgp_fitc* f, const double* Xs, int64_t ms
     if (!rc) rc = pool_alloc(ctx, &RK, (size_t)ms * ldp);
     if (!rc) rc = pool_alloc(ctx, &S, (size_t)ms * lds);
     if (!rc) rc = dev_alloc(ctx, &dxs, (size_t)ms * d);
-    if (!rc) rc = dev_alloc(ctx, &dzs, (size_t)np * ms * d);
+    if (!rc) rc = dev_alloc(ctx, &dzs, z_doubles(np, d, ms));
     if (!rc) rc = dev_alloc(ctx, &dout, (size_t)2 * ms);
     auto body = [&]() -> int {
         PGP_CUDA(ctx, cudaMemcpyAsync(dxs, Xs, sizeof(double) * ms * d, cudaMemcpyHostToDevice, s));

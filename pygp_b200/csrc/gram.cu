@@ -3,18 +3,30 @@
 // ExactGP.loglikelihood (pygp/inference/exact.py:131-141) and the diagonal
 // forms (Kernel.dget / dgrad).
 //
-// Bound: these kernels write (or read) 8 B per entry and spend
-// ~(3 ndim + 40) FP64 instructions per entry, so on B200 (64 FP64 lanes/SM)
-// they are HBM-bound only for ndim <= 2 and FP64-pipe-bound above that;
-// DESIGN.md section 4 has the arithmetic.
+// Bound: these kernels write (or read) 8 B per entry and spend 2 ndim FP64
+// instructions per entry on the distance plus the epilogue (fastmath.cuh: 11 for SE,
+// 20 for Matern-5/2), so on B200 (64 FP64 lanes/SM) they are HBM-bound for small
+// ndim and FP64-issue-bound above ndim ~ 8; DESIGN.md section 4 has the arithmetic.
 //
 // Layout: inputs are pre-divided by the length-scales (launch_scale, the
-// reference's `rescale`), one scaled copy Z[p] per leaf kernel.  A CTA stages
-// the 64 rows and 64 columns of its tile in shared memory TRANSPOSED
-// ([leaf][dim][64]) so that threads of a warp read consecutive columns without
-// bank conflicts; each thread owns a 4 x 4 micro-tile (rows ty+16a, column
-// pairs 2tx+32h) so the output is written with coalesced 128-bit stores.
+// reference's `rescale`), one scaled copy per leaf kernel, DIMENSION-MAJOR
+// (gram.cuh).  A CTA stages the 64 rows and 64 columns of its tile in shared
+// memory as [leaf][dim][64] -- one 512-byte bulk copy (cp.async.bulk, the TMA
+// engine, completion on an mbarrier) per (leaf, dim) row when the operands are
+// 16-byte aligned, coalesced loads otherwise -- so that threads of a warp read
+// consecutive columns without bank conflicts; each thread owns a 4 x 4
+// micro-tile (rows ty+16a, column pairs 2tx+32h) and the output is written with
+// coalesced 128-bit stores, one micro-tile row at a time.
+//
+// Round-2 measurements that shaped this file (profiles/r02a_gram_probe2.txt,
+// N = 32768, full symmetric square, fraction of the 6545 GB/s HBM copy roof):
+//                               Matern-5/2 d=16   SE d=8   SE d=1
+//   round 1 kernel                    0.38          0.64     0.91
+//   + fastmath epilogue               0.38          0.66     1.02
+//   + bulk-copy staging, 64 regs      0.525         0.78     1.06
+// i.e. the library sqrt / exp AND the strided per-thread staging both had to go.
 
+#include "fastmath.cuh"
 #include "gram.cuh"
 
 namespace pgp {
@@ -30,30 +42,87 @@ struct Tile {
     __device__ int col(int b) const { return 2 * tx + 32 * (b >> 1) + (b & 1); }
 };
 
-// stage `rows` x ndim doubles of every leaf's scaled inputs, transposed to [k][row].
-// Lanes run along the ROW index: the shared stores are conflict-free and the index split is a shift (the
-// earlier k-fastest mapping cost two runtime integer divisions per element and 16-way conflicted stores --
-// 11-way on average over all shared stores of the kernel in ncu).  The global reads are then strided by
-// ndim doubles, but the 32-byte sectors they touch are reused by the next k through L1.
-__device__ __forceinline__ void stage_tile(double* dst, const double* Z, int64_t zstride, int64_t n,
-                                           int64_t r0, int ndim, int n_parts) {
-    for (int p = 0; p < n_parts; ++p) {
-        const double* Zp = Z + p * zstride;
-        double* dp = dst + p * ndim * kTile;
-        for (int idx = threadIdx.x; idx < ndim * kTile; idx += kThreads) {
-            const int k = idx / kTile, r = idx % kTile;      // kTile = 64: shifts
-            const int64_t gr = r0 + r;
-            dp[idx] = gr < n ? Zp[gr * ndim + k] : 0.0;
+// ---- shared memory: [exp table 512 B][mbarrier 16 B][DevSpecHdr][Zs1][Zs2][extra] -----------
+constexpr size_t kHdrBytes = ((sizeof(DevSpecHdr) + 15) / 16) * 16;
+constexpr size_t kSmemFixed = fm::kExpTabDoubles * sizeof(double) + 16 + kHdrBytes;
+
+struct Smem {
+    double* tab;
+    uint64_t* bar;
+    DevSpecHdr* S;
+    double* Zs1;
+    double* Zs2;
+    double* extra;
+    __device__ Smem(unsigned char* raw, int npd) {
+        tab = reinterpret_cast<double*>(raw);
+        bar = reinterpret_cast<uint64_t*>(raw + fm::kExpTabDoubles * sizeof(double));
+        S = reinterpret_cast<DevSpecHdr*>(raw + fm::kExpTabDoubles * sizeof(double) + 16);
+        Zs1 = reinterpret_cast<double*>(raw + kSmemFixed);
+        Zs2 = Zs1 + npd * kTile;
+        extra = Zs2 + npd * kTile;
+    }
+};
+
+// ---- bulk-copy engine (TMA) staging ------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(phase) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(void* sdst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sdst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// once per kernel, before the first stage_tiles: header, exp table, mbarrier
+__device__ __forceinline__ void smem_init(const Smem& sm, const DevSpec* spec, bool bulk) {
+    const int nwords = sizeof(DevSpecHdr) / 4;
+    const int* s = reinterpret_cast<const int*>(&spec->h);
+    int* d = reinterpret_cast<int*>(sm.S);
+    for (int i = threadIdx.x; i < nwords; i += kThreads) d[i] = s[i];
+    fm::load_exp_tab(sm.tab, threadIdx.x, kThreads);
+    if (bulk && threadIdx.x == 0) mbar_init(sm.bar, 1);
+    __syncthreads();
+}
+
+// Stage rows [i0, i0 + 64) of Z1 and [j0, j0 + 64) of Z2 for every (leaf, dim) pair pk:
+// Zs[pk][r] = Z[pk * zd + r0 + r].  Rows past n are the zero padding (or, for a row window,
+// rows of the parent array): always readable, never stored.  Returns with the tile visible
+// to every thread.  In a loop the caller puts a __syncthreads() before the next call.
+__device__ __forceinline__ void stage_tiles(const Smem& sm, const double* Z1, const double* Z2, int64_t zd1, int64_t zd2,
+                                            int64_t i0, int64_t j0, int npd, bool bulk, uint32_t& phase) {
+    if (bulk) {
+        if (threadIdx.x == 0) mbar_expect_tx(sm.bar, (uint32_t)(2 * npd * kTile * sizeof(double)));
+        for (int idx = threadIdx.x; idx < 2 * npd; idx += kThreads) {
+            const int which = idx >= npd, pk = which ? idx - npd : idx;
+            bulk_g2s((which ? sm.Zs2 : sm.Zs1) + pk * kTile, which ? Z2 + pk * zd2 + j0 : Z1 + pk * zd1 + i0,
+                     kTile * sizeof(double), sm.bar);
         }
+        mbar_wait(sm.bar, phase);
+        phase ^= 1;
+    } else {
+        for (int idx = threadIdx.x; idx < npd * kTile; idx += kThreads) {
+            const int pk = idx >> 6, r = idx & 63;
+            sm.Zs1[idx] = Z1[pk * zd1 + i0 + r];
+            sm.Zs2[idx] = Z2[pk * zd2 + j0 + r];
+        }
+        __syncthreads();
     }
 }
 
-__device__ __forceinline__ void load_hdr(DevSpecHdr* dst, const DevSpec* src) {
-    const int nwords = sizeof(DevSpecHdr) / 4;
-    const int* s = reinterpret_cast<const int*>(&src->h);
-    int* d = reinterpret_cast<int*>(dst);
-    for (int i = threadIdx.x; i < nwords; i += kThreads) d[i] = s[i];
-}
+// bulk copies need 16-byte aligned sources: base pointers and every (leaf, dim) row
+inline bool bulk_ok(const double* Z, int64_t zd) { return (reinterpret_cast<uintptr_t>(Z) & 15) == 0 && (zd & 1) == 0; }
 
 // triangular tile index -> (ti, tj) with tj <= ti
 __device__ __forceinline__ void tri_decode(int64_t idx, int* ti, int* tj) {
@@ -62,6 +131,54 @@ __device__ __forceinline__ void tri_decode(int64_t idx, int* ti, int* tj) {
     while ((t + 1) * (t + 2) / 2 <= idx) ++t;
     *ti = (int)t;
     *tj = (int)(idx - t * (t + 1) / 2);
+}
+
+// ---- one leaf at one entry ------------------------------------------------------------------------
+constexpr bool is_fast_type(int t) { return t == PGP_SE || (t >= PGP_MATERN1 && t <= PGP_MATERN5); }
+
+// covariance only, SE / Matern through fastmath.cuh.  `bad` is raised when the fast exp left the
+// normal range; the caller then redoes its micro-tile with the library (slow_redo).
+template <int PTYPE>
+__device__ __forceinline__ double fast_value(double two_logsf, double D, const double* tab, int& bad) {
+    if (PTYPE == PGP_SE) return fm::exp_tab(fma(D, -0.5, two_logsf), tab, bad);
+    const double r = fm::sqrt_pos(D);
+    const double S = fm::exp_tab(two_logsf - r, tab, bad);
+    if (PTYPE == PGP_MATERN1) return S;
+    if (PTYPE == PGP_MATERN3) return fma(S, r, S);
+    return S * fma(r, fma(r, fm::kFmC[5], 1.0), 1.0);
+}
+
+// covariance and hyper-gradient pieces (spec.cuh: PartVal); SE / Matern through fastmath.cuh with
+// the clamped exp (entries below 1e-307 only ever enter sums / derivative matrices here), the
+// other leaves through the library
+template <int PTYPE, bool GRAD>
+__device__ __forceinline__ void leaf_eval(const DevPart& p, double D, PartVal& v, const double* tab) {
+    if (PTYPE == PGP_SE) {
+        const double K = fm::exp_tab_clamped(fma(D, -0.5, p.two_logsf), tab);
+        v.K = K;
+        if (GRAD) { v.g_sf = 2 * K; v.g_iso = K * D; v.ardw = K; v.e0 = 0; }
+    } else if (PTYPE >= PGP_MATERN1 && PTYPE <= PGP_MATERN5) {
+        double rinv = 0.0;
+        const double r = (GRAD && PTYPE == PGP_MATERN1) ? fm::sqrt_rsqrt_pos(D, rinv) : fm::sqrt_pos(D);
+        const double S = fm::exp_tab_clamped(p.two_logsf - r, tab);
+        const double f = PTYPE == PGP_MATERN1 ? 1.0 : PTYPE == PGP_MATERN3 ? 1 + r : fma(r, fma(r, fm::kFmC[5], 1.0), 1.0);
+        const double K = S * f;
+        v.K = K;
+        if (GRAD) {
+            // matern.py:76-90: M = S df(r); d/d log ell = M r (iso) or (M / r) (z1k - z2k)^2 (ARD),
+            // M / r = S / r, S, S (1 + r) / 3 for nu = 1/2, 3/2, 5/2 without the division; `r < 1e-12 -> 0` kept
+            const double df = PTYPE == PGP_MATERN1 ? 1.0 : PTYPE == PGP_MATERN3 ? r : r * (1 + r) * fm::kFmC[5];
+            const double Mr = PTYPE == PGP_MATERN1 ? S * rinv : PTYPE == PGP_MATERN3 ? S : S * (1 + r) * fm::kFmC[5];
+            v.g_sf = 2 * K;
+            v.g_iso = S * df * r;
+            v.ardw = (r < 1e-12) ? 0.0 : Mr;
+            v.e0 = 0;
+        }
+    } else {
+        DevPart q = p;
+        q.type = PTYPE;   // compile-time type: the switch in part_eval folds
+        part_eval<GRAD>(q, D, v);
+    }
 }
 
 // all leaves at one entry: squared distances by direct differences
@@ -164,34 +281,124 @@ __device__ __forceinline__ double composite_gradxy(const DevSpecHdr& S, const De
     return node[S.n_nodes - 1].xy;
 }
 
+// squared distances of a thread's 4 x 4 micro-tile for one leaf (rows of Zs: [dim][64])
+__device__ __forceinline__ void micro_dist(const double* Zs1, const double* Zs2, int ndim, const Tile& t,
+                                           double (&D)[4][4]) {
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y) D[x][y] = 0.0;
+#pragma unroll 4
+    for (int k = 0; k < ndim; ++k) {
+        double zi[4], zj[4];
+#pragma unroll
+        for (int x = 0; x < 4; ++x) zi[x] = Zs1[k * kTile + t.row(x)];
+        const double2 q0 = *reinterpret_cast<const double2*>(&Zs2[k * kTile + 2 * t.tx]);
+        const double2 q1 = *reinterpret_cast<const double2*>(&Zs2[k * kTile + 2 * t.tx + 32]);
+        zj[0] = q0.x; zj[1] = q0.y; zj[2] = q1.x; zj[3] = q1.y;
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+            for (int y = 0; y < 4; ++y) {
+                const double df = zi[x] - zj[y];
+                D[x][y] = fma(df, df, D[x][y]);
+            }
+    }
+}
+
+// ---- vectorised composite value (trees of depth <= 2) ------------------------------------------
+// One leaf for the thread's whole micro-tile: 16 distances, then ONE warp-uniform switch on the
+// leaf type around a 16-entry epilogue loop -- instead of the per-entry tree interpreter, whose
+// local arrays and rolled loops ran the SE + Periodic Gram build at 1.0 TB/s (round 1).
+__device__ __noinline__ double lib_value(const DevPart& part, double D) {
+    PartVal v;
+    part_eval<false>(part, D, v);
+    return v.K;
+}
+
+__device__ __forceinline__ void leaf_vec(const DevPart& part, const double* Zs1, const double* Zs2, int ndim,
+                                         const Tile& t, const double* tab, double (&K)[4][4], int& bad) {
+    micro_dist(Zs1, Zs2, ndim, t, K);
+#define PGP_LEAF_LOOP(EXPR)                              \
+    _Pragma("unroll") for (int x = 0; x < 4; ++x)        \
+        _Pragma("unroll") for (int y = 0; y < 4; ++y) { const double D = K[x][y]; K[x][y] = (EXPR); }
+    switch (part.type) {
+        case PGP_SE: PGP_LEAF_LOOP(fast_value<PGP_SE>(part.two_logsf, D, tab, bad)) break;
+        case PGP_MATERN1: PGP_LEAF_LOOP(fast_value<PGP_MATERN1>(part.two_logsf, D, tab, bad)) break;
+        case PGP_MATERN3: PGP_LEAF_LOOP(fast_value<PGP_MATERN3>(part.two_logsf, D, tab, bad)) break;
+        case PGP_MATERN5: PGP_LEAF_LOOP(fast_value<PGP_MATERN5>(part.two_logsf, D, tab, bad)) break;
+        default: PGP_LEAF_LOOP(lib_value(part, D)) break;     // Periodic / RQ: library sincos / pow
+    }
+#undef PGP_LEAF_LOOP
+}
+
+__device__ __forceinline__ void vec_fold(double (&acc)[4][4], const double (&v)[4][4], int kind, bool first) {
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y)
+            acc[x][y] = first ? v[x][y] : (kind == NK_SUM ? acc[x][y] + v[x][y] : acc[x][y] * v[x][y]);
+}
+
+// value of a depth <= 2 tree on the micro-tile, folding children in the order tree_forward does
+__device__ __forceinline__ void composite_vec(const DevSpecHdr& S, const double* Zs1, const double* Zs2, int ndim,
+                                              const Tile& t, const double* tab, double (&res)[4][4], int& bad) {
+    const int root = S.n_nodes - 1;
+    if (S.node_kind[root] == NK_LEAF) {
+        const int p = S.node_leaf[root];
+        leaf_vec(S.parts[p], Zs1 + p * ndim * kTile, Zs2 + p * ndim * kTile, ndim, t, tab, res, bad);
+        return;
+    }
+    const int rkind = S.node_kind[root];
+    const int* rc = S.child + S.node_child0[root];
+    double v[4][4];
+    for (int c = 0; c < S.node_nchild[root]; ++c) {
+        const int cn = rc[c];
+        if (S.node_kind[cn] == NK_LEAF) {
+            const int p = S.node_leaf[cn];
+            leaf_vec(S.parts[p], Zs1 + p * ndim * kTile, Zs2 + p * ndim * kTile, ndim, t, tab, v, bad);
+            vec_fold(res, v, rkind, c == 0);
+        } else {
+            double sub[4][4];
+            const int ckind = S.node_kind[cn];
+            const int* gc = S.child + S.node_child0[cn];
+            for (int g = 0; g < S.node_nchild[cn]; ++g) {
+                const int p = S.node_leaf[gc[g]];
+                leaf_vec(S.parts[p], Zs1 + p * ndim * kTile, Zs2 + p * ndim * kTile, ndim, t, tab, v, bad);
+                vec_fold(sub, v, ckind, g == 0);
+            }
+            vec_fold(res, sub, rkind, c == 0);
+        }
+    }
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------
-// scale: Z[b][p][i][k] = X[i][k] / ell[b][p][k]
+// scale: Z[b][p][k][i] = X[i][k] / ell[b][p][k], zero for n <= i < zd
 // ---------------------------------------------------------------------------
-__global__ void scale_kernel(const DevSpec* __restrict__ spec, const double* __restrict__ X, int64_t n,
+__global__ void scale_kernel(const DevSpec* __restrict__ spec, const double* __restrict__ X, int64_t n, int64_t zd,
                              int ndim, int n_parts, double* __restrict__ Z) {
     const int b = blockIdx.y;
     const DevSpec* sp = spec + b;
-    const int64_t per_part = n * ndim;
-    const int64_t total = per_part * n_parts;
+    const int64_t total = (int64_t)n_parts * ndim * zd;
     double* Zb = Z + (int64_t)b * total;
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (int64_t)gridDim.x * blockDim.x) {
-        int p = (int)(idx / per_part);
-        int64_t rem = idx - p * per_part;
-        int k = (int)(rem % ndim);
-        Zb[idx] = X[rem] / sp->ell[p][k];
+        const int64_t pk = idx / zd, i = idx - pk * zd;
+        const int p = (int)(pk / ndim), k = (int)(pk - (int64_t)p * ndim);
+        Zb[idx] = i < n ? X[i * ndim + k] / sp->ell[p][k] : 0.0;
     }
 }
 
 int launch_scale(pgp_ctx* ctx, const DevSpec* d_spec, const double* d_X, int64_t n, int ndim,
                  int n_parts, double* d_Z, int batch) {
     if (n == 0) return 0;
-    int64_t total = n * ndim * n_parts;
+    const int64_t zd = z_stride(n);
+    int64_t total = zd * ndim * n_parts;
     int blocks = (int)std::min<int64_t>(ceil_div(total, 256), 148 * 8);
     Launch L(ctx, PC_OTHER, 16.0 * total * batch);
-    scale_kernel<<<dim3(blocks, batch), 256, 0, ctx->stream>>>(d_spec, d_X, n, ndim, n_parts, d_Z);
+    scale_kernel<<<dim3(blocks, batch), 256, 0, ctx->stream>>>(d_spec, d_X, n, zd, ndim, n_parts, d_Z);
     return check_launch(ctx, "scale_kernel");
 }
 
@@ -199,18 +406,76 @@ int launch_scale(pgp_ctx* ctx, const DevSpec* d_spec, const double* d_X, int64_t
 // Gram / single hyper-gradient tile kernel
 //   PTYPE >= 0: single leaf of that type (register micro-tile fast path)
 //   PTYPE <  0: composite, one entry at a time through the tree
+//   MODE 0 value, 1 d/d hyper[hidx], 2 d/d x1[xdim], 3 d2/d x1[xdim] d x2[ydim]
 // ---------------------------------------------------------------------------
-// Matern values: capped at 64 registers (4 CTAs / SM; a few spilled bytes): the kernel is latency-bound, and the
-// fourth resident CTA is worth +6 % (2.33 -> 2.48 TB/s at d = 16); SE is 2 % faster without the cap.
+struct GramKArgs : GramArgs {
+    int bulk = 0;
+};
+
+// store one micro-tile row (4 entries: column pairs gj0 + 32 h).  OS1: unit column stride (every mode
+// but the input-gradients).  The noise of the diagonal is added by the caller, on diagonal tiles only.
+template <bool OS1>
+__device__ __forceinline__ void store_row(double* out, int64_t ldo, int64_t ostride, int64_t n1, int64_t n2, bool vec_ok,
+                                          int64_t gi, int64_t gj0, const double (&v)[4]) {
+    if (gi >= n1) return;
+    const int64_t os = OS1 ? 1 : ostride;
+    double* rowp = out + gi * ldo + gj0 * os;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int64_t gj = gj0 + 32 * h;
+        double* dst = rowp + 32 * h * os;
+        if (OS1 && vec_ok && gj + 1 < n2) {
+            *reinterpret_cast<double2*>(dst) = make_double2(v[2 * h], v[2 * h + 1]);
+        } else {
+            if (gj < n2) dst[0] = v[2 * h];
+            if (gj + 1 < n2) dst[os] = v[2 * h + 1];
+        }
+    }
+}
+
+// K + sn2 I: on a diagonal tile (i0 == j0) the entry (row, col) of the micro-tile row is on the diagonal
+// when col == row
+__device__ __forceinline__ void add_noise_row(double (&v)[4], const Tile& t, int x, double noise) {
+#pragma unroll
+    for (int y = 0; y < 4; ++y)
+        if (t.col(y) == t.row(x)) v[y] += noise;
+}
+
+// cold path of the fast value kernels: the thread's micro-tile again, with the library functions
+// (scalars by value: taking the address of the kernel parameter block would copy it to the stack
+// in every thread's prologue)
+template <int PTYPE>
+__device__ __noinline__ void slow_redo(const DevSpecHdr* S, const double* Zs1, const double* Zs2, int ndim, double* out,
+                                       int64_t ldo, int64_t n1, int64_t n2, int64_t i0, int64_t j0, double noise,
+                                       double* T) {
+    Tile t;
+    DevPart part = S->parts[0];
+    part.type = PTYPE;
+    for (int x = 0; x < 4; ++x)
+        for (int y = 0; y < 4; ++y) {
+            double D = 0.0;
+            for (int k = 0; k < ndim; ++k) {
+                const double df = Zs1[k * kTile + t.row(x)] - Zs2[k * kTile + t.col(y)];
+                D = fma(df, df, D);
+            }
+            PartVal v;
+            part_eval<false>(part, D, v);
+            const int64_t gi = i0 + t.row(x), gj = j0 + t.col(y);
+            if (T) T[t.row(x) * (kTile + 1) + t.col(y)] = v.K;
+            if (gi < n1 && gj < n2) out[gi * ldo + gj] = v.K + (gi == gj ? noise : 0.0);
+        }
+}
+
 template <int PTYPE, int MODE>
-__global__ void __launch_bounds__(kThreads, (MODE == 0 && PTYPE >= PGP_MATERN1 && PTYPE <= PGP_MATERN5) ? 4 : 0) gram_kernel(GramArgs a) {
+__global__ void __launch_bounds__(kThreads, (MODE == 0 && is_fast_type(PTYPE)) ? 4 : (MODE == 0 && PTYPE < 0) ? 2 : 1) gram_kernel(GramKArgs a) {
     constexpr bool GRAD1 = MODE == 1;
     constexpr bool GRADX = MODE == 2;
     constexpr bool GRADXY = MODE == 3;      // composite path only (PTYPE < 0)
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    DevSpecHdr* S = reinterpret_cast<DevSpecHdr*>(smem_raw);
-    double* Zs1 = reinterpret_cast<double*>(smem_raw + ((sizeof(DevSpecHdr) + 15) / 16) * 16);
-    double* Zs2 = Zs1 + a.n_parts * a.ndim * kTile;
+    constexpr bool FAST = MODE == 0 && is_fast_type(PTYPE);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int ndim = a.ndim, n_parts = a.n_parts, npd = n_parts * ndim;
+    const Smem sm(smem_raw, npd);
+    const DevSpecHdr* S = sm.S;
 
     const bool tri_grid = a.lower_only || a.symmetric;
     const int b = tri_grid ? blockIdx.y : blockIdx.z;
@@ -218,74 +483,91 @@ __global__ void __launch_bounds__(kThreads, (MODE == 0 && PTYPE >= PGP_MATERN1 &
     if (tri_grid) tri_decode(blockIdx.x, &ti, &tj);
     else { ti = blockIdx.y; tj = blockIdx.x; }
     const int64_t i0 = (int64_t)ti * kTile, j0 = (int64_t)tj * kTile;
-    const int ndim = a.ndim, n_parts = a.n_parts;
 
-    load_hdr(S, a.spec + b);
-    const int64_t zs1 = a.zs1 ? a.zs1 : a.n1 * ndim, zs2 = a.zs2 ? a.zs2 : a.n2 * ndim;
-    stage_tile(Zs1, a.Z1 + (int64_t)b * n_parts * zs1, zs1, a.n1, i0, ndim, n_parts);
-    stage_tile(Zs2, a.Z2 + (int64_t)b * n_parts * zs2, zs2, a.n2, j0, ndim, n_parts);
-    __syncthreads();
+    smem_init(sm, a.spec + b, a.bulk);
+    uint32_t phase = 0;
+    stage_tiles(sm, a.Z1 + (int64_t)b * npd * a.zd1, a.Z2 + (int64_t)b * npd * a.zd2, a.zd1, a.zd2, i0, j0, npd, a.bulk, phase);
 
     Tile t;
     double* out = a.out + (int64_t)b * a.out_bstride;
     int gpart = 0, gkind = 0, gdim = 0;
     if (GRAD1) classify_hyper(*S, a.hidx, &gpart, &gkind, &gdim);
     const double noise = a.add_noise ? S->sn2 : 0.0;
+    const bool diag_noise = a.add_noise && i0 == j0;     // tile-uniform: off the diagonal tiles nothing is added
     const int xdim = a.xdim;
+    const bool vec_ok = a.ostride == 1 && ((a.ldo & 1) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    const bool mirror = a.symmetric && ti != tj;
+    double* T = sm.extra;                   // [64][kTile + 1] transpose scratch of the mirrored tile
+    constexpr int TP = kTile + 1;
+    int bad = 0;
 
-    double res[4][4];
     if (PTYPE >= 0) {
         double D[4][4];
+        micro_dist(sm.Zs1, sm.Zs2, ndim, t, D);
+        const DevPart part = S->parts[0];
 #pragma unroll
-        for (int x = 0; x < 4; ++x)
-#pragma unroll
-            for (int y = 0; y < 4; ++y) D[x][y] = 0.0;
-        for (int k = 0; k < ndim; ++k) {
-            double zi[4], zj[4];
-#pragma unroll
-            for (int x = 0; x < 4; ++x) zi[x] = Zs1[k * kTile + t.row(x)];
-            double2 q0 = *reinterpret_cast<const double2*>(&Zs2[k * kTile + 2 * t.tx]);
-            double2 q1 = *reinterpret_cast<const double2*>(&Zs2[k * kTile + 2 * t.tx + 32]);
-            zj[0] = q0.x; zj[1] = q0.y; zj[2] = q1.x; zj[3] = q1.y;
-#pragma unroll
-            for (int x = 0; x < 4; ++x)
-#pragma unroll
-                for (int y = 0; y < 4; ++y) {
-                    double df = zi[x] - zj[y];
-                    D[x][y] += df * df;
-                }
-        }
-        DevPart part = S->parts[0];
-        part.type = PTYPE;  // compile-time type: the switch in part_eval folds
-#pragma unroll
-        for (int x = 0; x < 4; ++x)
+        for (int x = 0; x < 4; ++x) {
+            double v[4];
 #pragma unroll
             for (int y = 0; y < 4; ++y) {
-                PartVal v;
-                part_eval<GRAD1 || GRADX>(part, D[x][y], v);
-                if (GRADX) {
-                    double sd = Zs1[xdim * kTile + t.row(x)] - Zs2[xdim * kTile + t.col(y)];
-                    res[x][y] = leaf_gradx(part, v, sd, a.spec[b].ell[0][xdim]);
-                } else if (GRAD1) {
-                    double dk2 = 0.0;
-                    if (gkind == SLOT_ARD) {
-                        double df = Zs1[gdim * kTile + t.row(x)] - Zs2[gdim * kTile + t.col(y)];
-                        dk2 = df * df;
-                    }
-                    res[x][y] = slot_value(v, gkind, dk2);
+                if (FAST) {
+                    v[y] = fast_value<PTYPE>(part.two_logsf, D[x][y], sm.tab, bad);
                 } else {
-                    res[x][y] = v.K;
+                    PartVal pv;
+                    leaf_eval<PTYPE, GRAD1 || GRADX>(part, D[x][y], pv, sm.tab);
+                    if (GRADX) {
+                        double sd = sm.Zs1[xdim * kTile + t.row(x)] - sm.Zs2[xdim * kTile + t.col(y)];
+                        DevPart q = part;
+                        q.type = PTYPE;
+                        v[y] = leaf_gradx(q, pv, sd, a.spec[b].ell[0][xdim]);
+                    } else if (GRAD1) {
+                        double dk2 = 0.0;
+                        if (gkind == SLOT_ARD) {
+                            double df = sm.Zs1[gdim * kTile + t.row(x)] - sm.Zs2[gdim * kTile + t.col(y)];
+                            dk2 = df * df;
+                        }
+                        v[y] = slot_value(pv, gkind, dk2);
+                    } else {
+                        v[y] = pv.K;
+                    }
                 }
             }
+            if (diag_noise) add_noise_row(v, t, x, noise);
+            store_row<MODE < 2>(out, a.ldo, a.ostride, a.n1, a.n2, vec_ok, i0 + t.row(x), j0 + 2 * t.tx, v);
+            if (mirror) {
+#pragma unroll
+                for (int y = 0; y < 4; ++y) T[t.row(x) * TP + t.col(y)] = v[y];
+            }
+        }
+        if (FAST && __builtin_expect(bad, 0))
+            slow_redo<PTYPE>(S, sm.Zs1, sm.Zs2, ndim, out, a.ldo, a.n1, a.n2, i0, j0, noise, mirror ? T : nullptr);
     } else {
+        bool interp = true;
+        if (MODE == 0 && S->depth2) {
+            // vectorised composite: whole micro-tile per leaf, children folded in tree order
+            double res[4][4];
+            composite_vec(*S, sm.Zs1, sm.Zs2, ndim, t, sm.tab, res, bad);
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+                if (diag_noise) add_noise_row(res[x], t, x, noise);
+                store_row<true>(out, a.ldo, 1, a.n1, a.n2, vec_ok, i0 + t.row(x), j0 + 2 * t.tx, res[x]);
+                if (mirror) {
+#pragma unroll
+                    for (int y = 0; y < 4; ++y) T[t.row(x) * TP + t.col(y)] = res[x][y];
+                }
+            }
+            interp = bad != 0;      // a leaf left the fast exp's range: redo this thread's entries below
+        }
 #pragma unroll 1
-        for (int x = 0; x < 4; ++x)
+        for (int x = 0; interp && x < 4; ++x) {
+            double v[4];
 #pragma unroll 1
             for (int y = 0; y < 4; ++y) {
-                const double* z1 = Zs1 + t.row(x);
-                const double* z2 = Zs2 + t.col(y);
+                const double* z1 = sm.Zs1 + t.row(x);
+                const double* z2 = sm.Zs2 + t.col(y);
+                double r;
                 if (GRADXY) {
-                    res[x][y] = composite_gradxy(*S, a.spec + b, z1, z2, xdim, a.ydim);
+                    r = composite_gradxy(*S, a.spec + b, z1, z2, xdim, a.ydim);
                 } else if (GRADX) {
                     PartVal pv[kMaxParts];
                     double val[kMaxNodes], adj[kMaxNodes];
@@ -297,36 +579,23 @@ __global__ void __launch_bounds__(kThreads, (MODE == 0 && PTYPE >= PGP_MATERN1 &
                         double sd = z1[(p * ndim + xdim) * kTile] - z2[(p * ndim + xdim) * kTile];
                         g += adj[S->leaf_node[p]] * leaf_gradx(S->parts[p], pv[p], sd, a.spec[b].ell[p][xdim]);
                     }
-                    res[x][y] = g;
+                    r = g;
                 } else if (GRAD1) {
-                    res[x][y] = composite_grad1(*S, z1, z2, gpart, gkind, gdim);
+                    r = composite_grad1(*S, z1, z2, gpart, gkind, gdim);
                 } else {
                     PartVal pv[kMaxParts];
                     double val[kMaxNodes];
                     eval_parts<false>(*S, z1, z2, pv);
-                    res[x][y] = tree_forward(*S, pv, val);
+                    r = tree_forward(*S, pv, val);
                 }
+                // dynamic y: keep v[] in registers with a static store
+                if (y == 0) v[0] = r; else if (y == 1) v[1] = r; else if (y == 2) v[2] = r; else v[3] = r;
             }
-    }
-
-    const int64_t os = a.ostride;
-    const bool vec_ok = os == 1 && ((a.ldo & 1) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+            if (diag_noise) add_noise_row(v, t, x, noise);
+            store_row<MODE < 2>(out, a.ldo, a.ostride, a.n1, a.n2, vec_ok, i0 + t.row(x), j0 + 2 * t.tx, v);
+            if (mirror) {
 #pragma unroll
-    for (int x = 0; x < 4; ++x) {
-        int64_t gi = i0 + t.row(x);
-        if (gi >= a.n1) continue;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            int64_t gj = j0 + t.col(2 * h);
-            double v0 = res[x][2 * h], v1 = res[x][2 * h + 1];
-            if (gi == gj) v0 += noise;
-            if (gi == gj + 1) v1 += noise;
-            double* dst = out + gi * a.ldo + gj * os;
-            if (vec_ok && gj + 1 < a.n2) {
-                *reinterpret_cast<double2*>(dst) = make_double2(v0, v1);
-            } else {
-                if (gj < a.n2) dst[0] = v0;
-                if (gj + 1 < a.n2) dst[os] = v1;
+                for (int y = 0; y < 4; ++y) T[t.row(x) * TP + t.col(y)] = v[y];
             }
         }
     }
@@ -335,13 +604,7 @@ __global__ void __launch_bounds__(kThreads, (MODE == 0 && PTYPE >= PGP_MATERN1 &
     // transpose of this one -- k and every dk/dhyper are symmetric in (x1, x2) --
     // so it is written from a shared-memory transpose instead of being
     // recomputed: half the FP64 work per byte written.
-    if (a.symmetric && ti != tj) {
-        double* T = Zs2 + n_parts * ndim * kTile;   // [64][kTile + 1]
-        constexpr int TP = kTile + 1;
-#pragma unroll
-        for (int x = 0; x < 4; ++x)
-#pragma unroll
-            for (int y = 0; y < 4; ++y) T[t.row(x) * TP + t.col(y)] = res[x][y];
+    if (mirror) {
         __syncthreads();
 #pragma unroll
         for (int x = 0; x < 4; ++x) {
@@ -365,7 +628,7 @@ __global__ void __launch_bounds__(kThreads, (MODE == 0 && PTYPE >= PGP_MATERN1 &
 }
 
 template <int PTYPE, int MODE>
-static int launch_gram_t(pgp_ctx* ctx, const GramArgs& a, size_t smem) {
+static int launch_gram_t(pgp_ctx* ctx, const GramKArgs& a, size_t smem) {
     auto kern = gram_kernel<PTYPE, MODE>;
     PGP_TRY(ensure_dyn_smem(ctx, kern, smem));
     int64_t t1 = ceil_div(a.n1, kTile), t2 = ceil_div(a.n2, kTile);
@@ -384,19 +647,25 @@ static int launch_gram_t(pgp_ctx* ctx, const GramArgs& a, size_t smem) {
     return check_launch(ctx, "gram_kernel");
 }
 
-int launch_gram(pgp_ctx* ctx, const GramArgs& a) {
-    if (a.n1 == 0 || a.n2 == 0) return 0;
-    if ((a.lower_only || a.symmetric) && a.n1 != a.n2)
+int launch_gram(pgp_ctx* ctx, const GramArgs& a0) {
+    if (a0.n1 == 0 || a0.n2 == 0) return 0;
+    if ((a0.lower_only || a0.symmetric) && a0.n1 != a0.n2)
         return ctx->fail(PGP_E_ARG, "gram: lower_only / symmetric need a square matrix");
-    if (a.n_parts * a.ndim > 192)
+    if (a0.n_parts * a0.ndim > 192)
         return ctx->fail(PGP_E_ARG, "gram: n_parts * ndim > 192 exceeds the shared-memory tile");
-    size_t smem = ((sizeof(DevSpecHdr) + 15) / 16) * 16 + 2ull * a.n_parts * a.ndim * kTile * sizeof(double);
+    GramKArgs a;
+    static_cast<GramArgs&>(a) = a0;
+    if (!a.zd1) a.zd1 = z_stride(a.n1);
+    if (!a.zd2) a.zd2 = z_stride(a.n2);
+    static const int use_bulk = [] { const char* e = getenv("PGP_GRAM_BULK"); return e ? atoi(e) : 1; }();
+    a.bulk = use_bulk && bulk_ok(a.Z1, a.zd1) && bulk_ok(a.Z2, a.zd2);
+    size_t smem = kSmemFixed + 2ull * a.n_parts * a.ndim * kTile * sizeof(double);
     if (a.symmetric) smem += (size_t)kTile * (kTile + 1) * sizeof(double);
     const int mode = a.xdim >= 0 ? (a.ydim >= 0 ? 3 : 2) : (a.hidx >= 0 ? 1 : 0);
     if (mode >= 2 && (a.xdim >= a.ndim || a.ydim >= a.ndim || a.symmetric || a.lower_only))
         return ctx->fail(PGP_E_ARG, "gram: bad input-gradient request");
     if (mode == 3) return launch_gram_t<-1, 3>(ctx, a, smem);    // second derivatives: tree path only
-    if (a.ostride != 1 && a.symmetric) return ctx->fail(PGP_E_ARG, "gram: strided output cannot be mirrored");
+    if (a.ostride != 1 && (a.symmetric || mode < 2)) return ctx->fail(PGP_E_ARG, "gram: strided output is for input-gradients only");
     int st = a.n_parts == 1 ? a.single_type : -1;
 #define PGP_GRAM_CASE(T)                                                                  \
     case T:                                                                               \
@@ -420,38 +689,19 @@ int launch_gram(pgp_ctx* ctx, const GramArgs& a) {
 // acc[1 + h] (the caller owns acc[0]); K and all dK_h are recomputed from the
 // staged inputs, nothing is read from memory.
 template <int PTYPE>
-__device__ __forceinline__ void trace_tile(const DevSpecHdr* S, const double* Zs1, const double* Zs2, int ndim,
-                                           int n_parts, const Tile& t, double (&wq)[4][4], double* acc) {
+__device__ __forceinline__ void trace_tile(const DevSpecHdr* S, const double* Zs1, const double* Zs2, const double* tab,
+                                           int ndim, int n_parts, const Tile& t, double (&wq)[4][4], double* acc) {
     if (PTYPE >= 0) {
         double D[4][4];
-#pragma unroll
-        for (int x = 0; x < 4; ++x)
-#pragma unroll
-            for (int y = 0; y < 4; ++y) D[x][y] = 0.0;
-        for (int k = 0; k < ndim; ++k) {
-            double zi[4], zj[4];
-#pragma unroll
-            for (int x = 0; x < 4; ++x) zi[x] = Zs1[k * kTile + t.row(x)];
-            double2 q0 = *reinterpret_cast<const double2*>(&Zs2[k * kTile + 2 * t.tx]);
-            double2 q1 = *reinterpret_cast<const double2*>(&Zs2[k * kTile + 2 * t.tx + 32]);
-            zj[0] = q0.x; zj[1] = q0.y; zj[2] = q1.x; zj[3] = q1.y;
-#pragma unroll
-            for (int x = 0; x < 4; ++x)
-#pragma unroll
-                for (int y = 0; y < 4; ++y) {
-                    double df = zi[x] - zj[y];
-                    D[x][y] += df * df;
-                }
-        }
-        DevPart part = S->parts[0];
-        part.type = PTYPE;
+        micro_dist(Zs1, Zs2, ndim, t, D);
+        const DevPart part = S->parts[0];
         double s_sf = 0.0, s_iso = 0.0, s_e0 = 0.0;
 #pragma unroll
         for (int x = 0; x < 4; ++x)
 #pragma unroll
             for (int y = 0; y < 4; ++y) {
                 PartVal v;
-                part_eval<true>(part, D[x][y], v);
+                leaf_eval<PTYPE, true>(part, D[x][y], v, tab);
                 double w = wq[x][y];
                 s_sf += w * v.g_sf;
                 s_iso += w * v.g_iso;
@@ -535,15 +785,14 @@ __device__ __forceinline__ void trace_tile(const DevSpecHdr* S, const double* Zs
 constexpr int kTraceCtasPerSm = 4;
 
 template <int PTYPE>
-__global__ void __launch_bounds__(kThreads) trace_kernel(TraceArgs a, int64_t n_tiles) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    DevSpecHdr* S = reinterpret_cast<DevSpecHdr*>(smem_raw);
-    double* Zs1 = reinterpret_cast<double*>(smem_raw + ((sizeof(DevSpecHdr) + 15) / 16) * 16);
-    double* Zs2 = Zs1 + a.n_parts * a.ndim * kTile;
-    double* red = Zs2 + a.n_parts * a.ndim * kTile;  // [8 warps][nhyper + 1]
-
-    const int ndim = a.ndim, n_parts = a.n_parts, nh = a.nhyper;
-    load_hdr(S, a.spec);
+__global__ void __launch_bounds__(kThreads) trace_kernel(TraceArgs a, int64_t n_tiles, int bulk) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int ndim = a.ndim, n_parts = a.n_parts, nh = a.nhyper, npd = n_parts * ndim;
+    const Smem sm(smem_raw, npd);
+    const DevSpecHdr* S = sm.S;
+    double* red = sm.extra;  // [8 warps][nhyper + 1]
+    smem_init(sm, a.spec, bulk);
+    uint32_t phase = 0;
     Tile t;
 
     double acc[kMaxHyper + 1];
@@ -553,10 +802,8 @@ __global__ void __launch_bounds__(kThreads) trace_kernel(TraceArgs a, int64_t n_
         int ti, tj;
         tri_decode(tile, &ti, &tj);
         const int64_t i0 = (int64_t)ti * kTile, j0 = (int64_t)tj * kTile;
-        __syncthreads();  // previous tile fully consumed (also orders load_hdr)
-        stage_tile(Zs1, a.Z, a.n * ndim, a.n, i0, ndim, n_parts);
-        stage_tile(Zs2, a.Z, a.n * ndim, a.n, j0, ndim, n_parts);
-        __syncthreads();
+        __syncthreads();  // previous tile fully consumed
+        stage_tiles(sm, a.Z, a.Z, a.zd, a.zd, i0, j0, npd, bulk, phase);
 
         // weights: w Q_ij with w = 2 below the diagonal, 1 on it, 0 above / outside
         double wq[4][4];
@@ -577,7 +824,7 @@ __global__ void __launch_bounds__(kThreads) trace_kernel(TraceArgs a, int64_t n_
             }
         }
 
-        trace_tile<PTYPE>(S, Zs1, Zs2, ndim, n_parts, t, wq, acc);
+        trace_tile<PTYPE>(S, sm.Zs1, sm.Zs2, sm.tab, ndim, n_parts, t, wq, acc);
     }
 
     // CTA reduction in a fixed order -> one row of partials per CTA
@@ -606,15 +853,14 @@ __global__ void __launch_bounds__(kThreads) trace_kernel(TraceArgs a, int64_t n_
 // partials[cta][h]; reduced by trace_rect_finish_kernel in a fixed order.
 // ---------------------------------------------------------------------------
 template <int PTYPE>
-__global__ void __launch_bounds__(kThreads) trace_rect_kernel(TraceRectArgs a, int64_t t2, int64_t n_tiles) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    DevSpecHdr* S = reinterpret_cast<DevSpecHdr*>(smem_raw);
-    double* Zs1 = reinterpret_cast<double*>(smem_raw + ((sizeof(DevSpecHdr) + 15) / 16) * 16);
-    double* Zs2 = Zs1 + a.n_parts * a.ndim * kTile;
-    double* red = Zs2 + a.n_parts * a.ndim * kTile;  // [8 warps][nhyper + 1]
-
-    const int ndim = a.ndim, n_parts = a.n_parts, nh = a.nhyper;
-    load_hdr(S, a.spec);
+__global__ void __launch_bounds__(kThreads) trace_rect_kernel(TraceRectArgs a, int64_t t2, int64_t n_tiles, int bulk) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int ndim = a.ndim, n_parts = a.n_parts, nh = a.nhyper, npd = n_parts * ndim;
+    const Smem sm(smem_raw, npd);
+    const DevSpecHdr* S = sm.S;
+    double* red = sm.extra;  // [8 warps][nhyper + 1]
+    smem_init(sm, a.spec, bulk);
+    uint32_t phase = 0;
     Tile t;
 
     double acc[kMaxHyper + 1];
@@ -624,9 +870,7 @@ __global__ void __launch_bounds__(kThreads) trace_rect_kernel(TraceRectArgs a, i
         const int64_t ti = tile / t2, tj = tile - ti * t2;
         const int64_t i0 = ti * kTile, j0 = tj * kTile;
         __syncthreads();
-        stage_tile(Zs1, a.Z1, a.n1 * ndim, a.n1, i0, ndim, n_parts);
-        stage_tile(Zs2, a.Z2, a.n2 * ndim, a.n2, j0, ndim, n_parts);
-        __syncthreads();
+        stage_tiles(sm, a.Z1, a.Z2, a.zd1, a.zd2, i0, j0, npd, bulk, phase);
 
         double wq[4][4];
 #pragma unroll
@@ -651,7 +895,7 @@ __global__ void __launch_bounds__(kThreads) trace_rect_kernel(TraceRectArgs a, i
                 wq[x][y] = w;
             }
         }
-        trace_tile<PTYPE>(S, Zs1, Zs2, ndim, n_parts, t, wq, acc);
+        trace_tile<PTYPE>(S, sm.Zs1, sm.Zs2, sm.tab, ndim, n_parts, t, wq, acc);
     }
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -694,19 +938,23 @@ static int launch_trace_rect_t(pgp_ctx* ctx, const TraceRectArgs& a, size_t smem
                                int grid) {
     auto kern = trace_rect_kernel<PTYPE>;
     PGP_TRY(ensure_dyn_smem(ctx, kern, smem));
+    const int bulk = bulk_ok(a.Z1, a.zd1) && bulk_ok(a.Z2, a.zd2);
     Launch L(ctx, PC_TRACE, (a.mode == 0 ? 8.0 : 16.0) * (double)a.n1 * (double)a.n2);
-    kern<<<grid, kThreads, smem, ctx->stream>>>(a, t2, n_tiles);
+    kern<<<grid, kThreads, smem, ctx->stream>>>(a, t2, n_tiles, bulk);
     return check_launch(ctx, "trace_rect_kernel");
 }
 
-int launch_trace_rect(pgp_ctx* ctx, const TraceRectArgs& a) {
-    if (a.n1 <= 0 || a.n2 <= 0) return 0;
+int launch_trace_rect(pgp_ctx* ctx, const TraceRectArgs& a0) {
+    if (a0.n1 <= 0 || a0.n2 <= 0) return 0;
+    TraceRectArgs a = a0;
+    if (!a.zd1) a.zd1 = z_stride(a.n1);
+    if (!a.zd2) a.zd2 = z_stride(a.n2);
     if (a.n_parts * a.ndim > 192)
         return ctx->fail(PGP_E_ARG, "trace: n_parts * ndim > 192 exceeds the shared-memory tile");
     int64_t t2 = ceil_div(a.n2, kTile);
     int64_t n_tiles = ceil_div(a.n1, kTile) * t2;
     int grid = (int)trace_rect_cta_count(a.n1, a.n2);
-    size_t smem = ((sizeof(DevSpecHdr) + 15) / 16) * 16 + 2ull * a.n_parts * a.ndim * kTile * sizeof(double) +
+    size_t smem = kSmemFixed + 2ull * a.n_parts * a.ndim * kTile * sizeof(double) +
                   8ull * (a.nhyper + 1) * sizeof(double);
     int st = a.n_parts == 1 ? a.single_type : -1;
     int rc;
@@ -762,18 +1010,21 @@ template <int PTYPE>
 static int launch_trace_t(pgp_ctx* ctx, const TraceArgs& a, size_t smem, int64_t n_tiles, int grid) {
     auto kern = trace_kernel<PTYPE>;
     PGP_TRY(ensure_dyn_smem(ctx, kern, smem));
+    const int bulk = bulk_ok(a.Z, a.zd);
     Launch L(ctx, PC_TRACE, 4.0 * (double)a.n * (double)a.n);
-    kern<<<grid, kThreads, smem, ctx->stream>>>(a, n_tiles);
+    kern<<<grid, kThreads, smem, ctx->stream>>>(a, n_tiles, bulk);
     return check_launch(ctx, "trace_kernel");
 }
 
-int launch_trace(pgp_ctx* ctx, const TraceArgs& a) {
+int launch_trace(pgp_ctx* ctx, const TraceArgs& a0) {
+    TraceArgs a = a0;
+    if (!a.zd) a.zd = z_stride(a.n);
     if (a.n_parts * a.ndim > 192)
         return ctx->fail(PGP_E_ARG, "trace: n_parts * ndim > 192 exceeds the shared-memory tile");
     int64_t t = ceil_div(a.n, kTile);
     int64_t n_tiles = t * (t + 1) / 2;
     int grid = (int)trace_cta_count(a.n);
-    size_t smem = ((sizeof(DevSpecHdr) + 15) / 16) * 16 + 2ull * a.n_parts * a.ndim * kTile * sizeof(double) +
+    size_t smem = kSmemFixed + 2ull * a.n_parts * a.ndim * kTile * sizeof(double) +
                   8ull * (a.nhyper + 1) * sizeof(double);
     int st = a.n_parts == 1 ? a.single_type : -1;
     int rc;
@@ -793,6 +1044,30 @@ int launch_trace(pgp_ctx* ctx, const TraceArgs& a) {
                                                                   a.n, a.dlZ);
     }
     return check_launch(ctx, "trace_finish_kernel");
+}
+
+// ---------------------------------------------------------------------------
+// accuracy sweep of fastmath.cuh (pgp_dev_fastmath)
+// ---------------------------------------------------------------------------
+__global__ void fastmath_kernel(int which, const double* x, int64_t n, double* out) {
+    __shared__ double tab[fm::kExpTabDoubles];
+    fm::load_exp_tab(tab, threadIdx.x, blockDim.x);
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        int bad = 0;
+        double r;
+        if (which == 0) { r = fm::exp_tab(x[i], tab, bad); if (bad) r = exp(x[i]); }
+        else if (which == 1) r = fm::sqrt_pos(x[i]);
+        else r = fm::exp_tab_clamped(x[i], tab);
+        out[i] = r;
+    }
+}
+
+int launch_fastmath(pgp_ctx* ctx, int which, const double* d_x, int64_t n, double* d_out) {
+    if (n <= 0) return 0;
+    Launch L(ctx, PC_OTHER, 16.0 * n);
+    fastmath_kernel<<<(unsigned)std::min<int64_t>(ceil_div(n, 256), 1184), 256, 0, ctx->stream>>>(which, d_x, n, d_out);
+    return check_launch(ctx, "fastmath_kernel");
 }
 
 // ---------------------------------------------------------------------------

@@ -7,18 +7,24 @@ namespace pgp {
 
 constexpr int kTile = 64;  // covariance tile edge (entries)
 
-// Z[p][i][k] = X[i][k] / ell[p][k]   (pygp/kernels/_distances.py:17-23)
-// batch > 1: spec[b], Z[b][...] with X shared.
+// Scaled inputs are held DIMENSION-MAJOR: Z[b][p][k][i] = X[i][k] / ell[b][p][k] for i < n
+// (pygp/kernels/_distances.py:17-23), zero for n <= i < z_stride(n).  Row k of a tile's 64
+// inputs is then 512 contiguous bytes, which the tile kernels stage with one bulk-copy
+// (cp.async.bulk, the TMA engine) per row instead of 8 strided loads + shared stores per
+// thread; the padding lets every tile read 64 rows without a bound check.
+inline int64_t z_stride(int64_t n) { return round_up(n, kTile) + kTile; }
+inline size_t z_doubles(int n_parts, int ndim, int64_t n) { return (size_t)n_parts * ndim * z_stride(n); }
+// batch > 1: spec[b], Z[b][...] (batch stride z_doubles) with X shared.
 int launch_scale(pgp_ctx* ctx, const DevSpec* d_spec, const double* d_X, int64_t n, int ndim,
                  int n_parts, double* d_Z, int batch);
 
 struct GramArgs {
     const DevSpec* spec = nullptr;   // device, [batch]
-    const double* Z1 = nullptr;      // [batch][parts][n1][d]
-    const double* Z2 = nullptr;      // [batch][parts][n2][d] (may alias Z1)
+    const double* Z1 = nullptr;      // [batch][parts][d][zd1]
+    const double* Z2 = nullptr;      // [batch][parts][d][zd2] (may alias Z1)
     int64_t n1 = 0, n2 = 0;
-    int64_t zs1 = 0, zs2 = 0;        // doubles between the leaves' copies (0: n1 * ndim / n2 * ndim);
-                                     // lets Z1 / Z2 be a row window of a larger scaled array
+    int64_t zd1 = 0, zd2 = 0;        // doubles between consecutive dimensions (0: z_stride(n1) / z_stride(n2));
+                                     // Z1 + r0 with the parent's stride is a row window of a larger array
     int ndim = 0, n_parts = 0;
     double* out = nullptr;           // [batch] (n1, ldo)
     int64_t ldo = 0;
@@ -37,8 +43,9 @@ int launch_gram(pgp_ctx* ctx, const GramArgs& a);
 
 struct TraceArgs {
     const DevSpec* spec = nullptr;
-    const double* Z = nullptr;       // [parts][n][d]
+    const double* Z = nullptr;       // [parts][d][z_stride(n)]
     int64_t n = 0;
+    int64_t zd = 0;                  // 0: z_stride(n)
     int ndim = 0, n_parts = 0, nhyper = 0;
     const double* P = nullptr;       // lower triangle of K~^-1, (n, ldp)
     int64_t ldp = 0;
@@ -56,9 +63,10 @@ int launch_trace(pgp_ctx* ctx, const TraceArgs& a);
 // rectangular block; W dense (mode 0) or FITC's Cxu built on the fly (mode 1).
 struct TraceRectArgs {
     const DevSpec* spec = nullptr;
-    const double* Z1 = nullptr;      // [parts][n1][d]
-    const double* Z2 = nullptr;      // [parts][n2][d]
+    const double* Z1 = nullptr;      // [parts][d][z_stride(n1)]
+    const double* Z2 = nullptr;      // [parts][d][z_stride(n2)]
     int64_t n1 = 0, n2 = 0;
+    int64_t zd1 = 0, zd2 = 0;        // 0: z_stride(n1) / z_stride(n2)
     int ndim = 0, n_parts = 0, nhyper = 0;
     int mode = 0;
     int sym = 0;                     // mode 0, n1 == n2, X1 == X2: Wd holds the lower triangle of a symmetric W
@@ -79,5 +87,8 @@ int launch_trace_rect(pgp_ctx* ctx, const TraceRectArgs& a);
 
 // out[h][i] = d k(x_i, x_i) / d hyper_h for h < nhyper (hmode=1) or k(x_i,x_i) (hmode=0)
 int launch_diag(pgp_ctx* ctx, const DevSpec* d_spec, int64_t n, int hmode, int nhyper, double* d_out);
+
+// elementwise fastmath.cuh functions on device arrays (accuracy tests)
+int launch_fastmath(pgp_ctx* ctx, int which, const double* d_x, int64_t n, double* d_out);
 
 }  // namespace pgp

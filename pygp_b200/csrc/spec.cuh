@@ -43,6 +43,8 @@ struct DevSpecHdr {
     int node_child0[kMaxNodes];  // offset into child[]
     int child[kMaxNodes];
     int leaf_node[kMaxParts];    // node id of each leaf
+    int depth2;                  // 1: every child of the root is a leaf or an op over leaves only
+    int pad_;
     double sn2;                  // noise variance (GP paths), 0 for bare kernels
     double mean;
 };
@@ -144,6 +146,19 @@ inline int compile_spec(const pgp_kernel_spec* s, const double* hyp, double sn2,
     }
     if (sp_ != 1) { *err = "postfix program does not reduce to one kernel"; return PGP_E_ARG; }
     h.n_nodes = nn;
+    // trees of depth <= 2 (a sum of leaves and products of leaves, or the dual) take the vectorised
+    // composite path of the Gram kernel; anything deeper goes through the per-entry interpreter
+    h.depth2 = 1;
+    if (h.node_kind[nn - 1] != NK_LEAF) {
+        const int* rc = h.child + h.node_child0[nn - 1];
+        for (int c = 0; c < h.node_nchild[nn - 1]; ++c) {
+            const int cn = rc[c];
+            if (h.node_kind[cn] == NK_LEAF) continue;
+            const int* gc = h.child + h.node_child0[cn];
+            for (int g = 0; g < h.node_nchild[cn]; ++g)
+                if (h.node_kind[gc[g]] != NK_LEAF) h.depth2 = 0;
+        }
+    }
     return 0;
 }
 
