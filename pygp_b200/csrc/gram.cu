@@ -72,11 +72,14 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// try_wait with a suspend-time hint: a waiting warp sleeps in hardware instead of spinning -- the first
+// version (no hint) re-issued the test ~85 times per warp and tile, 9 % of all executed instructions
+// (ncu source view, profiles/r02c_gram_m5_ncu.txt), stealing issue slots from the warps doing FP64 work
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
     uint32_t ok;
     do {
-        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(phase) : "memory");
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(phase), "r"(0x989680u) : "memory");
     } while (!ok);
 }
 __device__ __forceinline__ void bulk_g2s(void* sdst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
@@ -85,40 +88,59 @@ __device__ __forceinline__ void bulk_g2s(void* sdst, const void* gsrc, uint32_t 
                  : "memory");
 }
 
-// once per kernel, before the first stage_tiles: header, exp table, mbarrier
-__device__ __forceinline__ void smem_init(const Smem& sm, const DevSpec* spec, bool bulk) {
-    const int nwords = sizeof(DevSpecHdr) / 4;
-    const int* s = reinterpret_cast<const int*>(&spec->h);
-    int* d = reinterpret_cast<int*>(sm.S);
-    for (int i = threadIdx.x; i < nwords; i += kThreads) d[i] = s[i];
-    fm::load_exp_tab(sm.tab, threadIdx.x, kThreads);
-    if (bulk && threadIdx.x == 0) mbar_init(sm.bar, 1);
-    __syncthreads();
-}
-
-// Stage rows [i0, i0 + 64) of Z1 and [j0, j0 + 64) of Z2 for every (leaf, dim) pair pk:
-// Zs[pk][r] = Z[pk * zd + r0 + r].  Rows past n are the zero padding (or, for a row window,
-// rows of the parent array): always readable, never stored.  Returns with the tile visible
-// to every thread.  In a loop the caller puts a __syncthreads() before the next call.
-__device__ __forceinline__ void stage_tiles(const Smem& sm, const double* Z1, const double* Z2, int64_t zd1, int64_t zd2,
-                                            int64_t i0, int64_t j0, int npd, bool bulk, uint32_t& phase) {
+// Staging of one tile pair is split in two so that the copies are in flight while the CTA sets up:
+//   stage_issue  rows [i0, i0 + 64) of Z1 and [j0, j0 + 64) of Z2 for every (leaf, dim) pair pk,
+//                Zs[pk][r] = Z[pk * zd + r0 + r]; bulk: warp 0 arms the mbarrier and issues one
+//                512-byte bulk copy per row (rows past n are the zero padding, or rows of the
+//                parent array for a row window: always readable, never stored)
+//   stage_wait   returns with the tile visible to every thread
+// In a loop the caller puts a __syncthreads() between the last read of a tile and the next issue.
+__device__ __forceinline__ void stage_issue(const Smem& sm, const double* Z1, const double* Z2, int64_t zd1, int64_t zd2,
+                                            int64_t i0, int64_t j0, int npd, bool bulk) {
     if (bulk) {
-        if (threadIdx.x == 0) mbar_expect_tx(sm.bar, (uint32_t)(2 * npd * kTile * sizeof(double)));
-        for (int idx = threadIdx.x; idx < 2 * npd; idx += kThreads) {
-            const int which = idx >= npd, pk = which ? idx - npd : idx;
-            bulk_g2s((which ? sm.Zs2 : sm.Zs1) + pk * kTile, which ? Z2 + pk * zd2 + j0 : Z1 + pk * zd1 + i0,
-                     kTile * sizeof(double), sm.bar);
+        if (threadIdx.x < 32) {
+            if (threadIdx.x == 0) mbar_expect_tx(sm.bar, (uint32_t)(2 * npd * kTile * sizeof(double)));
+            __syncwarp();
+            for (int idx = threadIdx.x; idx < 2 * npd; idx += 32) {
+                const int which = idx >= npd, pk = which ? idx - npd : idx;
+                bulk_g2s((which ? sm.Zs2 : sm.Zs1) + pk * kTile, which ? Z2 + pk * zd2 + j0 : Z1 + pk * zd1 + i0,
+                         kTile * sizeof(double), sm.bar);
+            }
         }
-        mbar_wait(sm.bar, phase);
-        phase ^= 1;
     } else {
         for (int idx = threadIdx.x; idx < npd * kTile; idx += kThreads) {
             const int pk = idx >> 6, r = idx & 63;
             sm.Zs1[idx] = Z1[pk * zd1 + i0 + r];
             sm.Zs2[idx] = Z2[pk * zd2 + j0 + r];
         }
+    }
+}
+
+__device__ __forceinline__ void stage_wait(const Smem& sm, bool bulk, uint32_t& phase) {
+    if (bulk) {
+        mbar_wait(sm.bar, phase);
+        phase ^= 1;
+    } else {
         __syncthreads();
     }
+}
+
+// Once per kernel: mbarrier, first tile's copies, then -- while they fly -- the exp table and (composite
+// kernels only: the tree interpreter indexes it at random) the spec header.  Single-leaf kernels read the
+// two scalars they need straight from the global spec instead of copying 800 bytes per CTA.
+template <bool HDR>
+__device__ __forceinline__ void smem_init_and_issue(const Smem& sm, const DevSpec* spec, const double* Z1, const double* Z2,
+                                                    int64_t zd1, int64_t zd2, int64_t i0, int64_t j0, int npd, bool bulk) {
+    if (bulk && threadIdx.x == 0) mbar_init(sm.bar, 1);      // init + fence by the thread that arms it
+    stage_issue(sm, Z1, Z2, zd1, zd2, i0, j0, npd, bulk);
+    if (HDR) {
+        const int nwords = sizeof(DevSpecHdr) / 4;
+        const int* s = reinterpret_cast<const int*>(&spec->h);
+        int* d = reinterpret_cast<int*>(sm.S);
+        for (int i = threadIdx.x; i < nwords; i += kThreads) d[i] = s[i];
+    }
+    fm::load_exp_tab(sm.tab, threadIdx.x, kThreads);
+    __syncthreads();                                          // table / header / mbarrier init visible to all
 }
 
 // bulk copies need 16-byte aligned sources: base pointers and every (leaf, dim) row
@@ -475,7 +497,6 @@ __global__ void __launch_bounds__(kThreads, (MODE == 0 && is_fast_type(PTYPE)) ?
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int ndim = a.ndim, n_parts = a.n_parts, npd = n_parts * ndim;
     const Smem sm(smem_raw, npd);
-    const DevSpecHdr* S = sm.S;
 
     const bool tri_grid = a.lower_only || a.symmetric;
     const int b = tri_grid ? blockIdx.y : blockIdx.z;
@@ -484,15 +505,19 @@ __global__ void __launch_bounds__(kThreads, (MODE == 0 && is_fast_type(PTYPE)) ?
     else { ti = blockIdx.y; tj = blockIdx.x; }
     const int64_t i0 = (int64_t)ti * kTile, j0 = (int64_t)tj * kTile;
 
-    smem_init(sm, a.spec + b, a.bulk);
+    // composites keep the header in shared memory; a single leaf reads its scalars from the global spec
+    const DevSpecHdr* S = PTYPE < 0 ? sm.S : &a.spec[b].h;
+    smem_init_and_issue<(PTYPE < 0)>(sm, a.spec + b, a.Z1 + (int64_t)b * npd * a.zd1, a.Z2 + (int64_t)b * npd * a.zd2,
+                                   a.zd1, a.zd2, i0, j0, npd, a.bulk);
     uint32_t phase = 0;
-    stage_tiles(sm, a.Z1 + (int64_t)b * npd * a.zd1, a.Z2 + (int64_t)b * npd * a.zd2, a.zd1, a.zd2, i0, j0, npd, a.bulk, phase);
 
     Tile t;
     double* out = a.out + (int64_t)b * a.out_bstride;
     int gpart = 0, gkind = 0, gdim = 0;
     if (GRAD1) classify_hyper(*S, a.hidx, &gpart, &gkind, &gdim);
     const double noise = a.add_noise ? S->sn2 : 0.0;
+    const double two_logsf = S->parts[0].two_logsf;
+    stage_wait(sm, a.bulk, phase);
     const bool diag_noise = a.add_noise && i0 == j0;     // tile-uniform: off the diagonal tiles nothing is added
     const int xdim = a.xdim;
     const bool vec_ok = a.ostride == 1 && ((a.ldo & 1) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
@@ -511,7 +536,7 @@ __global__ void __launch_bounds__(kThreads, (MODE == 0 && is_fast_type(PTYPE)) ?
 #pragma unroll
             for (int y = 0; y < 4; ++y) {
                 if (FAST) {
-                    v[y] = fast_value<PTYPE>(part.two_logsf, D[x][y], sm.tab, bad);
+                    v[y] = fast_value<PTYPE>(two_logsf, D[x][y], sm.tab, bad);
                 } else {
                     PartVal pv;
                     leaf_eval<PTYPE, GRAD1 || GRADX>(part, D[x][y], pv, sm.tab);
@@ -791,8 +816,8 @@ __global__ void __launch_bounds__(kThreads) trace_kernel(TraceArgs a, int64_t n_
     const Smem sm(smem_raw, npd);
     const DevSpecHdr* S = sm.S;
     double* red = sm.extra;  // [8 warps][nhyper + 1]
-    smem_init(sm, a.spec, bulk);
     uint32_t phase = 0;
+    bool first = true;
     Tile t;
 
     double acc[kMaxHyper + 1];
@@ -802,8 +827,14 @@ __global__ void __launch_bounds__(kThreads) trace_kernel(TraceArgs a, int64_t n_
         int ti, tj;
         tri_decode(tile, &ti, &tj);
         const int64_t i0 = (int64_t)ti * kTile, j0 = (int64_t)tj * kTile;
-        __syncthreads();  // previous tile fully consumed
-        stage_tiles(sm, a.Z, a.Z, a.zd, a.zd, i0, j0, npd, bulk, phase);
+        if (first) {
+            smem_init_and_issue<true>(sm, a.spec, a.Z, a.Z, a.zd, a.zd, i0, j0, npd, bulk);
+            first = false;
+        } else {
+            __syncthreads();  // previous tile fully consumed
+            stage_issue(sm, a.Z, a.Z, a.zd, a.zd, i0, j0, npd, bulk);
+        }
+        stage_wait(sm, bulk, phase);
 
         // weights: w Q_ij with w = 2 below the diagonal, 1 on it, 0 above / outside
         double wq[4][4];
@@ -859,8 +890,8 @@ __global__ void __launch_bounds__(kThreads) trace_rect_kernel(TraceRectArgs a, i
     const Smem sm(smem_raw, npd);
     const DevSpecHdr* S = sm.S;
     double* red = sm.extra;  // [8 warps][nhyper + 1]
-    smem_init(sm, a.spec, bulk);
     uint32_t phase = 0;
+    bool first = true;
     Tile t;
 
     double acc[kMaxHyper + 1];
@@ -869,8 +900,14 @@ __global__ void __launch_bounds__(kThreads) trace_rect_kernel(TraceRectArgs a, i
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t ti = tile / t2, tj = tile - ti * t2;
         const int64_t i0 = ti * kTile, j0 = tj * kTile;
-        __syncthreads();
-        stage_tiles(sm, a.Z1, a.Z2, a.zd1, a.zd2, i0, j0, npd, bulk, phase);
+        if (first) {
+            smem_init_and_issue<true>(sm, a.spec, a.Z1, a.Z2, a.zd1, a.zd2, i0, j0, npd, bulk);
+            first = false;
+        } else {
+            __syncthreads();
+            stage_issue(sm, a.Z1, a.Z2, a.zd1, a.zd2, i0, j0, npd, bulk);
+        }
+        stage_wait(sm, bulk, phase);
 
         double wq[4][4];
 #pragma unroll
