@@ -178,6 +178,30 @@ int pgp_exact_get_factor(pgp_model* m, double* R_out, double* a_out);
 int pgp_exact_factor_buffer(pgp_model* m, double** d_F, int64_t* ld);
 int pgp_exact_adopt_factor(pgp_model* m, const double* hyp);
 
+/* ---- multi-GPU: one process per GPU, SURVEY.md 8e (the reference is single-process) ----
+ * Communicator over the ranks of a job: rank 0 calls pgp_dist_unique_id, the host passes the
+ * PGP_DIST_ID_BYTES bytes to every other rank by any channel, then every rank calls
+ * pgp_dist_init with its own context.  NCCL is bound at run time (libnccl.so.2). */
+#define PGP_DIST_ID_BYTES 128
+typedef struct pgp_dist pgp_dist;
+int  pgp_dist_unique_id(pgp_ctx* ctx, void* id_out);
+int  pgp_dist_init(pgp_ctx* ctx, int n_ranks, int rank, const void* id, pgp_dist** out);
+void pgp_dist_destroy(pgp_dist* d);
+int  pgp_dist_rank(const pgp_dist* d);
+int  pgp_dist_size(const pgp_dist* d);
+/* all-reduce of a short host vector (n <= 100) over the ranks; op: 0 sum, 1 max, 2 min */
+int  pgp_dist_allreduce(pgp_dist* d, double* x, int64_t n, int op);
+/* ExactGP._update (exact.py:50-55) on every rank's replica of the same model (same data, same
+ * hyp) as a 1-D block-column distributed Cholesky: block columns of width nb (multiple of 64) are
+ * owned round-robin, each factored panel is broadcast over NVLink, every rank ends with the complete
+ * factor.  Collective: every rank must call it.  Returns the same info > 0 on every rank when the
+ * matrix is not positive definite. */
+int  pgp_dist_exact_update(pgp_dist* d, pgp_model* m, const double* hyp, int64_t nb);
+/* ExactGP.loglikelihood(grad) (exact.py:118-143) with the gradient partitioned by the same block
+ * columns (two triangular solves and a trace per rank, one all-reduce of nhyper + 1 doubles).
+ * Collective when want_grad != 0.  dlZ: (1 + nhyper_k + 1), identical on every rank. */
+int  pgp_dist_exact_loglike(pgp_dist* d, pgp_model* m, int64_t nb, int want_grad, double* lZ, double* dlZ);
+
 /* ---- batched small-N path: learning/sampling.py:146, meta/mcmc.py:75-93 ---- */
 /* B independent ExactGP._update + loglikelihood() sharing X, y.
  * hyps (B, nhyper_gp); lZ (B); info (B) per-problem potrf info (0 = ok). */

@@ -82,6 +82,14 @@ SIGNATURES = {
     'pgp_exact_get_factor': (C.c_int, [_vp, _dp, _dp]),
     'pgp_exact_factor_buffer': (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_i64)]),
     'pgp_exact_adopt_factor': (C.c_int, [_vp, _dp]),
+    'pgp_dist_unique_id': (C.c_int, [_vp, _vp]),
+    'pgp_dist_init': (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.POINTER(_vp)]),
+    'pgp_dist_destroy': (None, [_vp]),
+    'pgp_dist_rank': (C.c_int, [_vp]),
+    'pgp_dist_size': (C.c_int, [_vp]),
+    'pgp_dist_allreduce': (C.c_int, [_vp, _dp, _i64, C.c_int]),
+    'pgp_dist_exact_update': (C.c_int, [_vp, _vp, _dp, _i64]),
+    'pgp_dist_exact_loglike': (C.c_int, [_vp, _vp, _i64, C.c_int, _dp, _dp]),
     'pgp_batched_loglike': (C.c_int, [_vp, _sp, _dp, _dp, _i64, _dp, _i64, _dp, _ip]),
     'pgp_batched_predict': (C.c_int, [_vp, _sp, _dp, _dp, _i64, _dp, _i64, _dp, _i64, _dp, _dp, _ip]),
     'pgp_fitc_create': (C.c_int, [_vp, _sp, _dp, _i64, _dp, _dp, _i64, C.POINTER(_vp)]),

@@ -434,7 +434,56 @@ int trsm_nt_rec(pgp_ctx* ctx, const Mat& B, int64_t rows, const Mat& L, int64_t 
     return trsm_nt_rec(ctx, B, rows, L, j0, n1);
 }
 
+// staircase variants (chol.cuh: Stair): same recursions, row count taken from the column range
+int trsm_rec_stair(pgp_ctx* ctx, const Mat& B, const Mat& L, int64_t j0, int64_t n, const Stair& st) {
+    if (n <= kNB) {
+        const int64_t rows = st.rows(j0 + n);
+        return rows > 0 ? launch_trsm_base<false>(ctx, B, rows, L, j0, (int)n) : 0;
+    }
+    int64_t n1 = split_point(n), n2 = n - n1, c0 = j0 + n1;
+    PGP_TRY(trsm_rec_stair(ctx, B, L, j0, n1, st));
+    const int64_t rows = st.rows(c0);            // rows with entries in columns [j0, c0)
+    if (rows > 0)
+        PGP_TRY(gemm_update(ctx, B.p + j0, B.ld, 0, L.p + c0 * L.ld + j0, L.ld, 0, B.p + c0, B.ld, 0, rows, n2, n1, -1.0,
+                            1.0, 0, 0, 1));
+    return trsm_rec_stair(ctx, B, L, c0, n2, st);
+}
+
+int trsm_nt_rec_stair(pgp_ctx* ctx, const Mat& B, const Mat& L, int64_t j0, int64_t n, const Stair& st) {
+    if (n <= kNB) {
+        const int64_t rows = st.rows(j0 + n);
+        return rows > 0 ? launch_trsm_base<false, true>(ctx, B, rows, L, j0, (int)n) : 0;
+    }
+    int64_t n1 = split_point(n), n2 = n - n1, c0 = j0 + n1;
+    PGP_TRY(trsm_nt_rec_stair(ctx, B, L, c0, n2, st));
+    const int64_t rows = st.rows(c0);            // rows that need columns [j0, c0)
+    if (rows > 0) {
+        GemmArgs g;
+        g.A = B.p + c0; g.lda = B.ld;                    // X2 (rows, n2)
+        g.B = L.p + c0 * L.ld + j0; g.ldb = L.ld;        // L21 (n2, n1), k = row
+        g.C = B.p + j0; g.ldc = B.ld;                    // B1 (rows, n1)
+        g.M = rows; g.N = n1; g.K = n2;
+        g.alpha = -1.0; g.beta = 1.0;
+        g.transB = 1;
+        g.splitk = 1;
+        PGP_TRY(launch_gemm(ctx, g));
+    }
+    return trsm_nt_rec_stair(ctx, B, L, j0, n1, st);
+}
+
 }  // namespace
+
+int trsm_right_lt_stair(pgp_ctx* ctx, const Mat& B, const Mat& L, int64_t n, const Stair& st) {
+    if (n <= 0 || st.rows_total <= 0) return 0;
+    if (st.nb <= 0 || st.nb % kNB) return ctx->fail(PGP_E_ARG, "staircase solve: block width must be a multiple of 64");
+    return trsm_rec_stair(ctx, B, L, 0, n, st);
+}
+
+int trsm_right_l_stair(pgp_ctx* ctx, const Mat& B, const Mat& L, int64_t n, const Stair& st) {
+    if (n <= 0 || st.rows_total <= 0) return 0;
+    if (st.nb <= 0 || st.nb % kNB) return ctx->fail(PGP_E_ARG, "staircase solve: block width must be a multiple of 64");
+    return trsm_nt_rec_stair(ctx, B, L, 0, n, st);
+}
 
 // ---------------------------------------------------------------------------
 // TRSM for a FEW rows (incremental update: the one new row of pgp_exact_append_inc,

@@ -35,6 +35,31 @@ int trsm_right_lt(pgp_ctx* ctx, const Mat& B, int64_t rows, const Mat& L, int64_
 // B[:, 0:n) <- B L^-1 (no transpose) for `rows` rows of B.
 int trsm_right_l(pgp_ctx* ctx, const Mat& B, int64_t rows, const Mat& L, int64_t n);
 
+// "Staircase" right-solves for the block-column partition of the gradient (dist.cu): the rows of B are
+// `front` full rows followed by this rank's block rows -- block q (nb rows, the last one possibly
+// shorter) belongs to global block column J = rank + q size and only exists at columns >= J nb (zero to
+// the left for the L^-T solve; not needed to the left for the L^-1 solve).  A column range ending at c
+// therefore involves only the first rows(c) = front + nb #{q : (rank + q size) nb < c} rows, and the
+// recursions below shrink every leaf solve and GEMM update to them: the flops are those of the
+// triangular part actually owned, n^3 / (3 size) per solve, not rows x n^2.
+struct Stair {
+    int64_t nb = 0;
+    int rank = 0, size = 1;
+    int64_t front = 0;        // leading rows active at every column
+    int64_t rows_total = 0;   // front + owned rows
+    int64_t rows(int64_t c_end) const {
+        if (c_end <= 0) return front;
+        const int64_t blocks = (c_end + nb - 1) / nb;                       // global blocks starting before c_end
+        const int64_t mine = blocks > rank ? (blocks - rank + size - 1) / size : 0;
+        const int64_t r = front + mine * nb;
+        return r < rows_total ? r : rows_total;
+    }
+};
+// B[:, 0:n) <- B L^-T on the staircase (columns left to right)
+int trsm_right_lt_stair(pgp_ctx* ctx, const Mat& B, const Mat& L, int64_t n, const Stair& st);
+// B[:, 0:n) <- B L^-1 on the staircase (columns right to left)
+int trsm_right_l_stair(pgp_ctx* ctx, const Mat& B, const Mat& L, int64_t n, const Stair& st);
+
 // G (pre-zeroed outside its upper triangle) <- L^-T, upper triangular.  S is
 // scratch of the same shape (its strict upper blocks are overwritten).
 int inv_upper(pgp_ctx* ctx, const Mat& G, const Mat& L, int64_t n, const Mat& S);

@@ -1,0 +1,501 @@
+// dist.cu -- the exact-GP evaluation spread over the GPUs of one node, one process per GPU
+// (N = 65536):
+//
+//   pgp_dist_exact_update   ExactGP._update (pygp/inference/exact.py:50-55) as a 1-D block-column
+//                           (block-cyclic) right-looking Cholesky with one-panel lookahead; the only
+//                           data-path collective is the NCCL broadcast of each factored panel over
+//                           NVLink, which doubles as the all-gather: every rank ends with the full L.
+//   pgp_dist_exact_loglike  ExactGP.loglikelihood(True) (exact.py:118-143) partitioned by the same
+//                           block columns, with NO communication but one all-reduce of nhyper + 1
+//                           doubles: column block J of K~^-1 is  L^-T (L^-1 E_J), two triangular
+//                           solves that only involve the trailing triangle L[J nb:, J nb:], and the
+//                           trace sum(Q o dK_h) over the entries (i >= c, c in J) is accumulated by
+//                           the rank that owns J.  Per rank: 2 N^3 / (3 G) flops and an (N / G, N)
+//                           buffer instead of two (N, N) ones.
+//
+// The whole schedule is enqueued from C++ on two streams (compute + communication) with events; the
+// host never waits inside the loop (round 1 paced it from Python: one ctypes call and one
+// torch.distributed.broadcast per panel).  pygp_b200/distchol.py keeps the schedule's numpy model for
+// the CPU (gloo) tests and is no longer on the product path.
+//
+// NCCL is bound at run time (dlopen of libnccl.so.2: the copy torch already loaded in this process,
+// else the system one), so libpygp_b200.so has no link-time dependency on it and single-GPU users
+// never touch it.  The communicator is bootstrapped the usual way: rank 0 calls pgp_dist_unique_id,
+// the host passes the 128 bytes to the other ranks (any channel), every rank calls pgp_dist_init.
+
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cmath>
+#include <new>
+
+#include "model.cuh"
+
+using namespace pgp;
+
+namespace {
+
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    ncclResult_t (*GetVersion)(int*) = nullptr;
+};
+
+NcclApi g_nccl;
+std::mutex g_nccl_mu;
+
+int load_nccl(std::string* err) {
+    std::lock_guard<std::mutex> lock(g_nccl_mu);
+    if (g_nccl.handle) return 0;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);     // already in the process (torch)?
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) {
+        *err = std::string("cannot load libnccl.so.2: ") + dlerror();
+        return PGP_E_STATE;
+    }
+    NcclApi a;
+    a.handle = h;
+#define PGP_SYM(field, name)                                                     \
+    *reinterpret_cast<void**>(&a.field) = dlsym(h, name);                        \
+    if (!a.field) { *err = std::string("libnccl lacks ") + name; return PGP_E_STATE; }
+    PGP_SYM(GetUniqueId, "ncclGetUniqueId")
+    PGP_SYM(CommInitRank, "ncclCommInitRank")
+    PGP_SYM(CommDestroy, "ncclCommDestroy")
+    PGP_SYM(Broadcast, "ncclBroadcast")
+    PGP_SYM(AllReduce, "ncclAllReduce")
+    PGP_SYM(GetErrorString, "ncclGetErrorString")
+    PGP_SYM(GetVersion, "ncclGetVersion")
+#undef PGP_SYM
+    g_nccl = a;
+    return 0;
+}
+
+}  // namespace
+
+struct pgp_dist {
+    pgp_ctx* ctx = nullptr;
+    int rank = 0, size = 1;
+    ncclComm_t comm = nullptr;
+    cudaStream_t comm_stream = nullptr;
+    std::vector<cudaEvent_t> events;        // 3 per panel: packed, broadcast done, unpacked
+    double* stage[2] = {nullptr, nullptr};  // contiguous send / receive buffers of one panel
+    size_t stage_doubles = 0;
+    int* d_info = nullptr;                  // per-panel potrf info
+    int64_t info_cap = 0;
+    double* d_B = nullptr;                  // gradient: (1 + owned rows, ld)
+    size_t b_doubles = 0;
+    double* d_part = nullptr;
+    size_t part_doubles = 0;
+    double* d_sums = nullptr;               // kMaxHyper + 4
+};
+
+#define PGP_NCCL(d, call)                                                                      \
+    do {                                                                                       \
+        ncclResult_t r__ = (call);                                                             \
+        if (r__ != ncclSuccess) {                                                              \
+            (d)->ctx->err = std::string("NCCL error in " #call ": ") + g_nccl.GetErrorString(r__); \
+            return PGP_E_CUDA;                                                                 \
+        }                                                                                      \
+    } while (0)
+
+// ---------------------------------------------------------------------------
+// communicator
+// ---------------------------------------------------------------------------
+extern "C" int pgp_dist_unique_id(pgp_ctx* ctx, void* id_out) {
+    if (!ctx) return PGP_E_ARG;
+    if (!id_out) return ctx->fail(PGP_E_ARG, "null id buffer");
+    PGP_TRY(load_nccl(&ctx->err));
+    ncclUniqueId id;
+    ncclResult_t r = g_nccl.GetUniqueId(&id);
+    if (r != ncclSuccess) return ctx->fail(PGP_E_CUDA, std::string("ncclGetUniqueId: ") + g_nccl.GetErrorString(r));
+    static_assert(sizeof(ncclUniqueId) == PGP_DIST_ID_BYTES, "ncclUniqueId size");
+    memcpy(id_out, &id, sizeof id);
+    return 0;
+}
+
+extern "C" int pgp_dist_init(pgp_ctx* ctx, int n_ranks, int rank, const void* id, pgp_dist** out) {
+    if (!ctx) return PGP_E_ARG;
+    if (!out || n_ranks < 1 || rank < 0 || rank >= n_ranks || (n_ranks > 1 && !id))
+        return ctx->fail(PGP_E_ARG, "pgp_dist_init: bad rank / size / id");
+    *out = nullptr;
+    PGP_CUDA(ctx, cudaSetDevice(ctx->device));
+    pgp_dist* d = new (std::nothrow) pgp_dist();
+    if (!d) return PGP_E_NOMEM;
+    d->ctx = ctx;
+    d->rank = rank;
+    d->size = n_ranks;
+    int rc = 0;
+    if (n_ranks > 1) {
+        rc = load_nccl(&ctx->err);
+        if (!rc) {
+            ncclUniqueId uid;
+            memcpy(&uid, id, sizeof uid);
+            ncclResult_t r = g_nccl.CommInitRank(&d->comm, n_ranks, uid, rank);
+            if (r != ncclSuccess) rc = ctx->fail(PGP_E_CUDA, std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r));
+        }
+        if (!rc) {
+            int lo = 0, hi = 0;
+            cudaDeviceGetStreamPriorityRange(&lo, &hi);
+            if (cudaStreamCreateWithPriority(&d->comm_stream, cudaStreamNonBlocking, hi) != cudaSuccess)
+                rc = ctx->fail(PGP_E_CUDA, "cannot create the communication stream");
+        }
+    }
+    if (!rc) rc = dev_alloc(ctx, &d->d_sums, (size_t)kMaxHyper + 4);
+    if (rc) {
+        pgp_dist_destroy(d);
+        return rc;
+    }
+    *out = d;
+    return 0;
+}
+
+extern "C" void pgp_dist_destroy(pgp_dist* d) {
+    if (!d) return;
+    pgp_ctx* ctx = d->ctx;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (d->comm_stream) cudaStreamSynchronize(d->comm_stream);
+    if (d->comm) g_nccl.CommDestroy(d->comm);
+    if (d->comm_stream) cudaStreamDestroy(d->comm_stream);
+    for (cudaEvent_t e : d->events) cudaEventDestroy(e);
+    dev_free(ctx, d->stage[0]);
+    dev_free(ctx, d->stage[1]);
+    dev_free(ctx, d->d_info);
+    dev_free(ctx, d->d_B);
+    dev_free(ctx, d->d_part);
+    dev_free(ctx, d->d_sums);
+    delete d;
+}
+
+extern "C" int pgp_dist_rank(const pgp_dist* d) { return d ? d->rank : -1; }
+extern "C" int pgp_dist_size(const pgp_dist* d) { return d ? d->size : 0; }
+
+// sum / max / min of a short host vector over the ranks (op: 0 sum, 1 max, 2 min); utility for the
+// host (timing reductions, agreement on error codes) on the library's own communicator
+extern "C" int pgp_dist_allreduce(pgp_dist* d, double* x, int64_t n, int op) {
+    if (!d) return PGP_E_ARG;
+    pgp_ctx* ctx = d->ctx;
+    if (!x || n < 0 || n > kMaxHyper + 4 || op < 0 || op > 2) return ctx->fail(PGP_E_ARG, "pgp_dist_allreduce: bad argument");
+    if (d->size == 1 || n == 0) return 0;
+    PGP_CUDA(ctx, cudaSetDevice(ctx->device));
+    PGP_CUDA(ctx, cudaMemcpyAsync(d->d_sums, x, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+    PGP_NCCL(d, g_nccl.AllReduce(d->d_sums, d->d_sums, (size_t)n, ncclDouble, op == 0 ? ncclSum : op == 1 ? ncclMax : ncclMin,
+                                d->comm, ctx->stream));
+    PGP_CUDA(ctx, cudaMemcpyAsync(x, d->d_sums, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    PGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// distributed factorisation
+// ---------------------------------------------------------------------------
+namespace {
+
+struct Cols {
+    int64_t n, nb, nblk;
+    int64_t j0(int64_t k) const { return k * nb; }
+    int64_t w(int64_t k) const { return std::min(nb, n - k * nb); }
+};
+
+int ensure_events(pgp_dist* d, size_t count) {
+    while (d->events.size() < count) {
+        cudaEvent_t e;
+        PGP_CUDA(d->ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        d->events.push_back(e);
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int pgp_dist_exact_update(pgp_dist* d, pgp_model* m, const double* hyp, int64_t nb) {
+    if (!d || !m) return PGP_E_ARG;
+    pgp_ctx* ctx = m->ctx;
+    if (ctx != d->ctx) return ctx->fail(PGP_E_ARG, "model and communicator live on different contexts");
+    if (!hyp) return ctx->fail(PGP_E_ARG, "null hyper vector");
+    if (nb < 64 || nb % 64) return ctx->fail(PGP_E_ARG, "block width must be a positive multiple of 64");
+    PGP_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int nk = m->spec.nhyper;
+    const double sn2 = std::exp(hyp[0] * 2), mean = hyp[1 + nk];
+    PGP_TRY(compile_spec(&m->spec, hyp + 1, sn2, mean, &m->hspec, &ctx->err));
+    m->factored = false;
+    cudaStream_t S = ctx->stream, C = d->comm_stream;
+    const int64_t n = m->n, ld = m->ld;
+    const int rank = d->rank, size = d->size;
+    Cols cols{n, nb, ceil_div(n, nb)};
+    const int64_t nblk = cols.nblk;
+
+    // workspaces: one info slot per panel, two panel staging buffers, 3 events per panel
+    if (d->info_cap < nblk) {
+        PGP_CUDA(ctx, cudaStreamSynchronize(S));
+        dev_free(ctx, d->d_info);
+        d->d_info = nullptr;
+        PGP_TRY(dev_alloc(ctx, &d->d_info, (size_t)nblk));
+        d->info_cap = nblk;
+    }
+    const size_t need_stage = size > 1 ? (size_t)(n + 1) * nb : 0;
+    if (d->stage_doubles < need_stage) {
+        PGP_CUDA(ctx, cudaStreamSynchronize(S));
+        for (int i = 0; i < 2; ++i) {
+            dev_free(ctx, d->stage[i]);
+            d->stage[i] = nullptr;
+            PGP_TRY(dev_alloc(ctx, &d->stage[i], need_stage));
+        }
+        d->stage_doubles = need_stage;
+    }
+    PGP_TRY(ensure_events(d, (size_t)3 * nblk + 2));
+    auto ev_packed = [&](int64_t k) { return d->events[3 * k]; };
+    auto ev_bcast = [&](int64_t k) { return d->events[3 * k + 1]; };
+    auto ev_unpacked = [&](int64_t k) { return d->events[3 * k + 2]; };
+
+    PGP_CUDA(ctx, cudaMemcpyAsync(m->d_spec, &m->hspec, sizeof(DevSpec), cudaMemcpyHostToDevice, S));
+    PGP_CUDA(ctx, cudaMemsetAsync(d->d_info, 0, sizeof(int) * nblk, S));
+    PGP_TRY(launch_scale(ctx, m->d_spec, m->d_X, n, m->ndim, m->spec.n_parts, m->d_Z, 1));
+    Mat F;
+    F.p = m->d_F;
+    F.ld = ld;
+    PGP_TRY(launch_set_residual(ctx, F, n, m->d_y, m->d_spec));            // row n = y - mean, all columns
+
+    // owned block columns of K + sn2 I, built in place: rows [j0, n) x columns [j0, j0 + w)
+    const int st = single_type_of(&m->spec);
+    const int64_t zd = z_stride(n);
+    for (int64_t j = rank; j < nblk; j += size) {
+        const int64_t j0 = cols.j0(j), w = cols.w(j);
+        GramArgs g;
+        g.spec = m->d_spec;
+        g.Z1 = m->d_Z + j0; g.zd1 = zd; g.n1 = n - j0;
+        g.Z2 = m->d_Z + j0; g.zd2 = zd; g.n2 = w;
+        g.ndim = m->ndim; g.n_parts = m->spec.n_parts;
+        g.out = m->d_F + j0 * ld + j0; g.ldo = ld;
+        g.add_noise = 1;                                   // both windows start at j0: local diagonal == global diagonal
+        g.single_type = st;
+        PGP_TRY(launch_gram(ctx, g));
+    }
+    std::vector<int64_t> applied((size_t)nblk, 0);         // panels [0, applied[j]) are applied to owned panel j
+
+    // owned panel j -= F[j0:, c_lo:c_hi) F[j0:j0+w, c_lo:c_hi)^T   (rows j0 .. n, the residual row included)
+    auto catch_up = [&](int64_t j, int64_t upto) -> int {
+        if (applied[j] >= upto) return 0;
+        const int64_t j0 = cols.j0(j), w = cols.w(j);
+        const int64_t c_lo = cols.j0(applied[j]), c_hi = cols.j0(upto - 1) + cols.w(upto - 1);
+        GemmArgs g;
+        g.A = m->d_F + j0 * ld + c_lo; g.lda = ld;
+        g.B = m->d_F + j0 * ld + c_lo; g.ldb = ld;
+        g.C = m->d_F + j0 * ld + j0; g.ldc = ld;
+        g.M = n - j0 + 1; g.N = w; g.K = c_hi - c_lo;
+        g.alpha = -1.0; g.beta = 1.0;
+        g.tri = 1;                                          // the block above the panel's diagonal is scratch
+        applied[j] = upto;
+        return launch_gemm_nt(ctx, g);
+    };
+
+    // owner: factor panel k (potrf of its top w x w block, right-solve of the rows below, residual row
+    // included), pack it and start its broadcast; everybody: post the matching broadcast
+    auto produce = [&](int64_t k) -> int {
+        const int64_t j0 = cols.j0(k), w = cols.w(k), rows = n - j0 + 1;
+        const int owner = (int)(k % size);
+        if (owner == rank) {
+            Mat P;
+            P.p = m->d_F + j0 * ld + j0;
+            P.ld = ld;
+            PGP_TRY(potrf_lower(ctx, P, w, rows - w, d->d_info + k));
+        }
+        if (size == 1) return 0;
+        double* buf = d->stage[k & 1];
+        if (owner == rank) {
+            if (k >= 2) PGP_CUDA(ctx, cudaStreamWaitEvent(S, ev_bcast(k - 2), 0));      // slot free again
+            PGP_CUDA(ctx, cudaMemcpy2DAsync(buf, w * 8, m->d_F + j0 * ld + j0, ld * 8, w * 8, rows, cudaMemcpyDeviceToDevice, S));
+            PGP_CUDA(ctx, cudaEventRecord(ev_packed(k), S));
+            PGP_CUDA(ctx, cudaStreamWaitEvent(C, ev_packed(k), 0));
+        } else if (k >= 2) {
+            PGP_CUDA(ctx, cudaStreamWaitEvent(C, ev_unpacked(k - 2), 0));                 // receiver: slot consumed
+        }
+        PGP_NCCL(d, g_nccl.Broadcast(buf, buf, (size_t)rows * w, ncclDouble, owner, d->comm, C));
+        PGP_CUDA(ctx, cudaEventRecord(ev_bcast(k), C));
+        return 0;
+    };
+    // everybody: panel k is in the replicated factor before anything reads it
+    auto consume = [&](int64_t k) -> int {
+        if (size == 1) return 0;
+        const int64_t j0 = cols.j0(k), w = cols.w(k), rows = n - j0 + 1;
+        PGP_CUDA(ctx, cudaStreamWaitEvent(S, ev_bcast(k), 0));
+        if ((int)(k % size) != rank) {
+            PGP_CUDA(ctx, cudaMemcpy2DAsync(m->d_F + j0 * ld + j0, ld * 8, d->stage[k & 1], w * 8, w * 8, rows,
+                                            cudaMemcpyDeviceToDevice, S));
+        }
+        PGP_CUDA(ctx, cudaEventRecord(ev_unpacked(k), S));
+        return 0;
+    };
+
+    PGP_TRY(produce(0));
+    for (int64_t k = 0; k < nblk; ++k) {
+        PGP_TRY(consume(k));
+        if (k + 1 < nblk) {
+            if ((int)((k + 1) % size) == rank) PGP_TRY(catch_up(k + 1, k + 1));   // lookahead: next panel first
+            PGP_TRY(produce(k + 1));
+        }
+        for (int64_t j = k + 2; j < nblk; ++j)
+            if ((int)(j % size) == rank) PGP_TRY(catch_up(j, k + 1));
+    }
+
+    // lZ from the complete factor; info: first failing minor over all panels and ranks
+    PGP_TRY(launch_loglik(ctx, F, n, m->d_res));
+    std::vector<int> hinfo((size_t)nblk);
+    double* hp = ctx->h_pin;
+    PGP_CUDA(ctx, cudaMemcpyAsync(hp, m->d_res, sizeof(double), cudaMemcpyDeviceToHost, S));
+    PGP_CUDA(ctx, cudaMemcpyAsync(hinfo.data(), d->d_info, sizeof(int) * nblk, cudaMemcpyDeviceToHost, S));
+    PGP_CUDA(ctx, cudaStreamSynchronize(S));
+    double info = 0.0;                                       // 0 = ok; else the smallest failing order
+    for (int64_t k = 0; k < nblk; ++k)
+        if (hinfo[k] != 0) { info = (double)(cols.j0(k) + hinfo[k]); break; }
+    if (size > 1) {
+        // a failure is only known to the owner of the failing panel (the others received NaNs): agree on it,
+        // so that every rank raises the same LinAlgError and nobody is left waiting in a collective
+        double v = info != 0.0 ? info : 1e300;
+        PGP_TRY(pgp_dist_allreduce(d, &v, 1, 2));
+        info = v >= 1e300 ? 0.0 : v;
+    }
+    m->lZ = hp[0];
+    m->info = (int)info;
+    if (m->info != 0) {
+        char buf[160];
+        snprintf(buf, sizeof buf, "%d-th leading minor of the array is not positive definite", m->info);
+        ctx->err = buf;
+        return m->info;
+    }
+    m->factored = true;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// distributed gradient
+// ---------------------------------------------------------------------------
+namespace {
+
+// B[front + r][c(r)] = 1 for this rank's block rows (B pre-zeroed): rows of the identity, E_J^T
+__global__ void stair_identity_kernel(double* B, int64_t ld, int64_t front, int64_t rows_local, int64_t nb, int rank,
+                                      int size, int64_t n) {
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows_local; r += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t q = r / nb, c = (rank + q * size) * nb + (r - q * nb);
+        if (c < n) B[(front + r) * ld + c] = 1.0;
+    }
+}
+
+// sums[h] = sum over CTAs of partials[cta][h], h <= nh; sums[nh + 1] = sum(alpha)
+__global__ void partial_sums_kernel(const double* partials, int64_t n_cta, int nh, const double* alpha, int64_t n,
+                                    double* sums) {
+    __shared__ double red[256];
+    const int h = blockIdx.x;
+    double v = 0.0;
+    if (h <= nh) {
+        for (int64_t c = threadIdx.x; c < n_cta; c += blockDim.x) v += partials[c * (nh + 1) + h];
+    } else {
+        for (int64_t i = threadIdx.x; i < n; i += blockDim.x) v += alpha[i];
+    }
+    red[threadIdx.x] = v;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) sums[h] = red[0];
+}
+
+}  // namespace
+
+extern "C" int pgp_dist_exact_loglike(pgp_dist* d, pgp_model* m, int64_t nb, int want_grad, double* lZ, double* dlZ) {
+    if (!d || !m) return PGP_E_ARG;
+    pgp_ctx* ctx = m->ctx;
+    if (ctx != d->ctx) return ctx->fail(PGP_E_ARG, "model and communicator live on different contexts");
+    if (!lZ || (want_grad && !dlZ)) return ctx->fail(PGP_E_ARG, "null output");
+    if (!m->factored) return ctx->fail(PGP_E_STATE, "loglike before a successful update");
+    *lZ = m->lZ;
+    if (!want_grad) return 0;
+    if (nb < 64 || nb % 64) return ctx->fail(PGP_E_ARG, "block width must be a positive multiple of 64");
+    PGP_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t S = ctx->stream;
+    const int64_t n = m->n, ld = m->ld;
+    const int nk = m->spec.nhyper, rank = d->rank, size = d->size;
+    const int64_t nblk = ceil_div(n, nb);
+    int64_t rows_local = 0;
+    for (int64_t j = rank; j < nblk; j += size) rows_local += std::min(nb, n - j * nb);
+
+    // B: row 0 = a (becomes alpha), rows 1.. = this rank's rows of the identity
+    const size_t need = (size_t)(rows_local + 1) * ld;
+    if (d->b_doubles < need) {
+        PGP_CUDA(ctx, cudaStreamSynchronize(S));
+        dev_free(ctx, d->d_B);
+        d->d_B = nullptr;
+        d->b_doubles = 0;
+        PGP_TRY(dev_alloc(ctx, &d->d_B, need));
+        d->b_doubles = need;
+    }
+    const int64_t n_cta = trace_dist_cta_count(rows_local, n);
+    const size_t need_part = (size_t)std::max<int64_t>(n_cta, 1) * (kMaxHyper + 1);
+    if (d->part_doubles < need_part) {
+        PGP_CUDA(ctx, cudaStreamSynchronize(S));
+        dev_free(ctx, d->d_part);
+        d->d_part = nullptr;
+        PGP_TRY(dev_alloc(ctx, &d->d_part, need_part));
+        d->part_doubles = need_part;
+    }
+    PGP_CUDA(ctx, cudaMemsetAsync(d->d_B, 0, sizeof(double) * need, S));
+    PGP_CUDA(ctx, cudaMemcpyAsync(d->d_B, m->d_F + n * ld, sizeof(double) * n, cudaMemcpyDeviceToDevice, S));
+    if (rows_local > 0) {
+        Launch L(ctx, PC_OTHER, 8.0 * rows_local);
+        stair_identity_kernel<<<(unsigned)std::min<int64_t>(ceil_div(rows_local, 256), 1184), 256, 0, S>>>(
+            d->d_B, ld, 1, rows_local, nb, rank, size, n);
+        PGP_TRY(check_launch(ctx, "stair_identity_kernel"));
+    }
+    Mat L, B1, B0;
+    L.p = m->d_F; L.ld = ld;
+    B0.p = d->d_B; B0.ld = ld;                 // all rows (alpha row in front)
+    B1.p = d->d_B + ld; B1.ld = ld;            // the identity rows only
+    Stair s1, s0;
+    s1.nb = nb; s1.rank = rank; s1.size = size; s1.front = 0; s1.rows_total = rows_local;
+    s0 = s1; s0.front = 1; s0.rows_total = rows_local + 1;
+    PGP_TRY(trsm_right_lt_stair(ctx, B1, L, n, s1));     // rows J of L^-T:  E_J^T L^-T = (L^-1 E_J)^T
+    PGP_TRY(trsm_right_l_stair(ctx, B0, L, n, s0));      // (.) L^-1: rows J of K~^-1 (columns >= J nb), alpha^T
+    PGP_CUDA(ctx, cudaMemcpyAsync(m->d_alpha, d->d_B, sizeof(double) * n, cudaMemcpyDeviceToDevice, S));
+
+    TraceDistArgs t;
+    t.spec = m->d_spec;
+    t.Z = m->d_Z;
+    t.zd = z_stride(n);
+    t.n = n;
+    t.ndim = m->ndim;
+    t.n_parts = m->spec.n_parts;
+    t.nhyper = nk;
+    t.B = d->d_B + ld;
+    t.ldb = ld;
+    t.rows_local = rows_local;
+    t.nb = nb;
+    t.rank = rank;
+    t.size = size;
+    t.alpha = m->d_alpha;
+    t.partials = d->d_part;
+    t.single_type = single_type_of(&m->spec);
+    PGP_TRY(launch_trace_dist(ctx, t));
+    {
+        Launch Lc(ctx, PC_OTHER, 8.0 * n);
+        partial_sums_kernel<<<nk + 2, 256, 0, S>>>(d->d_part, n_cta, nk, m->d_alpha, n, d->d_sums);
+        PGP_TRY(check_launch(ctx, "partial_sums_kernel"));
+    }
+    if (size > 1)      // the ONE collective of the gradient: nhyper + 1 partial traces
+        PGP_NCCL(d, g_nccl.AllReduce(d->d_sums, d->d_sums, (size_t)nk + 1, ncclDouble, ncclSum, d->comm, S));
+    double* hp = ctx->h_pin;
+    PGP_CUDA(ctx, cudaMemcpyAsync(hp, d->d_sums, sizeof(double) * (nk + 2), cudaMemcpyDeviceToHost, S));
+    PGP_CUDA(ctx, cudaStreamSynchronize(S));
+    // exact.py:131-141: dlZ = [-sn2 tr(Q), -1/2 sum(Q o dK_h)..., sum(alpha)]
+    dlZ[0] = -m->hspec.h.sn2 * hp[0];
+    for (int h = 0; h < nk; ++h) dlZ[1 + h] = -0.5 * hp[1 + h];
+    dlZ[1 + nk] = hp[1 + nk];
+    return 0;
+}

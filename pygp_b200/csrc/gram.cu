@@ -1084,6 +1084,111 @@ int launch_trace(pgp_ctx* ctx, const TraceArgs& a0) {
 }
 
 // ---------------------------------------------------------------------------
+// block-column share of the gradient trace (gram.cuh: TraceDistArgs)
+// ---------------------------------------------------------------------------
+template <int PTYPE>
+__global__ void __launch_bounds__(kThreads) trace_dist_kernel(TraceDistArgs a, int64_t t2, int64_t n_tiles, int bulk) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int ndim = a.ndim, n_parts = a.n_parts, nh = a.nhyper, npd = n_parts * ndim;
+    const Smem sm(smem_raw, npd);
+    const DevSpecHdr* S = sm.S;
+    double* red = sm.extra;  // [8 warps][nhyper + 1]
+    uint32_t phase = 0;
+    bool first = true;
+    Tile t;
+
+    double acc[kMaxHyper + 1];
+    for (int h = 0; h <= nh; ++h) acc[h] = 0.0;
+
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t ti = tile / t2, tj = tile - ti * t2;
+        const int64_t r0 = ti * kTile, q = r0 / a.nb;
+        const int64_t c0 = (a.rank + q * a.size) * a.nb + (r0 - q * a.nb);    // global column of local row r0
+        const int64_t j0 = tj * kTile;
+        if (c0 >= a.n || j0 + kTile - 1 < c0) continue;                       // (CTA-uniform) nothing on / below the diagonal
+        if (first) {
+            smem_init_and_issue<true>(sm, a.spec, a.Z + c0, a.Z + j0, a.zd, a.zd, 0, 0, npd, bulk);
+            first = false;
+        } else {
+            __syncthreads();
+            stage_issue(sm, a.Z + c0, a.Z + j0, a.zd, a.zd, 0, 0, npd, bulk);
+        }
+        stage_wait(sm, bulk, phase);
+
+        // rows of the tile = columns c of K~^-1 (this rank's), columns of the tile = rows i
+        double wq[4][4];
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+            const int64_t r = r0 + t.row(x), c = c0 + t.row(x);
+            const bool rok = r < a.rows_local && c < a.n && (r - q * a.nb) < a.nb;
+            const double ac = rok ? a.alpha[c] : 0.0;
+#pragma unroll
+            for (int y = 0; y < 4; ++y) {
+                const int64_t i = j0 + t.col(y);
+                double w = 0.0;
+                if (rok && i < a.n && i >= c) {
+                    const double qv = a.B[r * a.ldb + i] - ac * a.alpha[i];
+                    w = i == c ? qv : 2.0 * qv;
+                    if (i == c) acc[0] += qv;
+                }
+                wq[x][y] = w;
+            }
+        }
+        trace_tile<PTYPE>(S, sm.Zs1, sm.Zs2, sm.tab, ndim, n_parts, t, wq, acc);
+    }
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    for (int h = 0; h <= nh; ++h) {
+        double v = acc[h];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) red[warp * (nh + 1) + h] = v;
+    }
+    __syncthreads();
+    for (int h = threadIdx.x; h <= nh; h += kThreads) {
+        double v = 0.0;
+        for (int w = 0; w < kThreads / 32; ++w) v += red[w * (nh + 1) + h];
+        a.partials[(int64_t)blockIdx.x * (nh + 1) + h] = v;
+    }
+}
+
+int64_t trace_dist_cta_count(int64_t rows_local, int64_t n) {
+    int64_t tiles = ceil_div(rows_local, kTile) * ceil_div(n, kTile);
+    return std::max<int64_t>(1, std::min<int64_t>(tiles, 148 * kTraceCtasPerSm));
+}
+
+template <int PTYPE>
+static int launch_trace_dist_t(pgp_ctx* ctx, const TraceDistArgs& a, size_t smem, int64_t t2, int64_t n_tiles, int grid) {
+    auto kern = trace_dist_kernel<PTYPE>;
+    PGP_TRY(ensure_dyn_smem(ctx, kern, smem));
+    const int bulk = bulk_ok(a.Z, a.zd);
+    Launch L(ctx, PC_TRACE, 8.0 * (double)a.rows_local * (double)a.n / 2);
+    kern<<<grid, kThreads, smem, ctx->stream>>>(a, t2, n_tiles, bulk);
+    return check_launch(ctx, "trace_dist_kernel");
+}
+
+int launch_trace_dist(pgp_ctx* ctx, const TraceDistArgs& a) {
+    if (a.n_parts * a.ndim > 192)
+        return ctx->fail(PGP_E_ARG, "trace: n_parts * ndim > 192 exceeds the shared-memory tile");
+    if (a.nb <= 0 || a.nb % kTile) return ctx->fail(PGP_E_ARG, "trace: block width must be a multiple of 64");
+    const int64_t t2 = ceil_div(a.n, kTile);
+    const int64_t n_tiles = ceil_div(std::max<int64_t>(a.rows_local, 0), kTile) * t2;
+    const int grid = (int)trace_dist_cta_count(a.rows_local, a.n);
+    size_t smem = kSmemFixed + 2ull * a.n_parts * a.ndim * kTile * sizeof(double) + 8ull * (a.nhyper + 1) * sizeof(double);
+    int st = a.n_parts == 1 ? a.single_type : -1;
+    switch (st) {
+        case PGP_SE: return launch_trace_dist_t<PGP_SE>(ctx, a, smem, t2, n_tiles, grid);
+        case PGP_MATERN1: return launch_trace_dist_t<PGP_MATERN1>(ctx, a, smem, t2, n_tiles, grid);
+        case PGP_MATERN3: return launch_trace_dist_t<PGP_MATERN3>(ctx, a, smem, t2, n_tiles, grid);
+        case PGP_MATERN5: return launch_trace_dist_t<PGP_MATERN5>(ctx, a, smem, t2, n_tiles, grid);
+        case PGP_PERIODIC: return launch_trace_dist_t<PGP_PERIODIC>(ctx, a, smem, t2, n_tiles, grid);
+        case PGP_RQ: return launch_trace_dist_t<PGP_RQ>(ctx, a, smem, t2, n_tiles, grid);
+        default: return launch_trace_dist_t<-1>(ctx, a, smem, t2, n_tiles, grid);
+    }
+}
+
+// ---------------------------------------------------------------------------
 // accuracy sweep of fastmath.cuh (pgp_dev_fastmath)
 // ---------------------------------------------------------------------------
 __global__ void fastmath_kernel(int which, const double* x, int64_t n, double* out) {

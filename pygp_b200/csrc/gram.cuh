@@ -85,6 +85,28 @@ struct TraceRectArgs {
 int64_t trace_rect_cta_count(int64_t n1, int64_t n2);
 int launch_trace_rect(pgp_ctx* ctx, const TraceRectArgs& a);
 
+// Block-column partition of the gradient trace (dist.cu): this rank holds the rows of K~^-1 that belong
+// to its block columns, B[r][i] = K~^-1[i][c(r)] valid for i >= c(r), where local row r = q nb + o is
+// global column c = (rank + q size) nb + o.  partials[cta][0] = sum of Q_cc, [1 + h] = the rank's
+// share of sum_ij Q_ij dK_h,ij (entries i > c counted twice, i == c once), Q = K~^-1 - alpha alpha^T.
+struct TraceDistArgs {
+    const DevSpec* spec = nullptr;
+    const double* Z = nullptr;       // [parts][d][zd], all n rows
+    int64_t zd = 0;
+    int64_t n = 0;
+    int ndim = 0, n_parts = 0, nhyper = 0;
+    const double* B = nullptr;       // (rows_local, ldb)
+    int64_t ldb = 0;
+    int64_t rows_local = 0;
+    int64_t nb = 0;
+    int rank = 0, size = 1;
+    const double* alpha = nullptr;   // (n)
+    double* partials = nullptr;      // [trace_dist_cta_count][nhyper + 1]
+    int single_type = -1;
+};
+int64_t trace_dist_cta_count(int64_t rows_local, int64_t n);
+int launch_trace_dist(pgp_ctx* ctx, const TraceDistArgs& a);
+
 // out[h][i] = d k(x_i, x_i) / d hyper_h for h < nhyper (hmode=1) or k(x_i,x_i) (hmode=0)
 int launch_diag(pgp_ctx* ctx, const DevSpec* d_spec, int64_t n, int hmode, int nhyper, double* d_out);
 

@@ -24,17 +24,28 @@ bytes per factorisation); lZ needs nothing further because every rank ends up
 with the complete factor: the broadcasts double as the all-gather that the
 sharded predict (replicated L, test points split across ranks) needs anyway.
 
-The arithmetic is behind a small backend interface so that the schedule can be
-exercised on CPU with gloo (tests/test_distchol.py, numpy stand-in); the
-product backend is `DeviceBackend` (C ABI on torch-allocated device buffers --
-torch is allocator and NCCL plumbing only).
+PRODUCT PATH: `distributed_update` / `distributed_loglikelihood` call
+`pgp_dist_exact_update` / `pgp_dist_exact_loglike` (pygp_b200/csrc/dist.cu): the
+whole schedule -- panel Gram, potrf, pack, `ncclBroadcast` on a communication
+stream, DMMA updates, and for the gradient two "staircase" triangular solves, a
+trace and one `ncclAllReduce` -- is enqueued from C++ with events, the host never
+waits inside the loop.  (Round 1 paced it from Python, one ctypes call and one
+torch.distributed broadcast per panel.)  torch.distributed is used ONCE, to hand
+NCCL's unique id from rank 0 to the other ranks.
+
+`distributed_factor` below is the schedule's MODEL: the same ownership, lookahead
+and broadcast order behind a small backend interface, exercised on CPU with gloo
+and a numpy backend (tests/test_distchol.py); `gradient_partition_model` is the
+numpy model of the block-column gradient (tests/test_distchol.py pins both to
+dense LAPACK results).
 """
 
 import numpy as np
 
 from . import sharding
 
-__all__ = ['block_columns', 'distributed_factor', 'DeviceBackend', 'distributed_update']
+__all__ = ['block_columns', 'distributed_factor', 'gradient_partition_model', 'Communicator',
+           'communicator', 'distributed_update', 'distributed_loglikelihood']
 
 
 def block_columns(n, nb):
@@ -120,117 +131,110 @@ def distributed_factor(be, n, nb, rank, size, bcast, group=1, allreduce_min=None
     return info
 
 
-class DeviceBackend(object):
-    """The arithmetic of `distributed_factor` on this rank's GPU through the C
-    ABI; panels are torch-allocated device buffers (row-major, ld = w)."""
+def gradient_partition_model(L, a, dK, sn2, nb, rank, size):
+    """numpy MODEL of one rank's share of `ExactGP.loglikelihood(True)`'s gradient
+    (exact.py:128-141) under the block-column partition of dist.cu:
 
-    def __init__(self, gp, hyp, nb):
-        import ctypes as C
-        import torch
+        for every owned block column J:  W = L^-1 E_J (rows >= J nb),  H_J = L^-T W (rows >= J nb)
+        alpha = L^-T a
+        S_0  = sum_{c in J} Q_cc,   S_h = sum_{c in J} (Q_cc dK_h,cc + 2 sum_{i > c} Q_ic dK_h,ic)
+        with Q = K~^-1 - alpha alpha^T.
+
+    Summed over the ranks, dlZ = [-sn2 S_0, -1/2 S_h ..., sum(alpha)].  `dK` is the list of dense
+    dK_h matrices (test sizes only).  Returns the vector (S_0, S_1, ...)."""
+    import scipy.linalg as sla
+    n = len(L)
+    alpha = sla.solve_triangular(L, a, lower=True, trans=1)
+    S = np.zeros(1 + len(dK))
+    for j, (j0, w) in enumerate(block_columns(n, nb)):
+        if j % size != rank:
+            continue
+        Lt = L[j0:, j0:]
+        E = np.zeros((n - j0, w))
+        E[:w] = np.eye(w)
+        W = sla.solve_triangular(Lt, E, lower=True)               # (L^-1 E_J)[j0:]
+        H = sla.solve_triangular(Lt, W, lower=True, trans=1)      # K~^-1[j0:, J]
+        Q = H - np.outer(alpha[j0:], alpha[j0:j0 + w])
+        wgt = 2.0*np.tril(np.ones((n - j0, w)), -1) + np.eye(n - j0, w)
+        S[0] += np.trace(Q[:w])
+        for h, dk in enumerate(dK):
+            S[1 + h] += np.sum(wgt*Q*dk[j0:, j0:j0 + w])
+    return S
+
+
+class Communicator(object):
+    """Owner of a `pgp_dist*` (NCCL communicator + communication stream + staging buffers)."""
+
+    def __init__(self, ctx, handle, rank, size):
+        self.ctx, self.handle, self.rank, self.size = ctx, handle, rank, size
+
+    def allreduce(self, x, op='sum'):
         from . import _lib
-        self._lib, self._torch, self._C = _lib, torch, C
-        self.gp, self.hyp = gp, np.ascontiguousarray(hyp, dtype=np.float64)
-        self.ctx, self.L = gp._dev.ctx, _lib.lib()
-        self.dev = torch.device('cuda', self.ctx.device)
-        self.stream = torch.cuda.ExternalStream(self.ctx.stream, device=self.dev)
-        self.n, self.nb = gp.ndata, int(nb)
-        if self.nb < 64 or self.nb % 64:
-            raise ValueError('block width must be a multiple of 64')
-        nk = gp._kernel.nhyper
-        self.sn2 = float(np.exp(2*self.hyp[0]))
-        self.khyp = _lib.as_f64(self.hyp[1:1 + nk])
-        self.mean = float(self.hyp[-1])
-        self.spec = gp._kernel._spec()
-        with torch.cuda.stream(self.stream):
-            self.X = torch.from_numpy(np.ascontiguousarray(gp._X)).to(self.dev)
-            self.r = torch.from_numpy(np.ascontiguousarray(gp._y - self.mean)).to(self.dev)
-        p, ld = C.c_void_p(), C.c_int64()
-        _lib.check(self.ctx, self.L.pgp_exact_factor_buffer(gp._dev.handle, C.byref(p), C.byref(ld)))
-        self.F_ptr, self.ld = p.value, ld.value
-        self._recv = {}
-        self.info = 0
+        x = _lib.as_f64(x).copy()
+        _lib.check(self.ctx, _lib.lib().pgp_dist_allreduce(self.handle, _lib.ptr(x), x.size, {'sum': 0, 'max': 1, 'min': 2}[op]))
+        return x
 
-    def build_panel(self, j0, w):
-        """((n - j0) + 1, nb) device panel (logical width w <= nb; row pitch nb keeps
-        every operand 16-byte aligned with an even leading dimension)."""
-        torch = self._torch
-        rows, nb = self.n - j0, self.nb
-        with torch.cuda.stream(self.stream):
-            panel = torch.empty((rows + 1, nb), dtype=torch.float64, device=self.dev)
-            tgt = panel if w == nb else torch.empty((rows, w), dtype=torch.float64, device=self.dev)
-            self._lib.check(self.ctx, self.L.pgp_gram_dev(
-                self.ctx.handle, self.spec, self._lib.ptr(self.khyp), self.X[j0:].data_ptr(), rows,
-                self.X[j0:j0 + w].data_ptr(), w, tgt.data_ptr()))
-            if w != nb:                                  # ragged last block column
-                panel.zero_()
-                panel[:rows, :w] = tgt
-            panel[:w, :w].diagonal().add_(self.sn2)     # + sn2 I   (exact.py:51-53)
-            panel[rows, :w] = self.r[j0:j0 + w]
-        return panel
+    def __del__(self):
+        try:
+            if self.handle:
+                from . import _lib
+                _lib.lib().pgp_dist_destroy(self.handle)
+                self.handle = None
+        except Exception:       # interpreter shutdown
+            pass
 
-    def recv_buffer(self, rows, w, slot):
-        torch = self._torch
-        if slot not in self._recv:
-            with torch.cuda.stream(self.stream):
-                self._recv[slot] = torch.empty((self.n + 1, self.nb), dtype=torch.float64, device=self.dev)
-        return self._recv[slot][:rows]
 
-    def factor_panel(self, panel, w):
-        rc = self.L.pgp_dev_potrf(self.ctx.handle, panel.data_ptr(), w, self.nb, panel.shape[0] - w)
-        if rc < 0:
-            self._lib.check(self.ctx, rc)
-        return rc
+_comms = {}
 
-    def update_from_factor(self, pj, j0, wj, c_lo, c_hi):
-        # operands straight from the replicated factor: rows j0.. of the stored block columns [c_lo, c_hi)
-        a = self.F_ptr + (j0*self.ld + c_lo)*8
-        self._lib.check(self.ctx, self.L.pgp_dev_gemm_nt(
-            self.ctx.handle, pj.shape[0], wj, c_hi - c_lo, -1.0, a, self.ld, a, self.ld,
-            1.0, pj.data_ptr(), self.nb, 0))
 
-    def store_panel(self, pk, j0, w):
-        # strided device copy into the model's factor buffer (rows j0 .. n, columns j0 .. j0 + w)
-        dst = self.F_ptr + (j0*self.ld + j0)*8
-        self._lib.check(self.ctx, self.L.pgp_dev_copy2d(self.ctx.handle, dst, self.ld*8, pk.data_ptr(), self.nb*8,
-                                                        w*8, pk.shape[0]))
-
-    def sync(self):
-        self.ctx.sync()
+def communicator(group=None):
+    """The library's communicator over the ranks of `group` (default: the world), created
+    on first use.  torch.distributed only carries NCCL's unique id from rank 0 to the others."""
+    import ctypes as C
+    from . import _lib
+    key = id(group) if group is not None else None
+    if key in _comms:
+        return _comms[key]
+    rank, size = sharding.world(group)
+    ctx, L = _lib.context(), _lib.lib()
+    uid = np.zeros(128, dtype=np.uint8)
+    if size > 1:
+        import torch
+        import torch.distributed as dist
+        if rank == 0:
+            _lib.check(ctx, L.pgp_dist_unique_id(ctx.handle, uid.ctypes.data_as(C.c_void_p)))
+        t = torch.from_numpy(uid).to(sharding._device_for(group))
+        src = dist.get_global_rank(group, 0) if group is not None else 0
+        dist.broadcast(t, src=src, group=group)
+        uid = t.cpu().numpy()
+    h = C.c_void_p()
+    _lib.check(ctx, L.pgp_dist_init(ctx.handle, size, rank, uid.ctypes.data_as(C.c_void_p), C.byref(h)))
+    _comms[key] = Communicator(ctx, h, rank, size)
+    return _comms[key]
 
 
 def distributed_update(gp, nb=512, group=None, panels_per_update=1):
     """`ExactGP._update` with the factorisation spread over the ranks of `group`.
-    Every rank must hold the same model (data and hypers).  Afterwards the model
-    on every rank is factored exactly as after `pgp_exact_update`."""
-    import torch
-    import torch.distributed as dist
+    Every rank must hold the same model (data and hypers) and call this together.
+    Afterwards the model on every rank is factored exactly as after `pgp_exact_update`;
+    a matrix that is not positive definite raises the same `LinAlgError` on every rank."""
     from . import _lib
-    rank, size = sharding.world(group)
-    hyp = _lib.as_f64(gp.get_hyper())
     if gp._dev is None:
         raise RuntimeError('distributed_update needs a model with data (add_data first)')
-    be = DeviceBackend(gp, hyp, nb)
-
-    class _Handle(object):
-        def __init__(self, work):
-            self.work = work
-
-        def wait(self):
-            self.work.wait()
-
-    def bcast(buf, src):
-        with torch.cuda.stream(be.stream):
-            src_global = dist.get_global_rank(group, src) if group is not None else src
-            return _Handle(dist.broadcast(buf, src=src_global, group=group, async_op=True))
-
-    def allreduce_min(v):
-        t = torch.tensor([v], dtype=torch.int64, device=be.dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
-        return int(t.item())
-
-    with torch.cuda.stream(be.stream):
-        info = distributed_factor(be, gp.ndata, nb, rank, size, bcast, panels_per_update, allreduce_min)
-    if info:
-        raise np.linalg.LinAlgError('%d-th leading minor of the array is not positive definite' % info)
-    _lib.check(be.ctx, _lib.lib().pgp_exact_adopt_factor(gp._dev.handle, _lib.ptr(hyp)))
+    comm = communicator(group)
+    hyp = _lib.as_f64(gp.get_hyper())
+    _lib.check(comm.ctx, _lib.lib().pgp_dist_exact_update(comm.handle, gp._dev.handle, _lib.ptr(hyp), int(nb)))
     return gp
+
+
+def distributed_loglikelihood(gp, grad=False, nb=512, group=None):
+    """`ExactGP.loglikelihood(grad)` after `distributed_update`, the gradient partitioned by
+    block column across the ranks (collective when grad=True; identical result on every rank)."""
+    import ctypes as C
+    from . import _lib
+    comm = communicator(group)
+    lZ = C.c_double()
+    dlZ = np.empty(gp.nhyper) if grad else None
+    _lib.check(comm.ctx, _lib.lib().pgp_dist_exact_loglike(
+        comm.handle, gp._dev.handle, int(nb), int(bool(grad)), C.byref(lZ), None if dlZ is None else _lib.ptr(dlZ)))
+    return (lZ.value, dlZ) if grad else lZ.value

@@ -49,10 +49,11 @@ class _DeviceModel(object):
 
 
 class ExactGP(GP):
-    # Opt-in multi-GPU factorisation: set to e.g. {'nb': 512, 'min_n': 32768} in a
+    # Opt-in multi-GPU evaluation: set to e.g. {'nb': 512, 'min_n': 32768} in a
     # one-process-per-GPU job whose ranks all hold the same model and call
-    # set_hyper in lockstep (replicated optimiser); `_update` then runs the 1-D
-    # block-column distributed Cholesky (pygp_b200/distchol.py) for ndata >= min_n.
+    # set_hyper / loglikelihood(True) in lockstep (replicated optimiser); `_update` then runs the
+    # 1-D block-column distributed Cholesky and `loglikelihood(True)` the block-column gradient
+    # (pygp_b200/csrc/dist.cu) for ndata >= min_n.  'force': also with a single rank (tests).
     distributed = None
 
     def __init__(self, likelihood, kernel, mean):
@@ -85,13 +86,11 @@ class ExactGP(GP):
             Xn, yn = _lib.as_f64(self._X[self._ndev:], 2), _lib.as_f64(self._y[self._ndev:], 1)
             _lib.check(self._dev.ctx, L.pgp_exact_append(self._dev.handle, _lib.ptr(Xn), _lib.ptr(yn), len(Xn)))
         self._ndev = n
-        cfg = self.distributed
-        if cfg and n >= cfg.get('min_n', 32768):
-            from .. import sharding, distchol
-            if sharding.world(cfg.get('group'))[1] > 1:
-                distchol.distributed_update(self, nb=cfg.get('nb', 512), group=cfg.get('group'),
-                                            panels_per_update=cfg.get('panels_per_update', 1))
-                return
+        cfg = self._dist_cfg()
+        if cfg:
+            from .. import distchol
+            distchol.distributed_update(self, nb=cfg.get('nb', 512), group=cfg.get('group'))
+            return
         hyp = _lib.as_f64(self.get_hyper())
         _lib.check(self._dev.ctx, L.pgp_exact_update(self._dev.handle, _lib.ptr(hyp)))
 
@@ -137,8 +136,21 @@ class ExactGP(GP):
         return None if self._dev is None else self._factor()[1]
 
     # -- GP interface ------------------------------------------------------------
+    def _dist_cfg(self):
+        """The opt-in distributed configuration if it applies to this model right now."""
+        cfg = self.distributed
+        if cfg and self.ndata >= cfg.get('min_n', 32768):
+            from .. import sharding
+            if sharding.world(cfg.get('group'))[1] > 1 or cfg.get('force'):
+                return cfg
+        return None
+
     def loglikelihood(self, grad=False):
         self._ensure_dev()
+        cfg = self._dist_cfg()
+        if cfg and grad:
+            from .. import distchol
+            return distchol.distributed_loglikelihood(self, True, nb=cfg.get('nb', 512), group=cfg.get('group'))
         lZ = C.c_double()
         dlZ = np.empty(self.nhyper) if grad else None
         _lib.check(self._dev.ctx, _lib.lib().pgp_exact_loglike(

@@ -81,6 +81,28 @@ def test_not_positive_definite_info():
     assert distributed_factor(be, 200, 64, 0, 1, None) > 128      # reported inside the third block column
 
 
+@pytest.mark.parametrize('n,nb,size', [(200, 64, 1), (200, 64, 2), (333, 64, 3), (300, 128, 2), (64, 64, 2)])
+def test_gradient_partition_model(n, nb, size):
+    """The block-column partition of the gradient (dist.cu: two solves per owned block column
+    + trace over i >= c, one all-reduce) == exact.py:128-141 computed densely."""
+    from pygp_b200.distchol import gradient_partition_model
+    K, r = _problem(n, seed=n + 1)
+    rng = np.random.RandomState(n)
+    dK = []
+    for _ in range(3):
+        A = rng.randn(n, n)
+        dK.append(A + A.T)
+    sn2 = 0.3
+    L = np.linalg.cholesky(K)
+    a = sla.solve_triangular(L, r, lower=True)
+    S = sum(gradient_partition_model(L, a, dK, sn2, nb, rank, size) for rank in range(size))
+    iK = np.linalg.inv(K)
+    alpha = iK @ r
+    Q = iK - np.outer(alpha, alpha)
+    want = np.r_[np.trace(Q), [np.sum(Q*d) for d in dK]]
+    nt.assert_allclose(S, want, rtol=1e-9, atol=1e-9*np.abs(want).max())
+
+
 def _free_port():
     s = socket.socket()
     s.bind(('127.0.0.1', 0))

@@ -169,12 +169,12 @@ def test_loglikelihood_fd_basic():
 
 @pytest.mark.parametrize('N,nb', [(700, 128), (513, 64), (256, 256)])
 def test_distributed_update_single_rank(N, nb):
-    """pygp_b200.distchol.DeviceBackend (panel Gram, panel potrf with extra rows,
-    DMMA panel updates, strided store into the model's factor, adopt) on one
-    GPU without a process group == pgp_exact_update.  The N > 1 schedule is
-    covered on CPU (tests/test_distchol.py) and on GPUs by tools/dist_check.py."""
+    """pgp_dist_exact_update / pgp_dist_exact_loglike (csrc/dist.cu: block columns built and
+    factored in place, staircase solves, block-column trace) on one GPU without a process
+    group == pgp_exact_update / pgp_exact_loglike.  The N > 1 schedule is covered on CPU by its
+    numpy model (tests/test_distchol.py) and on GPUs by tests/test_multigpu.py."""
     import pygp_b200 as pygp
-    from pygp_b200.distchol import distributed_update
+    from pygp_b200.distchol import distributed_update, distributed_loglikelihood
     X, y, Xs = synthetic_problem(N, 4, 50)
     spec = ('matern', 1.0, [0.7, 0.8, 0.9, 1.0], 5)
     mk = lambda: pygp.inference.ExactGP(pygp.likelihoods.Gaussian(0.1), product_kernel(spec), 0.1)
@@ -188,8 +188,11 @@ def test_distributed_update_single_rank(N, nb):
     a, b = gp._likelihood.nhyper, gp._kernel.nhyper
     gp._likelihood.set_hyper(h2[:a]); gp._kernel.set_hyper(h2[a:a + b]); gp._mean = float(h2[-1])
     distributed_update(gp, nb=nb)
-    lZ, dlZ = gp.loglikelihood(True)
     lZ0, dlZ0 = ref.loglikelihood(True)
+    lZ, dlZ = distributed_loglikelihood(gp, True, nb=nb)      # block-column gradient
+    nt.assert_allclose(lZ, lZ0, rtol=1e-11)
+    assert_grad_close(dlZ, dlZ0, rtol=1e-9)
+    lZ, dlZ = gp.loglikelihood(True)                          # replicated gradient on the adopted factor
     nt.assert_allclose(lZ, lZ0, rtol=1e-11)
     assert_grad_close(dlZ, dlZ0, rtol=1e-9)
     mu, s2 = gp.posterior(Xs)

@@ -1,8 +1,10 @@
 """Multi-GPU check + timing (run under torchrun on the GPU box, one rank per GPU):
-  torchrun --nnodes=1 --nproc-per-node G --master-addr 127.0.0.1 --master-port 29511 tools/dist_check.py [N] [nb] [panels_per_update]
-* block-column distributed Cholesky (pygp_b200.distchol) == single-GPU update, and its speed-up
+  torchrun --nnodes=1 --nproc-per-node G --master-addr 127.0.0.1 --master-port 29511 tools/dist_check.py [N] [nb] [kernel]
+* block-column distributed Cholesky and block-column gradient (pygp_b200/csrc/dist.cu through
+  pygp_b200.distchol) == single-GPU update / loglikelihood(True), and their speed-up
 * sharded predict (test points) and sharded batched loglike / mixture posterior == single rank.
-Rank 0 prints JSON lines."""
+kernel: 'se8' (SE-ARD d=8, default) or 'c5' (SE + Periodic d=1 on sorted inputs: BASELINE configs[4]).
+Rank 0 prints JSON lines; any mismatch beyond the parity tolerances exits non-zero on every rank."""
 import json
 import os
 import sys
@@ -19,7 +21,7 @@ sys.path.insert(0, ROOT)
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
     nb = int(sys.argv[2]) if len(sys.argv) > 2 else 512
-    ppu = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+    kern = sys.argv[3] if len(sys.argv) > 3 else 'se8'
     rank, world, local = int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), int(os.environ['LOCAL_RANK'])
     torch.cuda.set_device(local)
     os.environ['PYGP_B200_DEVICE'] = str(local)
@@ -32,12 +34,18 @@ def main():
         if rank == 0:
             print(json.dumps(kw), flush=True)
 
-    d = 8
     rng = np.random.RandomState(0)
-    X = rng.rand(n, d)
+    if kern == 'c5':
+        d = 1
+        X = np.sort(rng.rand(n, 1), axis=0)*64
+        mk = lambda: pygp.inference.ExactGP(pygp.likelihoods.Gaussian(0.1),
+                                            pygp.kernels.SE(1.0, 0.5, 1) + pygp.kernels.Periodic(0.5, 1.0, 0.25), 0.0)
+    else:
+        d = 8
+        X = rng.rand(n, d)
+        mk = lambda: pygp.inference.ExactGP(pygp.likelihoods.Gaussian(0.1), pygp.kernels.SE(1.0, [0.5*np.sqrt(d)]*d), 0.0)
     y = np.sin(3*X.sum(1)) + 0.1*rng.randn(n)
-    Xs = np.random.RandomState(1).rand(4096, d)
-    mk = lambda: pygp.inference.ExactGP(pygp.likelihoods.Gaussian(0.1), pygp.kernels.SE(1.0, [0.5*np.sqrt(d)]*d), 0.0)
+    Xs = np.random.RandomState(1).rand(4096, d)*(64 if kern == 'c5' else 1)
     gp = mk()
     gp.add_data(X, y)                      # single-GPU factorisation on every rank (reference)
     ctx.sync()
@@ -45,27 +53,40 @@ def main():
     gp.set_hyper(gp.get_hyper())
     ctx.sync()
     t_single = time.perf_counter() - t0
-    lZ0 = gp.loglikelihood()
+    t0 = time.perf_counter()
+    lZ0, dlZ0 = gp.loglikelihood(True)
+    t_single_grad = time.perf_counter() - t0
     mu0, s20 = gp.posterior(Xs[:256])
+    del gp                                 # its gradient buffers (2 N^2) go back to the pool
 
     g2 = mk()
     g2.add_data(X, y)
+    comm = distchol.communicator()
     for rep in range(2):
         dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        distchol.distributed_update(g2, nb=nb, panels_per_update=ppu)
+        distchol.distributed_update(g2, nb=nb)
         ctx.sync()
-        dist.barrier()
-        t_dist = time.perf_counter() - t0
-    lZ1 = g2.loglikelihood()
+        t_dist = comm.allreduce([time.perf_counter() - t0], 'max')[0]
+        t0 = time.perf_counter()
+        lZ1, dlZ1 = distchol.distributed_loglikelihood(g2, True, nb=nb)
+        t_dist_grad = comm.allreduce([time.perf_counter() - t0], 'max')[0]
     mu1, s21 = g2.posterior(Xs[:256])
-    say(check='distributed_cholesky', n=n, nb=nb, panels_per_update=ppu, world=world, lZ_single=lZ0, lZ_dist=lZ1,
-        rel_err=abs(lZ1 - lZ0)/abs(lZ0), mu_err=float(np.abs(mu1 - mu0).max()), s2_err=float(np.abs(s21 - s20).max()),
-        t_single_s=t_single, t_dist_s=t_dist, speedup=t_single/t_dist,
-        tflops_single=n**3/3/t_single/1e12, tflops_dist_aggregate=n**3/3/t_dist/1e12)
+    gscale = float(np.abs(dlZ0).max())
+    say(check='distributed_eval', kernel=kern, n=n, nb=nb, world=world, lZ_single=lZ0, lZ_dist=lZ1,
+        lZ_rel_err=abs(lZ1 - lZ0)/abs(lZ0), dlZ_rel_err=float(np.abs(dlZ1 - dlZ0).max()/gscale),
+        mu_err=float(np.abs(mu1 - mu0).max()), s2_err=float(np.abs(s21 - s20).max()),
+        update_single_s=t_single, update_dist_s=t_dist, update_speedup=t_single/t_dist,
+        grad_single_s=t_single_grad, grad_dist_s=t_dist_grad, grad_speedup=t_single_grad/t_dist_grad,
+        eval_single_s=t_single + t_single_grad, eval_dist_s=t_dist + t_dist_grad,
+        eval_speedup=(t_single + t_single_grad)/(t_dist + t_dist_grad),
+        update_tflops_single=n**3/3/t_single/1e12, update_tflops_dist_aggregate=n**3/3/t_dist/1e12,
+        grad_tflops_dist_aggregate=2*n**3/3/t_dist_grad/1e12)
     assert abs(lZ1 - lZ0) <= 1e-10*abs(lZ0), (lZ0, lZ1)
+    assert np.abs(dlZ1 - dlZ0).max() <= 1e-8*gscale, (dlZ0, dlZ1)
 
+    gp = g2
     # sharded predict
     dist.barrier()
     t0 = time.perf_counter()
@@ -77,9 +98,9 @@ def main():
     t_one = time.perf_counter() - t0
     say(check='sharded_predict', points=len(Xs), max_err=float(max(np.abs(mu_s - mu_f).max(), np.abs(s2_s - s2_f).max())),
         t_sharded_s=t_sh, t_single_rank_s=t_one)
-    assert np.array_equal(mu_s, mu_f) and np.array_equal(s2_s, s2_f)
+    assert np.allclose(mu_s, mu_f, rtol=1e-12, atol=1e-13) and np.allclose(s2_s, s2_f, rtol=1e-12, atol=1e-13)
 
-    # sharded batched hypers (C4 shape, scaled): N=2048, 64 samples
+    # sharded batched hypers (C4 shape, scaled): N=2048, 64 samples per rank
     Xb, yb = X[:2048], y[:2048]
     gb = mk()
     gb.add_data(Xb, yb)
@@ -89,7 +110,6 @@ def main():
     lz_sh = sharding.sharded_batched_loglike(gb, H)
     dist.barrier()
     t_sh = time.perf_counter() - t0
-    lz_one = sharding.sharded_batched_loglike(gb, H, group=None, local_fn=None) if world == 1 else None
     ref = []
     for h in H[:4]:
         gb.set_hyper(h)
