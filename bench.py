@@ -9,15 +9,22 @@ loglikelihood(grad=True).  Synthetic data per SURVEY.md section 8d.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-N > 1 (torchrun, one rank per GPU): the evaluation itself does not shard
-("replicas only") -- every rank evaluates its own hyper
-vectors on its own replica, as independent optimiser restarts / chains do, and
-`value` is the aggregate evaluations/s.  Predict IS sharded by test points and
-reported as predict_points_per_s.
+N > 1 (torchrun, one rank per GPU): the N = 32768 evaluation fits one GPU and its
+optimiser loop is sequential ("replicas only") -- `value` is the
+aggregate evaluations/s of independent replicas (restarts / chains), weak scaling.
+The paths that DO partition are measured beside it at every N (same JSON line):
+  dist_chol_n65536   BASELINE configs[4]: SE + Periodic, N = 65536 -- block-column
+                     distributed Cholesky + block-column gradient (csrc/dist.cu, NCCL panel
+                     broadcast), seconds and speed-up over the one-GPU evaluation
+  predict_strong     a FIXED total of test points (default 1 Mi) through
+                     sharding.sharded_posterior, host arrays in, all-gather included
+  mcmc_4096x2048     BASELINE configs[3]: 4096 hyper samples x N = 2048 through
+                     sharding.sharded_batched_loglike (batched Cholesky, sharded by sample)
 
 --impl reference times the reference's algorithm on the host cores (the numpy
-oracle port; the reference itself is Python 2 and cannot travel to the GPU
-box) on a bounded sample, extrapolated to the metric's N by an a N^2 + b N^3 fit.
+oracle port; the reference itself is Python 2 and cannot travel to the GPU box) with
+all host threads, at N = 8192, N^3-extrapolated (x64) to the metric's N
+and labelled so, plus a bare LAPACK dpotrf + dpotri lower bound.
 """
 
 import argparse
@@ -27,6 +34,12 @@ import subprocess
 import sys
 import threading
 import time
+
+if 'reference' in sys.argv:
+    # the reference arm is a CPU job: every host core, set before numpy loads its BLAS (torchrun exports
+    # OMP_NUM_THREADS=1 to the ranks, which made round 1's N > 1 reference arm silently single-threaded)
+    for _k in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS'):
+        os.environ[_k] = str(os.cpu_count() or 1)
 
 import numpy as np
 
@@ -147,37 +160,69 @@ def sum_over_ranks(x, world):
 
 
 # ---------------------------------------------------------------------------
-def cpu_reference_eval(n_s, d, steps, warmup, rank=0):
-    """The reference algorithm (oracle port) on the host cores: set_hyper +
-    loglikelihood(True) at a bounded N, returns seconds per evaluation."""
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the reference arm is a CPU job on rank 0
+    and gets every core.  Must run before numpy / scipy load their BLAS."""
+    n = str(os.cpu_count() or 1)
+    for k in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS'):
+        os.environ[k] = n
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(int(n))
+    except Exception:
+        pass
+
+
+def cpu_reference_eval(n_s, d, budget_s, max_steps, rank=0):
+    """The reference algorithm (oracle port of exact.py:50-55,118-143) on the host cores:
+    set_hyper + loglikelihood(True) at a bounded N.  One warm-up at N/4 (BLAS threads, page
+    faults), then timed evaluations at n_s until `max_steps` or the time budget is used.
+    Returns (seconds per evaluation, evaluations timed)."""
     from oracle.pygp_oracle import make_kernel, OExactGP
-    X, y = problem(n_s, d)
     ell = list(0.5*np.sqrt(d)*np.ones(d))
-    gp = OExactGP(0.1, make_kernel(('matern', 1.0, ell, 5)), 0.0)
-    gp.add_data(X, y)
-    times = []
-    for s in range(warmup + steps):
-        h = step_hypers(d, s, rank)
+
+    def model(n):
+        X, y = problem(n, d)
+        gp = OExactGP(0.1, make_kernel(('matern', 1.0, ell, 5)), 0.0)
+        gp.add_data(X, y)
+        return gp
+    w = model(max(256, n_s//4))
+    w.set_hyper(step_hypers(d, 0, rank))
+    w.loglikelihood(True)
+    del w
+    gp = model(n_s)
+    times, t_start = [], time.perf_counter()
+    for s in range(max(1, max_steps)):
+        h = step_hypers(d, 1 + s, rank)
         t0 = time.perf_counter()
         gp.set_hyper(h)
         gp.loglikelihood(True)
-        dt = time.perf_counter() - t0
-        if s >= warmup:
-            times.append(dt)
-    return float(np.mean(times))
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_start + times[-1] > budget_s:
+            break
+    return float(np.mean(times)), len(times)
 
 
-def cpu_extrapolate(n, n_s, d, sec_full):
-    """The reference's cost is a N^2 (the (d+1)-matrix gradient loop, single
-    threaded) + b N^3 (Cholesky, cho_solve): fit both terms from the timed
-    sample at n_s and one more evaluation at n_s/2, then extrapolate to n."""
-    n_h = n_s // 2
-    sec_half = cpu_reference_eval(n_h, d, 1, 1)
-    A = np.array([[n_h**2, n_h**3], [n_s**2, n_s**3]], dtype=float)
-    a, b = np.linalg.solve(A, np.array([sec_half, sec_full]))
-    if a < 0 or b < 0:                  # degenerate fit: fall back to pure N^3
-        a, b = 0.0, sec_full/n_s**3
-    return a*n**2 + b*n**3, sec_half, n_h
+def lapack_lower_bound(n_l, n):
+    """Bare LAPACK dpotrf + dpotri (what any CPU implementation of loglike+grad must at least do:
+    the factor and the explicit inverse, N^3 flops) on an SPD matrix of order n_l, N^3-scaled to n.
+    n_l = n (16 GiB at 32768, ~minutes of CPU) under --cpu-full, else a bounded n_l."""
+    from scipy.linalg import lapack
+    rng = np.random.RandomState(0)
+    A = rng.rand(n_l, 64)
+    K = A @ A.T
+    K[np.diag_indices(n_l)] += n_l
+    K = np.asfortranarray(K)
+    t0 = time.perf_counter()
+    c, info = lapack.dpotrf(K, lower=1, overwrite_a=1)
+    t1 = time.perf_counter()
+    inv, info2 = lapack.dpotri(c, lower=1, overwrite_c=1)
+    t2 = time.perf_counter()
+    assert info == 0 and info2 == 0
+    scale = (float(n)/n_l)**3
+    return {'n': n_l, 'dpotrf_s': t1 - t0, 'dpotri_s': t2 - t1, 'gflops': n_l**3/(t2 - t0)/1e9,
+            'scaled_to_n': n, 'scale': scale, 'seconds_at_n': (t2 - t0)*scale, 'evals_per_s_at_n': 1.0/((t2 - t0)*scale),
+            'what': 'scipy.linalg.lapack dpotrf + dpotri, N^3 flops, N^3-scaled x%.0f' % scale}
 
 
 def host_threads():
@@ -188,26 +233,36 @@ def host_threads():
         return os.cpu_count() or 1
 
 
+def cpu_baseline_record(args, budget_s, max_steps):
+    n, d, n_s = args.n, args.d, args.cpu_n
+    sec, k = cpu_reference_eval(n_s, d, budget_s, max_steps)
+    scale = (float(n)/n_s)**3
+    sec_n = sec*scale
+    lap = lapack_lower_bound(n if args.cpu_full else min(n, args.lapack_n), n)
+    sample = ('oracle numpy port of exact.py:50-55,118-143 (set_hyper + loglikelihood(True)), Matern-5/2 ARD d=%d: '
+              '%.2f s/eval at N=%d (%d timed), N^3-EXTRAPOLATED x%.0f to N=%d = %.0f s (the reference itself needs '
+              '>72 GiB at N=32768; its O(N^2) per-hyper loop makes N^3 scaling pessimistic for the CPU by <2x); '
+              'bare LAPACK lower bound: %.0f s' % (d, sec, n_s, k, scale, n, sec_n, lap['seconds_at_n']))
+    return {'value': 1.0/sec_n, 'unit': UNIT, 'cores': host_threads(), 'kind': 'port', 'sample': sample,
+            'sample_n': n_s, 'sample_s_per_eval': sec, 'sample_evals': k, 'extrapolation_factor': scale,
+            'lapack_lower_bound': lap}, sec_n, k
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    n, d, n_s = args.n, args.d, args.cpu_n
-    sec = cpu_reference_eval(n_s, d, args.steps, args.warmup)
-    sec_n, sec_half, n_h = cpu_extrapolate(n, n_s, d, sec)
-    scale = sec_n/sec
-    value = 1.0/sec_n
-    cores = host_threads()
-    sample = ('oracle numpy port of exact.py:50-55,118-143 (set_hyper + loglikelihood(True)), Matern-5/2 ARD d=%d: '
-              '%.2f s/eval at N=%d, %.2f s at N=%d; a N^2 + b N^3 fit extrapolated to N=%d = %.0f s '
-              '(the reference itself needs >72 GiB at N=32768)' % (d, sec, n_s, sec_half, n_h, n, sec_n))
+    use_all_host_threads()
+    cpu, sec_n, k = cpu_baseline_record(args, args.cpu_budget, args.steps)
+    value = cpu['value']
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
-        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': sec_n*1e3, 'higher_is_better': True,
+        'steps': k, 'warmup': 1, 'steps_requested': args.steps, 'ms_per_step': sec_n*1e3, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': 'ExactGP Matern-5/2 ARD d=%d N=%d loglike+grad (CPU sample N=%d, extrapolated x%.0f)'
-                               % (d, n, n_s, scale)},
-        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+        'config': {'workload': 'ExactGP Matern-5/2 ARD d=%d N=%d loglike+grad (CPU sample N=%d, N^3-extrapolated x%.0f; '
+                               'timed evaluations bounded by a %.0f s budget)'
+                               % (args.d, args.n, args.cpu_n, cpu['extrapolation_factor'], args.cpu_budget)},
+        'cpu_baseline': cpu,
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -377,14 +432,11 @@ def run_ours(args):
         extra['gram_build_d1'] = 'SE iso d=1 N=%d: %.1f MB written in %.3f ms' % (ng, work1/1e6, ms1)
         del out
 
-    # ---- CPU baseline (rank 0, N = 1 only) ------------------------------------------------
+    # ---- CPU baseline (rank 0, N = 1 only): ONE evaluation of the oracle port at N = 8192 -----------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        sec = cpu_reference_eval(args.cpu_n, d, 1, 1)
-        sec_n, sec_half, n_h = cpu_extrapolate(n, args.cpu_n, d, sec)
-        cpu = {'value': 1.0/sec_n, 'unit': UNIT, 'cores': host_threads(), 'kind': 'port',
-               'sample': 'oracle port (set_hyper + loglikelihood(True)), d=%d: %.2f s at N=%d, %.2f s at N=%d; '
-                         'a N^2 + b N^3 fit extrapolated to N=%d = %.0f s' % (d, sec, args.cpu_n, sec_half, n_h, n, sec_n)}
+        use_all_host_threads()
+        cpu, _, _ = cpu_baseline_record(args, 0.0, 1)
 
     if rank == 0:
         g_l, g_ms, g_work = prof['gemm']
@@ -435,7 +487,16 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--n', type=int, default=32768)
     ap.add_argument('--d', type=int, default=16)
-    ap.add_argument('--cpu-n', type=int, default=3072, dest='cpu_n')
+    ap.add_argument('--cpu-n', type=int, default=8192, dest='cpu_n', help='N of the CPU sample (SURVEY 8d: 8192)')
+    ap.add_argument('--cpu-budget', type=float, default=150.0, dest='cpu_budget',
+                    help='reference arm: stop timing further evaluations after this many seconds')
+    ap.add_argument('--lapack-n', type=int, default=16384, dest='lapack_n',
+                    help='order of the dpotrf+dpotri lower-bound sample (N^3-scaled to --n)')
+    ap.add_argument('--cpu-full', action='store_true', dest='cpu_full', help='LAPACK lower bound at the full N')
+    ap.add_argument('--predict-total', type=int, default=1 << 20, dest='predict_total',
+                    help='test points of the strong-scaling predict leg (total over all ranks)')
+    ap.add_argument('--no-scale-legs', action='store_true', dest='no_scale_legs',
+                    help='skip dist_chol_n65536 / predict_strong / mcmc_4096x2048')
     ap.add_argument('--predict-pts', type=int, default=16384, dest='predict_pts', help='test points per rank')
     ap.add_argument('--no-cpu', action='store_true', dest='no_cpu')
     args = ap.parse_args()

@@ -443,9 +443,19 @@ int trsm_rec_stair(pgp_ctx* ctx, const Mat& B, const Mat& L, int64_t j0, int64_t
     int64_t n1 = split_point(n), n2 = n - n1, c0 = j0 + n1;
     PGP_TRY(trsm_rec_stair(ctx, B, L, j0, n1, st));
     const int64_t rows = st.rows(c0);            // rows with entries in columns [j0, c0)
-    if (rows > 0)
-        PGP_TRY(gemm_update(ctx, B.p + j0, B.ld, 0, L.p + c0 * L.ld + j0, L.ld, 0, B.p + c0, B.ld, 0, rows, n2, n1, -1.0,
-                            1.0, 0, 0, 1));
+    if (rows > 0) {
+        GemmArgs g;
+        g.A = B.p + j0; g.lda = B.ld;                    // X1 (rows, n1): block q is zero left of its first column
+        g.B = L.p + c0 * L.ld + j0; g.ldb = L.ld;        // L21 (n2, n1)
+        g.C = B.p + c0; g.ldc = B.ld;                    // B2 (rows, n2)
+        g.M = rows; g.N = n2; g.K = n1;
+        g.alpha = -1.0; g.beta = 1.0;
+        g.stair = 1;                                     // contraction of a row block starts at its first column
+        g.stair_front = st.front; g.stair_nb = st.nb;
+        g.stair_first = (int64_t)st.rank * st.nb; g.stair_step = (int64_t)st.size * st.nb;
+        g.stair_off = j0;
+        PGP_TRY(launch_gemm_nt(ctx, g));
+    }
     return trsm_rec_stair(ctx, B, L, c0, n2, st);
 }
 
@@ -466,6 +476,10 @@ int trsm_nt_rec_stair(pgp_ctx* ctx, const Mat& B, const Mat& L, int64_t j0, int6
         g.alpha = -1.0; g.beta = 1.0;
         g.transB = 1;
         g.splitk = 1;
+        g.stair = 2;                                     // a row block needs no column left of its first one
+        g.stair_front = st.front; g.stair_nb = st.nb;
+        g.stair_first = (int64_t)st.rank * st.nb; g.stair_step = (int64_t)st.size * st.nb;
+        g.stair_off = j0;
         PGP_TRY(launch_gemm(ctx, g));
     }
     return trsm_nt_rec_stair(ctx, B, L, j0, n1, st);

@@ -250,10 +250,27 @@ extern "C" int pgp_dist_exact_update(pgp_dist* d, pgp_model* m, const double* hy
         }
         d->stage_doubles = need_stage;
     }
-    PGP_TRY(ensure_events(d, (size_t)3 * nblk + 2));
-    auto ev_packed = [&](int64_t k) { return d->events[3 * k]; };
-    auto ev_bcast = [&](int64_t k) { return d->events[3 * k + 1]; };
-    auto ev_unpacked = [&](int64_t k) { return d->events[3 * k + 2]; };
+    PGP_TRY(ensure_events(d, (size_t)5 * nblk + 2));
+    auto ev_packed = [&](int64_t k) { return d->events[5 * k]; };        // panel k packed (panel stream)
+    auto ev_bcast = [&](int64_t k) { return d->events[5 * k + 1]; };     // broadcast of panel k done (comm stream)
+    auto ev_unpacked = [&](int64_t k) { return d->events[5 * k + 2]; };  // panel k in the replicated factor (main)
+    auto ev_trail = [&](int64_t k) { return d->events[5 * k + 3]; };     // trailing updates of step k enqueued (main)
+    auto ev_fact = [&](int64_t k) { return d->events[5 * k + 4]; };      // panel k factored (panel stream)
+    cudaEvent_t ev_start = d->events[5 * nblk];
+    // The panel chain (update of the next panel, its potrf, the pack) runs on a second, high-priority
+    // stream P so that on the owner it overlaps the trailing updates of the same step (the single-GPU
+    // lookahead of chol.cu, here across the panel broadcast as well).
+    if (!ctx->stream2) {
+        int lo = 0, hi = 0;
+        PGP_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        PGP_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, hi));
+    }
+    cudaStream_t P = ctx->stream2;
+    struct Swap {
+        pgp_ctx* c; cudaStream_t saved;
+        Swap(pgp_ctx* c_, cudaStream_t s) : c(c_), saved(c_->stream) { c->stream = s; }
+        ~Swap() { c->stream = saved; }
+    };
 
     PGP_CUDA(ctx, cudaMemcpyAsync(m->d_spec, &m->hspec, sizeof(DevSpec), cudaMemcpyHostToDevice, S));
     PGP_CUDA(ctx, cudaMemsetAsync(d->d_info, 0, sizeof(int) * nblk, S));
@@ -296,37 +313,48 @@ extern "C" int pgp_dist_exact_update(pgp_dist* d, pgp_model* m, const double* hy
         return launch_gemm_nt(ctx, g);
     };
 
-    // owner: factor panel k (potrf of its top w x w block, right-solve of the rows below, residual row
-    // included), pack it and start its broadcast; everybody: post the matching broadcast
+    // owner: bring panel k up to date with panel k - 1, factor it (potrf of its top w x w block, right-solve
+    // of the rows below, residual row included) and pack it -- all on the panel stream; everybody: post the
+    // matching broadcast on the communication stream
     auto produce = [&](int64_t k) -> int {
         const int64_t j0 = cols.j0(k), w = cols.w(k), rows = n - j0 + 1;
         const int owner = (int)(k % size);
+        double* buf = size > 1 ? d->stage[k & 1] : nullptr;
         if (owner == rank) {
-            Mat P;
-            P.p = m->d_F + j0 * ld + j0;
-            P.ld = ld;
-            PGP_TRY(potrf_lower(ctx, P, w, rows - w, d->d_info + k));
-        }
-        if (size == 1) return 0;
-        double* buf = d->stage[k & 1];
-        if (owner == rank) {
-            if (k >= 2) PGP_CUDA(ctx, cudaStreamWaitEvent(S, ev_bcast(k - 2), 0));      // slot free again
-            PGP_CUDA(ctx, cudaMemcpy2DAsync(buf, w * 8, m->d_F + j0 * ld + j0, ld * 8, w * 8, rows, cudaMemcpyDeviceToDevice, S));
-            PGP_CUDA(ctx, cudaEventRecord(ev_packed(k), S));
-            PGP_CUDA(ctx, cudaStreamWaitEvent(C, ev_packed(k), 0));
+            // the panel stream needs: panel k - 1 in the factor, and the main stream's updates of panel k
+            // (steps <= k - 2) finished; for k = 0 the Gram build
+            PGP_CUDA(ctx, cudaStreamWaitEvent(P, k > 0 ? ev_unpacked(k - 1) : ev_start, 0));
+            if (k >= 2) PGP_CUDA(ctx, cudaStreamWaitEvent(P, ev_trail(k - 2), 0));
+            if (size > 1 && k >= 2) PGP_CUDA(ctx, cudaStreamWaitEvent(P, ev_bcast(k - 2), 0));   // staging slot free again
+            {
+                Swap sw(ctx, P);
+                PGP_TRY(catch_up(k, k));
+                Mat Pm;
+                Pm.p = m->d_F + j0 * ld + j0;
+                Pm.ld = ld;
+                PGP_TRY(potrf_lower(ctx, Pm, w, rows - w, d->d_info + k));
+            }
+            if (size > 1) {
+                PGP_CUDA(ctx, cudaMemcpy2DAsync(buf, w * 8, m->d_F + j0 * ld + j0, ld * 8, w * 8, rows, cudaMemcpyDeviceToDevice, P));
+                PGP_CUDA(ctx, cudaEventRecord(ev_packed(k), P));
+                PGP_CUDA(ctx, cudaStreamWaitEvent(C, ev_packed(k), 0));
+            }
+            PGP_CUDA(ctx, cudaEventRecord(ev_fact(k), P));
         } else if (k >= 2) {
             PGP_CUDA(ctx, cudaStreamWaitEvent(C, ev_unpacked(k - 2), 0));                 // receiver: slot consumed
         }
+        if (size == 1) return 0;
         PGP_NCCL(d, g_nccl.Broadcast(buf, buf, (size_t)rows * w, ncclDouble, owner, d->comm, C));
         PGP_CUDA(ctx, cudaEventRecord(ev_bcast(k), C));
         return 0;
     };
-    // everybody: panel k is in the replicated factor before anything reads it
+    // everybody: panel k is in the replicated factor before the main stream reads it
     auto consume = [&](int64_t k) -> int {
-        if (size == 1) return 0;
         const int64_t j0 = cols.j0(k), w = cols.w(k), rows = n - j0 + 1;
-        PGP_CUDA(ctx, cudaStreamWaitEvent(S, ev_bcast(k), 0));
-        if ((int)(k % size) != rank) {
+        if ((int)(k % size) == rank) {
+            PGP_CUDA(ctx, cudaStreamWaitEvent(S, ev_fact(k), 0));
+        } else {
+            PGP_CUDA(ctx, cudaStreamWaitEvent(S, ev_bcast(k), 0));
             PGP_CUDA(ctx, cudaMemcpy2DAsync(m->d_F + j0 * ld + j0, ld * 8, d->stage[k & 1], w * 8, w * 8, rows,
                                             cudaMemcpyDeviceToDevice, S));
         }
@@ -334,15 +362,14 @@ extern "C" int pgp_dist_exact_update(pgp_dist* d, pgp_model* m, const double* hy
         return 0;
     };
 
+    PGP_CUDA(ctx, cudaEventRecord(ev_start, S));
     PGP_TRY(produce(0));
     for (int64_t k = 0; k < nblk; ++k) {
         PGP_TRY(consume(k));
-        if (k + 1 < nblk) {
-            if ((int)((k + 1) % size) == rank) PGP_TRY(catch_up(k + 1, k + 1));   // lookahead: next panel first
-            PGP_TRY(produce(k + 1));
-        }
-        for (int64_t j = k + 2; j < nblk; ++j)
+        if (k + 1 < nblk) PGP_TRY(produce(k + 1));          // lookahead: the next panel is on its way ...
+        for (int64_t j = k + 2; j < nblk; ++j)              // ... while this step's trailing updates run
             if ((int)(j % size) == rank) PGP_TRY(catch_up(j, k + 1));
+        PGP_CUDA(ctx, cudaEventRecord(ev_trail(k), S));
     }
 
     // lZ from the complete factor; info: first failing minor over all panels and ranks
@@ -454,15 +481,57 @@ extern "C" int pgp_dist_exact_loglike(pgp_dist* d, pgp_model* m, int64_t nb, int
             d->d_B, ld, 1, rows_local, nb, rank, size, n);
         PGP_TRY(check_launch(ctx, "stair_identity_kernel"));
     }
-    Mat L, B1, B0;
+    // Every row of B is an independent right-hand side, so the owned block rows are cut into two groups of
+    // about equal work that run their two solves on two streams: while one group sits in the latency-bound
+    // 64-column leaf steps of its recursion, the other one's GEMM updates keep the tensor pipe busy.
+    Mat L;
     L.p = m->d_F; L.ld = ld;
-    B0.p = d->d_B; B0.ld = ld;                 // all rows (alpha row in front)
-    B1.p = d->d_B + ld; B1.ld = ld;            // the identity rows only
-    Stair s1, s0;
-    s1.nb = nb; s1.rank = rank; s1.size = size; s1.front = 0; s1.rows_total = rows_local;
-    s0 = s1; s0.front = 1; s0.rows_total = rows_local + 1;
-    PGP_TRY(trsm_right_lt_stair(ctx, B1, L, n, s1));     // rows J of L^-T:  E_J^T L^-T = (L^-1 E_J)^T
-    PGP_TRY(trsm_right_l_stair(ctx, B0, L, n, s0));      // (.) L^-1: rows J of K~^-1 (columns >= J nb), alpha^T
+    const int64_t nq = nblk > rank ? (nblk - rank + size - 1) / size : 0;     // owned block rows
+    int64_t q1 = nq;
+    {
+        double total = 0.0, acc = 0.0;
+        for (int64_t q = 0; q < nq; ++q) { const double r = (double)(n - (rank + q * size) * nb); total += r * r; }
+        for (int64_t q = 0; q < nq; ++q) {
+            const double r = (double)(n - (rank + q * size) * nb);
+            acc += r * r;
+            if (acc >= 0.5 * total) { q1 = q + 1; break; }
+        }
+        static const int two = [] { const char* e = getenv("PGP_DIST_GRAD_STREAMS"); return e ? atoi(e) : 2; }();
+        if (two < 2 || nq < 2) q1 = nq;
+    }
+    auto solve_group = [&](int64_t qa, int64_t qb, bool with_alpha) -> int {
+        if (qb <= qa && !with_alpha) return 0;
+        const int64_t r_lo = qa * nb, r_hi = std::min(qb * nb, rows_local);       // local identity rows [r_lo, r_hi)
+        Mat B1;
+        B1.p = d->d_B + (1 + r_lo) * ld; B1.ld = ld;
+        Stair s1;
+        s1.nb = nb; s1.rank = rank + (int)(qa * size); s1.size = size; s1.front = 0; s1.rows_total = r_hi - r_lo;
+        PGP_TRY(trsm_right_lt_stair(ctx, B1, L, n, s1));     // rows J of L^-T:  E_J^T L^-T = (L^-1 E_J)^T
+        Mat B0 = B1;
+        Stair s0 = s1;
+        if (with_alpha) { B0.p = d->d_B; s0.front = 1; s0.rows_total += 1; }      // row 0 = a rides along: alpha^T = a^T L^-1
+        return trsm_right_l_stair(ctx, B0, L, n, s0);        // (.) L^-1: rows J of K~^-1 (columns >= J nb)
+    };
+    if (q1 < nq) {
+        if (!ctx->stream2) {
+            int lo = 0, hi = 0;
+            PGP_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            PGP_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, hi));
+        }
+        PGP_TRY(ensure_events(d, 2));
+        cudaStream_t P = ctx->stream2;
+        PGP_CUDA(ctx, cudaEventRecord(d->events[0], S));
+        PGP_CUDA(ctx, cudaStreamWaitEvent(P, d->events[0], 0));
+        ctx->stream = P;
+        int rc2 = solve_group(q1, nq, false);
+        ctx->stream = S;
+        PGP_TRY(rc2);
+        PGP_CUDA(ctx, cudaEventRecord(d->events[1], P));
+        PGP_TRY(solve_group(0, q1, true));
+        PGP_CUDA(ctx, cudaStreamWaitEvent(S, d->events[1], 0));
+    } else {
+        PGP_TRY(solve_group(0, nq, true));
+    }
     PGP_CUDA(ctx, cudaMemcpyAsync(m->d_alpha, d->d_B, sizeof(double) * n, cudaMemcpyDeviceToDevice, S));
 
     TraceDistArgs t;

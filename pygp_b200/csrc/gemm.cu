@@ -71,7 +71,9 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 // (A is (K, M) row-major / B is (K, N) row-major); its tile is then staged as
 // [k][m] with a row of BM + 4 doubles, which keeps the fragment loads
 // (lane -> m = lane/4, k = lane%4) conflict-free as well: 132 = 4 (mod 16).
-template <int WM, int WN, class C, bool TA, bool TB>
+// STAIR: staircase operands (gemm.cuh) -- a separate instantiation, so that the kernels of the factorisation
+// keep their register allocation (the 16-warp variant sits at its 128-register cap).
+template <int WM, int WN, class C, bool TA, bool TB, bool STAIR = false>
 __global__ void __launch_bounds__(WM * WN * 32, C::BM == 64 ? 2 : 1) gemm_kernel(GemmArgs a, int tm, int tn) {
     constexpr int BM = C::BM, BN = C::BN;
     constexpr int THREADS = WM * WN * 32;
@@ -99,6 +101,12 @@ __global__ void __launch_bounds__(WM * WN * 32, C::BM == 64 ? 2 : 1) gemm_kernel
     const int64_t m0 = (int64_t)tile_m * BM;
     const int64_t n0 = (int64_t)tile_n * BN;
     if (a.tri && n0 > m0 + BM - 1 + a.tri_off) return;
+    // staircase operands (gemm.cuh): first column at which this tile row's block exists, relative to the
+    // operand's column 0 (32-bit arithmetic: the prologue must not cost the main loop registers)
+    int stair_rel = 0;
+    if (STAIR && a.stair && tile_m * BM >= (int)a.stair_front)
+        stair_rel = (int)(a.stair_first - a.stair_off) + (tile_m * BM - (int)a.stair_front) / (int)a.stair_nb * (int)a.stair_step;
+    if (STAIR && (a.stair & 2) && tile_n * BN + BN - 1 < stair_rel) return;
 
     const int b = blockIdx.z;
     const double* __restrict__ A = a.A + (int64_t)b * a.strideA;
@@ -111,6 +119,10 @@ __global__ void __launch_bounds__(WM * WN * 32, C::BM == 64 ? 2 : 1) gemm_kernel
         ks = m0 + a.krow_off;
         if (ks < 0) ks = 0;
         ks = ks / BK * BK;
+        if (ks > a.K) ks = a.K;
+    }
+    if (STAIR && (a.stair & 1) && stair_rel > 0) {
+        ks = stair_rel / BK * BK;
         if (ks > a.K) ks = a.K;
     }
     if (a.kcol) {  // B is upper triangular in (k, col): the contraction may stop at the tile's last column
@@ -377,9 +389,16 @@ __global__ void splitk_reduce_kernel(GemmArgs a) {
 namespace {
 template <int WM, int WN, class C, bool TA, bool TB>
 int launch_variant(pgp_ctx* ctx, const GemmArgs& a, int64_t tm, int64_t tn) {
+    dim3 grid((unsigned)(tm * tn), (unsigned)std::max(a.splitk, 1), a.batch);
+    if (a.stair) {
+        if (TA) return ctx->fail(PGP_E_ARG, "gemm: staircase operands need A stored (M, K)");
+        auto kern = gemm_kernel<WM, WN, C, false, TB, true>;
+        PGP_TRY(ensure_dyn_smem(ctx, kern, C::SMEM));
+        kern<<<grid, WM * WN * 32, C::SMEM, ctx->stream>>>(a, (int)tm, (int)tn);
+        return 0;
+    }
     auto kern = gemm_kernel<WM, WN, C, TA, TB>;
     PGP_TRY(ensure_dyn_smem(ctx, kern, C::SMEM));
-    dim3 grid((unsigned)(tm * tn), (unsigned)std::max(a.splitk, 1), a.batch);
     kern<<<grid, WM * WN * 32, C::SMEM, ctx->stream>>>(a, (int)tm, (int)tn);
     return 0;
 }
@@ -420,7 +439,7 @@ int launch_gemm(pgp_ctx* ctx, const GemmArgs& a_in) {
     // (FITC: p x p results contracted over n >> p): partials go to a workspace
     // and are summed in a fixed order
     a.splitk = 1;
-    if (a_in.splitk != 1 && !a.krow && !a.kcol && a.batch == 1) {
+    if (a_in.splitk != 1 && !a.krow && !a.kcol && !a.stair && a.batch == 1) {
         int64_t tiles = count_tiles(BM);
         int64_t want = a_in.splitk > 1 ? a_in.splitk : (2 * ctx->sm_count) / std::max<int64_t>(tiles, 1);
         int64_t max_by_k = a.K / 2048;  // keep >= 2048 contraction steps per slice
@@ -450,6 +469,12 @@ int launch_gemm(pgp_ctx* ctx, const GemmArgs& a_in) {
         double cols = (double)a.N, klen = (double)a.K;
         if (a.tri) cols = std::min(std::max(mid + (double)a.tri_off + 1.0, 0.0), (double)a.N);
         if (a.krow) klen = std::min(std::max((double)a.K - (mid + (double)a.krow_off), 0.0), (double)a.K);
+        if (a.stair) {
+            const int64_t r0 = ti * (int64_t)BM;
+            const double S = r0 >= a.stair_front ? (double)(a.stair_first + (r0 - a.stair_front) / a.stair_nb * a.stair_step) : 0.0;
+            if (a.stair & 1) klen = std::min(std::max((double)a.K - (S - (double)a.stair_off), 0.0), klen);
+            if (a.stair & 2) cols = std::min(std::max((double)a.N - (S - (double)a.stair_off), 0.0), cols);
+        }
         if (a.kcol) {
             // sum over the columns j of (j + 1 + off - kstart) clipped to [0, K - kstart]; exact for the
             // regular triangular cases used here (kstart = K - klen)

@@ -29,6 +29,13 @@ struct GemmArgs {
     // k = j0 + BN + kcol_off.  Used by the bottom-up triangular inverse.
     int kcol = 0;
     int64_t kcol_off = 0;
+    // stair: the rows of A and C are `stair_front` dense rows followed by blocks of stair_nb rows, block q
+    // of which only exists from column S(q) = stair_first + q stair_step of the caller's column space
+    // (chol.cuh: Stair).  Bit 1: A's block q is zero for k + stair_off < S(q), so the contraction of a tile
+    // row may start there (as krow, with a slope of stair_step / stair_nb).  Bit 2: C's block q is only
+    // needed at columns n + stair_off >= S(q): tiles wholly to the left are skipped.
+    int stair = 0;
+    int64_t stair_front = 0, stair_nb = 1, stair_first = 0, stair_step = 0, stair_off = 0;
     int batch = 1;
     int64_t strideA = 0, strideB = 0, strideC = 0;
     // general forms (launch_gemm): transA -> A is stored (K x M) row-major,

@@ -72,6 +72,23 @@ def main():
         t0 = time.perf_counter()
         lZ1, dlZ1 = distchol.distributed_loglikelihood(g2, True, nb=nb)
         t_dist_grad = comm.allreduce([time.perf_counter() - t0], 'max')[0]
+    if os.environ.get('PGP_DIST_PROF'):
+        # per-class device time of one distributed evaluation on this rank (CUDA events per launch)
+        names = ['gemm', 'gram', 'trace', 'potrf_base', 'trsm_base', 'other']
+        for what in ('update', 'grad'):
+            ctx.profile(True)
+            t0 = time.perf_counter()
+            if what == 'update':
+                distchol.distributed_update(g2, nb=nb)
+            else:
+                distchol.distributed_loglikelihood(g2, True, nb=nb)
+            ctx.sync()
+            wall = time.perf_counter() - t0
+            prof = {nm: ctx.profile_read(i) for i, nm in enumerate(names)}
+            ctx.profile(False)
+            say(check='dist_profile_rank0', what=what, wall_s=wall,
+                classes={nm: {'launches': v[0], 'ms': round(v[1], 2), 'tflops_or_GBps': round(v[2]/max(v[1], 1e-9)/1e9, 2)}
+                         for nm, v in prof.items()})
     mu1, s21 = g2.posterior(Xs[:256])
     gscale = float(np.abs(dlZ0).max())
     say(check='distributed_eval', kernel=kern, n=n, nb=nb, world=world, lZ_single=lZ0, lZ_dist=lZ1,
