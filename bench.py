@@ -395,12 +395,36 @@ def run_ours(args):
     extra['predict_points_per_s'] = m_loc*world/p_s
     extra['predict_fp64_tflops_per_gpu'] = m_loc*float(n)*n/p_s/1e12
     extra['predict_points'] = m_loc*world
-    Xs_h = Xs.cpu().numpy()
+    Xs_pin = torch.empty((m_loc, d), dtype=torch.float64).pin_memory()      # pinned host test points
+    Xs_pin.copy_(Xs)
+    Xs_h = Xs_pin.numpy()
     barrier(world)
     t0 = time.perf_counter()
     gp.posterior(Xs_h)
     extra['predict_points_per_s_e2e'] = m_loc*world/max_over_ranks(time.perf_counter() - t0, world)
     del Xs, mu, s2
+
+    # ---- the paths that partition, measured at every N ------------------------
+    if not args.no_scale_legs:
+        from pygp_b200 import sharding, distchol
+        # (1) predict, STRONG scaling: a fixed total of test points through sharding.sharded_posterior
+        #     (host array in, per-rank slice H2D + predict + D2H, all-gather of (mu, s2) included)
+        m_tot = args.predict_total
+        Xt = np.random.RandomState(7).rand(m_tot, d)
+        sharding.sharded_posterior(gp, Xt[:world*256])                 # warm-up (buffers, NCCL channel)
+        barrier(world)
+        t0 = time.perf_counter()
+        mu_t, s2_t = sharding.sharded_posterior(gp, Xt)
+        t_pred = max_over_ranks(time.perf_counter() - t0, world)
+        assert mu_t.shape == (m_tot,) and np.all(np.isfinite(mu_t)) and np.all(s2_t > 0)
+        extra['predict_strong'] = {
+            'points_total': m_tot, 'seconds': t_pred, 'points_per_s': m_tot/t_pred,
+            'fp64_tflops_per_gpu': m_tot/world*float(n)*n/t_pred/1e12,
+            'what': 'sharding.sharded_posterior: N=%d d=%d model replicated, %d test points split over %d rank(s), '
+                    'host arrays, all-gather of (mu, s2) included' % (n, d, m_tot, world)}
+        del Xt, mu_t, s2_t
+    kern_main = gp._kernel
+    del gp
 
     if rank == 0:
         ng = min(n, 32768)
@@ -421,7 +445,7 @@ def run_ours(args):
             ctx.profile(False)
             return work/ms/1e6, ms, work
         # the workload's kernel (FP64-pipe bound: ~(2d + 45) DP instructions per entry) ...
-        gbs, ms, work = gram_rate(gp._kernel, X[:ng])
+        gbs, ms, work = gram_rate(kern_main, X[:ng])
         extra['gram_build_GBps'] = gbs
         extra['gram_build_hbm_frac'] = gbs/hbm_peak
         extra['gram_build'] = 'Kernel.get(X) full square N=%d d=%d: %.1f MB written in %.3f ms' % (ng, d, work/1e6, ms)
@@ -431,6 +455,79 @@ def run_ours(args):
         extra['gram_build_d1_hbm_frac'] = gbs1/hbm_peak
         extra['gram_build_d1'] = 'SE iso d=1 N=%d: %.1f MB written in %.3f ms' % (ng, work1/1e6, ms1)
         del out
+
+    if not args.no_scale_legs:
+        from pygp_b200 import sharding, distchol
+        ctx.sync()
+        # (2) batched MCMC (BASELINE configs[3]): 4096 hyper samples x N = 2048 SE-ARD d = 8 through
+        #     sharding.sharded_batched_loglike: B / G samples per rank, results all-gathered
+        nb_, db_, B_ = 2048, 8, 4096
+        Xb, yb = problem(nb_, db_, seed=2)
+        gb = pygp.inference.ExactGP(pygp.likelihoods.Gaussian(0.1),
+                                    pygp.kernels.SE(1.0, list(0.5*np.sqrt(db_)*np.ones(db_))), 0.0)
+        gb.add_data(Xb, yb)
+        H = gb.get_hyper() + np.random.RandomState(2).uniform(-0.5, 0.5, size=(B_, gb.nhyper))
+        sharding.sharded_batched_loglike(gb, H[:world*8])              # warm-up
+        barrier(world)
+        t0 = time.perf_counter()
+        lz_b = sharding.sharded_batched_loglike(gb, H)
+        t_b = max_over_ranks(time.perf_counter() - t0, world)
+        assert lz_b.shape == (B_,) and np.all(np.isfinite(lz_b))
+        extra['mcmc_4096x2048'] = {
+            'samples': B_, 'n': nb_, 'seconds': t_b, 'samples_per_s': B_/t_b,
+            'potrf_tflops_per_gpu': B_/world*float(nb_)**3/3/t_b/1e12,
+            'what': 'sharding.sharded_batched_loglike: %d hyper vectors x N=%d SE-ARD d=%d, sharded by sample over '
+                    '%d rank(s) (batched Gram + Cholesky + solve), all-gather of lZ included' % (B_, nb_, db_, world)}
+        del gb, lz_b
+
+        torch.cuda.empty_cache()
+        # (3) C5 (BASELINE configs[4]): SE + Periodic, N = 65536.  One-GPU evaluation (every rank runs it on its
+        #     own GPU) and the block-column distributed evaluation over all ranks (csrc/dist.cu)
+        n5, nb5 = args.c5_n, args.c5_nb
+        rng5 = np.random.RandomState(0)
+        X5 = np.sort(rng5.rand(n5, 1), axis=0)*64
+        y5 = np.sin(3*X5.sum(1)) + 0.1*rng5.randn(n5)
+        mk5 = lambda: pygp.inference.ExactGP(pygp.likelihoods.Gaussian(0.1),
+                                             pygp.kernels.SE(1.0, 0.5, 1) + pygp.kernels.Periodic(0.5, 1.0, 0.25), 0.0)
+        g5 = mk5()
+        g5.add_data(X5, y5)                                            # upload + first factorisation (untimed)
+        h5 = g5.get_hyper()
+        ctx.sync()
+        t0 = time.perf_counter()
+        g5.set_hyper(h5 + 0.01)
+        ctx.sync()
+        t_u1 = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        lZ5, dlZ5 = g5.loglikelihood(True)
+        t_g1 = time.perf_counter() - t0
+        t_u1, t_g1 = max_over_ranks(t_u1, world), max_over_ranks(t_g1, world)
+        c5 = {'n': n5, 'nb': nb5, 'update_1gpu_s': t_u1, 'loglike_grad_1gpu_s': t_g1,
+              'eval_1gpu_s': t_u1 + t_g1, 'eval_1gpu_tflops': float(n5)**3/(t_u1 + t_g1)/1e12}
+        del g5                                                         # its 2 N^2 gradient buffers return to the pool
+        g5 = mk5()
+        g5.add_data(X5, y5)
+        g5._likelihood.set_hyper((h5 + 0.01)[:1]); g5._kernel.set_hyper((h5 + 0.01)[1:-1]); g5._mean = float(h5[-1] + 0.01)
+        for rep in range(2):                                           # first pass: buffers, NCCL channels
+            barrier(world)
+            t0 = time.perf_counter()
+            distchol.distributed_update(g5, nb=nb5)
+            ctx.sync()
+            t_ud = max_over_ranks(time.perf_counter() - t0, world)
+            t0 = time.perf_counter()
+            lZd, dlZd = distchol.distributed_loglikelihood(g5, True, nb=nb5)
+            t_gd = max_over_ranks(time.perf_counter() - t0, world)
+        c5.update({'update_s': t_ud, 'loglike_grad_s': t_gd, 'eval_s': t_ud + t_gd,
+                   'speedup_vs_1gpu': (t_u1 + t_g1)/(t_ud + t_gd), 'update_speedup_vs_1gpu': t_u1/t_ud,
+                   'loglike_grad_speedup_vs_1gpu': t_g1/t_gd,
+                   'aggregate_tflops': float(n5)**3/(t_ud + t_gd)/1e12,
+                   'lZ_rel_diff_vs_1gpu': abs(lZd - lZ5)/abs(lZ5),
+                   'dlZ_rel_diff_vs_1gpu': float(np.abs(dlZd - dlZ5).max()/np.abs(dlZ5).max()),
+                   'what': 'SE + Periodic d=1, N=%d: ExactGP._update + loglikelihood(True); 1 GPU = pgp_exact_update / '
+                           '_loglike, %d rank(s) = pgp_dist_exact_update / _loglike (block columns of %d, NCCL panel '
+                           'broadcast, block-column gradient + one all-reduce)' % (n5, world, nb5)})
+        assert c5['lZ_rel_diff_vs_1gpu'] <= 1e-10 and c5['dlZ_rel_diff_vs_1gpu'] <= 1e-8, c5
+        extra['dist_chol_n65536'] = c5
+        del g5
 
     # ---- CPU baseline (rank 0, N = 1 only): ONE evaluation of the oracle port at N = 8192 -----------
     cpu = None
@@ -444,6 +541,11 @@ def run_ours(args):
         # roofline.traffic: DRAM bytes of ONE launch of the dominant kernel from the committed ncu --set full
         # capture (an 8192^3 launch; the launches of a step have many shapes, so the capture's own algorithmic
         # bytes are given beside it in traffic_detail)
+        fp64_file = None
+        try:
+            fp64_file = json.load(open(os.path.join(ROOT, 'profiles', 'fp64_peak.json')))
+        except Exception:
+            pass
         traffic, traffic_detail = None, None
         try:
             traffic_detail = json.load(open(os.path.join(ROOT, 'profiles', 'gemm_traffic.json')))
@@ -466,7 +568,10 @@ def run_ours(args):
                          'traffic': traffic, 'traffic_detail': traffic_detail, 'launches': g_l, 'avg_launch_ms': g_ms/max(g_l, 1),
                          'share_of_step': g_ms*1e-3/dev_s,
                          'peak_source': 'cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 '
-                                        'entry; nominal 37 TFLOP/s); HBM %s' % hbm_src},
+                                        'entry; nominal 37 TFLOP/s); HBM %s' % hbm_src,
+                         'fp64_peaks_on_file': fp64_file,
+                         'frac_of_dmma_issue_peak': (achieved/fp64_file['dmma_tflops']
+                                                     if fp64_file and fp64_file.get('dmma_tflops') else None)},
             'kernel_ms_per_step': {nm: prof[nm][1]/K for nm in names},
             'kernel_launches_per_step': {nm: prof[nm][0]/K for nm in names},
             'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': int(launches),
@@ -495,6 +600,8 @@ def main():
     ap.add_argument('--cpu-full', action='store_true', dest='cpu_full', help='LAPACK lower bound at the full N')
     ap.add_argument('--predict-total', type=int, default=1 << 20, dest='predict_total',
                     help='test points of the strong-scaling predict leg (total over all ranks)')
+    ap.add_argument('--c5-n', type=int, default=65536, dest='c5_n')
+    ap.add_argument('--c5-nb', type=int, default=512, dest='c5_nb')
     ap.add_argument('--no-scale-legs', action='store_true', dest='no_scale_legs',
                     help='skip dist_chol_n65536 / predict_strong / mcmc_4096x2048')
     ap.add_argument('--predict-pts', type=int, default=16384, dest='predict_pts', help='test points per rank')

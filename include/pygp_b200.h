@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PGP_ABI_VERSION 1
+#define PGP_ABI_VERSION 2
 
 #define PGP_MAX_PARTS 8     /* leaf kernels in one composite            */
 #define PGP_MAX_OPS   16    /* postfix program length                   */
@@ -203,12 +203,13 @@ int  pgp_dist_exact_update(pgp_dist* d, pgp_model* m, const double* hyp, int64_t
 int  pgp_dist_exact_loglike(pgp_dist* d, pgp_model* m, int64_t nb, int want_grad, double* lZ, double* dlZ);
 
 /* ---- batched small-N path: learning/sampling.py:146, meta/mcmc.py:75-93 ---- */
-/* B independent ExactGP._update + loglikelihood() sharing X, y.
- * hyps (B, nhyper_gp); lZ (B); info (B) per-problem potrf info (0 = ok). */
+/* B independent ExactGP._update + loglikelihood(grad) sharing X, y (learning/optimization.py:54-62 over
+ * several restarts, meta/smc.py particles).  hyps (B, nhyper_gp); lZ (B); dlZ (B, nhyper_gp) or NULL
+ * (likelihood only); info (B) per-problem potrf info (0 = ok; that problem's lZ / dlZ are then undefined). */
 int pgp_batched_loglike(pgp_ctx* ctx, const pgp_kernel_spec* spec,
                         const double* X, const double* y, int64_t n,
                         const double* hyps, int64_t B,
-                        double* lZ, int32_t* info);
+                        double* lZ, double* dlZ, int32_t* info);
 /* B independent posteriors at the same test points: mu, s2 are (B, ms). */
 int pgp_batched_predict(pgp_ctx* ctx, const pgp_kernel_spec* spec,
                         const double* X, const double* y, int64_t n,

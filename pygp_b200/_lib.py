@@ -90,7 +90,7 @@ SIGNATURES = {
     'pgp_dist_allreduce': (C.c_int, [_vp, _dp, _i64, C.c_int]),
     'pgp_dist_exact_update': (C.c_int, [_vp, _vp, _dp, _i64]),
     'pgp_dist_exact_loglike': (C.c_int, [_vp, _vp, _i64, C.c_int, _dp, _dp]),
-    'pgp_batched_loglike': (C.c_int, [_vp, _sp, _dp, _dp, _i64, _dp, _i64, _dp, _ip]),
+    'pgp_batched_loglike': (C.c_int, [_vp, _sp, _dp, _dp, _i64, _dp, _i64, _dp, _dp, _ip]),
     'pgp_batched_predict': (C.c_int, [_vp, _sp, _dp, _dp, _i64, _dp, _i64, _dp, _i64, _dp, _dp, _ip]),
     'pgp_fitc_create': (C.c_int, [_vp, _sp, _dp, _i64, _dp, _dp, _i64, C.POINTER(_vp)]),
     'pgp_dtc_create': (C.c_int, [_vp, _sp, _dp, _i64, _dp, _dp, _i64, C.POINTER(_vp)]),
@@ -131,7 +131,7 @@ def lib():
                     fn = getattr(handle, name)      # AttributeError if the .so lacks it
                     fn.restype = res
                     fn.argtypes = args
-                if handle.pgp_abi_version() != 1:
+                if handle.pgp_abi_version() != 2:
                     raise LibraryNotBuilt('libpygp_b200.so ABI version mismatch')
                 _lib = handle
     return _lib

@@ -85,6 +85,10 @@ extern "C" void pgp_ctx_destroy(pgp_ctx* ctx) {
         cudaStreamSynchronize(ctx->stream2);
         cudaStreamDestroy(ctx->stream2);
     }
+    for (cudaStream_t st : ctx->aux) {
+        cudaStreamSynchronize(st);
+        cudaStreamDestroy(st);
+    }
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -1104,7 +1108,7 @@ extern "C" int pgp_exact_get_factor(pgp_model* m, double* R_out, double* a_out) 
 // batched small-N path
 // ---------------------------------------------------------------------------
 static int batched_impl(pgp_ctx* ctx, const pgp_kernel_spec* spec, const double* X, const double* y, int64_t n,
-                        const double* hyps, int64_t B, const double* Xs, int64_t ms, double* lZ, double* mu,
+                        const double* hyps, int64_t B, const double* Xs, int64_t ms, double* lZ, double* dlZ, double* mu,
                         double* s2, int32_t* info) {
     if (!ctx) return PGP_E_ARG;
     if (!spec || !X || !y || !hyps || n <= 0 || B < 0) return ctx->fail(PGP_E_ARG, "null argument or bad size");
@@ -1114,6 +1118,8 @@ static int batched_impl(pgp_ctx* ctx, const pgp_kernel_spec* spec, const double*
     const int d = spec->ndim, np = spec->n_parts, nk = spec->nhyper, nh = nk + 2;
     const int64_t ld = lead_dim(n);
     const bool pred = Xs != nullptr && ms > 0;
+    const bool grad = dlZ != nullptr;
+    constexpr int kGradStreams = 4;
     // per-problem device footprint -> chunk of the batch that fits a 24 GiB budget
     size_t per = sizeof(double) * ((size_t)(n + 1) * ld + z_doubles(np, d, n)) + sizeof(DevSpec);
     if (pred) per += sizeof(double) * ((size_t)ms * ld + z_doubles(np, d, ms) + 2 * ms);
@@ -1143,6 +1149,37 @@ static int batched_impl(pgp_ctx* ctx, const pgp_kernel_spec* spec, const double*
     std::vector<DevSpec> hspecs((size_t)chunk);
     std::vector<int> hinfo((size_t)chunk);
     std::vector<double> hres((size_t)chunk);
+    // gradient (exact.py:128-141 per hyper vector): the inverse, V V^T and the trace of each problem run as on one
+    // model, kGradStreams problems side by side on their own streams and scratch (G, H, alpha, partials)
+    DevBuf dgrad, dalpha, dpart;
+    PoolBuf dG, dH;
+    std::vector<double> hgrad;
+    cudaEvent_t ev_main = nullptr;
+    std::vector<cudaEvent_t> ev_aux;
+    if (grad) {
+        while ((int)ctx->aux.size() < kGradStreams) {
+            cudaStream_t st;
+            PGP_CUDA(ctx, cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+            ctx->aux.push_back(st);
+        }
+        PGP_TRY(alloc<double>(ctx, dgrad, (size_t)chunk * nh));
+        PGP_TRY(alloc<double>(ctx, dalpha, (size_t)kGradStreams * n));
+        PGP_TRY(alloc<double>(ctx, dpart, (size_t)kGradStreams * trace_cta_count(n) * (kMaxHyper + 1)));
+        PGP_TRY(dG.get(ctx, (size_t)kGradStreams * n * ld));
+        PGP_TRY(dH.get(ctx, (size_t)kGradStreams * n * ld));
+        PGP_CUDA(ctx, cudaMemsetAsync(dG.p, 0, sizeof(double) * kGradStreams * n * ld, ctx->stream));
+        hgrad.resize((size_t)chunk * nh);
+        PGP_CUDA(ctx, cudaEventCreateWithFlags(&ev_main, cudaEventDisableTiming));
+        for (int i = 0; i < kGradStreams; ++i) {
+            cudaEvent_t e;
+            PGP_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            ev_aux.push_back(e);
+        }
+    }
+    struct EvGuard {
+        cudaEvent_t& m; std::vector<cudaEvent_t>& a;
+        ~EvGuard() { if (m) cudaEventDestroy(m); for (auto e : a) cudaEventDestroy(e); }
+    } ev_guard{ev_main, ev_aux};
 
     for (int64_t b0 = 0; b0 < B; b0 += chunk) {
         const int bc = (int)std::min<int64_t>(chunk, B - b0);
@@ -1184,6 +1221,43 @@ static int batched_impl(pgp_ctx* ctx, const pgp_kernel_spec* spec, const double*
         PGP_TRY(launch_loglik(ctx, F, n, dres.as<double>()));
         PGP_CUDA(ctx, cudaMemcpyAsync(hres.data(), dres.p, sizeof(double) * bc, cudaMemcpyDeviceToHost, ctx->stream));
         PGP_CUDA(ctx, cudaMemcpyAsync(hinfo.data(), dinfo.p, sizeof(int) * bc, cudaMemcpyDeviceToHost, ctx->stream));
+        if (grad) {
+            cudaStream_t main_s = ctx->stream;
+            PGP_CUDA(ctx, cudaEventRecord(ev_main, main_s));
+            int rc2 = 0;
+            for (int i = 0; i < kGradStreams; ++i) PGP_CUDA(ctx, cudaStreamWaitEvent(ctx->aux[i], ev_main, 0));
+            for (int b = 0; b < bc && !rc2; ++b) {
+                const int si = b % kGradStreams;
+                ctx->stream = ctx->aux[si];
+                Mat Fb, G, H;
+                Fb.p = dF.p + (size_t)b * F.bstride; Fb.ld = ld;
+                G.p = dG.p + (size_t)si * n * ld; G.ld = ld;
+                H.p = dH.p + (size_t)si * n * ld; H.ld = ld;
+                double* alpha = dalpha.as<double>() + (size_t)si * n;
+                rc2 = inv_upper(ctx, G, Fb, n, H);
+                if (!rc2) rc2 = launch_gemv_upper(ctx, G.p, ld, Fb.p + n * ld, n, alpha);
+                if (!rc2) rc2 = syrk_upper_lower(ctx, H, G, n);
+                if (!rc2) {
+                    TraceArgs t;
+                    t.spec = dspec.as<DevSpec>() + b;
+                    t.Z = dZ.as<double>() + (size_t)b * z_doubles(np, d, n);
+                    t.n = n; t.ndim = d; t.n_parts = np; t.nhyper = nk;
+                    t.P = H.p; t.ldp = ld;
+                    t.alpha = alpha;
+                    t.partials = dpart.as<double>() + (size_t)si * trace_cta_count(n) * (kMaxHyper + 1);
+                    t.dlZ = dgrad.as<double>() + (size_t)b * nh;
+                    t.single_type = single_type(spec);
+                    rc2 = launch_trace(ctx, t);
+                }
+            }
+            ctx->stream = main_s;
+            PGP_TRY(rc2);
+            for (int i = 0; i < kGradStreams; ++i) {
+                PGP_CUDA(ctx, cudaEventRecord(ev_aux[i], ctx->aux[i]));
+                PGP_CUDA(ctx, cudaStreamWaitEvent(main_s, ev_aux[i], 0));
+            }
+            PGP_CUDA(ctx, cudaMemcpyAsync(hgrad.data(), dgrad.p, sizeof(double) * bc * nh, cudaMemcpyDeviceToHost, main_s));
+        }
         if (pred) {
             PGP_TRY(launch_scale(ctx, dspec.as<DevSpec>(), dXs.as<double>(), ms, d, np, dZs.as<double>(), bc));
             GramArgs c;
@@ -1217,22 +1291,23 @@ static int batched_impl(pgp_ctx* ctx, const pgp_kernel_spec* spec, const double*
         for (int b = 0; b < bc; ++b) {
             if (lZ) lZ[b0 + b] = hres[b];
             if (info) info[b0 + b] = hinfo[b];
+            if (grad) for (int h = 0; h < nh; ++h) dlZ[(b0 + b) * nh + h] = hgrad[(size_t)b * nh + h];
         }
     }
     return 0;
 }
 
 extern "C" int pgp_batched_loglike(pgp_ctx* ctx, const pgp_kernel_spec* spec, const double* X, const double* y,
-                                   int64_t n, const double* hyps, int64_t B, double* lZ, int32_t* info) {
+                                   int64_t n, const double* hyps, int64_t B, double* lZ, double* dlZ, int32_t* info) {
     if (ctx && !lZ) return ctx->fail(PGP_E_ARG, "null output");
-    return batched_impl(ctx, spec, X, y, n, hyps, B, nullptr, 0, lZ, nullptr, nullptr, info);
+    return batched_impl(ctx, spec, X, y, n, hyps, B, nullptr, 0, lZ, dlZ, nullptr, nullptr, info);
 }
 
 extern "C" int pgp_batched_predict(pgp_ctx* ctx, const pgp_kernel_spec* spec, const double* X, const double* y,
                                    int64_t n, const double* hyps, int64_t B, const double* Xs, int64_t ms,
                                    double* mu, double* s2, int32_t* info) {
     if (ctx && (!Xs || !mu || !s2 || ms < 0)) return ctx->fail(PGP_E_ARG, "null or negative argument");
-    return batched_impl(ctx, spec, X, y, n, hyps, B, Xs, ms, nullptr, mu, s2, info);
+    return batched_impl(ctx, spec, X, y, n, hyps, B, Xs, ms, nullptr, nullptr, mu, s2, info);
 }
 
 // ---------------------------------------------------------------------------

@@ -40,6 +40,7 @@ struct pgp_ctx {
     size_t smem_optin = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;   // panel stream of the lookahead Cholesky (created on first use)
+    std::vector<cudaStream_t> aux;    // extra streams of the batched gradient (independent problems side by side)
     std::vector<cudaEvent_t> sync_events;   // reusable untimed events for cross-stream ordering
     std::string err;
     int64_t launches = 0;

@@ -89,6 +89,9 @@ struct pgp_dist {
     size_t stage_doubles = 0;
     int* d_info = nullptr;                  // per-panel potrf info
     int64_t info_cap = 0;
+    double* d_V = nullptr;                  // (nb, nb): inverse of a panel's diagonal factor; d_Vs: scratch
+    double* d_Vs = nullptr;
+    int64_t v_nb = 0;
     double* d_B = nullptr;                  // gradient: (1 + owned rows, ld)
     size_t b_doubles = 0;
     double* d_part = nullptr;
@@ -168,6 +171,8 @@ extern "C" void pgp_dist_destroy(pgp_dist* d) {
     dev_free(ctx, d->stage[0]);
     dev_free(ctx, d->stage[1]);
     dev_free(ctx, d->d_info);
+    dev_free(ctx, d->d_V);
+    dev_free(ctx, d->d_Vs);
     dev_free(ctx, d->d_B);
     dev_free(ctx, d->d_part);
     dev_free(ctx, d->d_sums);
@@ -250,6 +255,15 @@ extern "C" int pgp_dist_exact_update(pgp_dist* d, pgp_model* m, const double* hy
         }
         d->stage_doubles = need_stage;
     }
+    if (size > 1 && d->v_nb < nb) {
+        PGP_CUDA(ctx, cudaStreamSynchronize(S));
+        dev_free(ctx, d->d_V);
+        dev_free(ctx, d->d_Vs);
+        d->d_V = d->d_Vs = nullptr;
+        PGP_TRY(dev_alloc(ctx, &d->d_V, (size_t)nb * nb));
+        PGP_TRY(dev_alloc(ctx, &d->d_Vs, (size_t)nb * nb));
+        d->v_nb = nb;
+    }
     PGP_TRY(ensure_events(d, (size_t)5 * nblk + 2));
     auto ev_packed = [&](int64_t k) { return d->events[5 * k]; };        // panel k packed (panel stream)
     auto ev_bcast = [&](int64_t k) { return d->events[5 * k + 1]; };     // broadcast of panel k done (comm stream)
@@ -296,6 +310,8 @@ extern "C" int pgp_dist_exact_update(pgp_dist* d, pgp_model* m, const double* hy
         PGP_TRY(launch_gram(ctx, g));
     }
     std::vector<int64_t> applied((size_t)nblk, 0);         // panels [0, applied[j]) are applied to owned panel j
+    static const int64_t group_env = [] { const char* e = getenv("PGP_DIST_GROUP"); return e ? atoll(e) : 0; }();
+    const int64_t group = group_env > 0 ? group_env : std::max<int64_t>(1, 2048 / nb);
 
     // owned panel j -= F[j0:, c_lo:c_hi) F[j0:j0+w, c_lo:c_hi)^T   (rows j0 .. n, the residual row included)
     auto catch_up = [&](int64_t j, int64_t upto) -> int {
@@ -313,19 +329,24 @@ extern "C" int pgp_dist_exact_update(pgp_dist* d, pgp_model* m, const double* hy
         return launch_gemm_nt(ctx, g);
     };
 
-    // owner: bring panel k up to date with panel k - 1, factor it (potrf of its top w x w block, right-solve
-    // of the rows below, residual row included) and pack it -- all on the panel stream; everybody: post the
-    // matching broadcast on the communication stream
+    // The panel chain -- broadcast of panel k -> update of panel k + 1 -> its potrf -> its broadcast -- is the
+    // critical path (per rank and step it outlasts the trailing updates from ~4 GPUs up), so it is kept as
+    // short as the data dependencies allow.  With more than one rank the owner works on a DENSE copy of its
+    // panel (row pitch nb) in the staging buffer it will be broadcast from:
+    //   update      with panel k - 1 read straight from the staging buffer it was received into (no wait for its
+    //               unpacking into F), written to the panel's place in F
+    //   potrf       of the top block only; the rows below as one GEMM with its explicit inverse, written
+    //               DENSE (row pitch nb) into the staging buffer the panel is broadcast from: no pack step
+    //   broadcast   from that buffer; the copy of the solved rows back into the owner's F follows off the chain.
+    // Measured on the way here (8 GPUs, N = 65536, nb = 512; profiles/r02_dist_*.txt): everything in place with
+    // pack after potrf and unpack before the next update 0.58 s; dense panels (pack first) 0.57 s; round 1's
+    // Python-paced schedule 0.51 s.
     auto produce = [&](int64_t k) -> int {
         const int64_t j0 = cols.j0(k), w = cols.w(k), rows = n - j0 + 1;
         const int owner = (int)(k % size);
-        double* buf = size > 1 ? d->stage[k & 1] : nullptr;
-        if (owner == rank) {
-            // the panel stream needs: panel k - 1 in the factor, and the main stream's updates of panel k
-            // (steps <= k - 2) finished; for k = 0 the Gram build
+        if (size == 1) {                      // one rank: in place, panel chain on P
             PGP_CUDA(ctx, cudaStreamWaitEvent(P, k > 0 ? ev_unpacked(k - 1) : ev_start, 0));
             if (k >= 2) PGP_CUDA(ctx, cudaStreamWaitEvent(P, ev_trail(k - 2), 0));
-            if (size > 1 && k >= 2) PGP_CUDA(ctx, cudaStreamWaitEvent(P, ev_bcast(k - 2), 0));   // staging slot free again
             {
                 Swap sw(ctx, P);
                 PGP_TRY(catch_up(k, k));
@@ -334,17 +355,64 @@ extern "C" int pgp_dist_exact_update(pgp_dist* d, pgp_model* m, const double* hy
                 Pm.ld = ld;
                 PGP_TRY(potrf_lower(ctx, Pm, w, rows - w, d->d_info + k));
             }
-            if (size > 1) {
-                PGP_CUDA(ctx, cudaMemcpy2DAsync(buf, w * 8, m->d_F + j0 * ld + j0, ld * 8, w * 8, rows, cudaMemcpyDeviceToDevice, P));
-                PGP_CUDA(ctx, cudaEventRecord(ev_packed(k), P));
-                PGP_CUDA(ctx, cudaStreamWaitEvent(C, ev_packed(k), 0));
-            }
             PGP_CUDA(ctx, cudaEventRecord(ev_fact(k), P));
-        } else if (k >= 2) {
-            PGP_CUDA(ctx, cudaStreamWaitEvent(C, ev_unpacked(k - 2), 0));                 // receiver: slot consumed
+            return 0;
         }
-        if (size == 1) return 0;
-        PGP_NCCL(d, g_nccl.Broadcast(buf, buf, (size_t)rows * w, ncclDouble, owner, d->comm, C));
+        double* buf = d->stage[k & 1];
+        if (owner == rank) {
+            double* Fp = m->d_F + j0 * ld + j0;             // the panel in this rank's replica of the factor
+            PGP_CUDA(ctx, cudaStreamWaitEvent(P, k >= 2 ? ev_trail(k - 2) : ev_start, 0));   // main stream's updates of panel k
+            {
+                Swap sw(ctx, P);
+                if (k >= 1) {
+                    // panel k -= P_{k-1}[rows >= j0] P_{k-1}[block k]^T, P_{k-1} read straight from the staging buffer it
+                    // was received into (dense, pitch nb): no wait for its unpacking into F
+                    PGP_CUDA(ctx, cudaStreamWaitEvent(P, ev_bcast(k - 1), 0));
+                    const double* prev = d->stage[(k - 1) & 1] + (j0 - cols.j0(k - 1)) * nb;
+                    GemmArgs g;
+                    g.A = prev; g.lda = nb;
+                    g.B = prev; g.ldb = nb;
+                    g.C = Fp; g.ldc = ld;
+                    g.M = rows; g.N = w; g.K = cols.w(k - 1);
+                    g.alpha = -1.0; g.beta = 1.0;
+                    g.tri = 1;
+                    PGP_TRY(launch_gemm_nt(ctx, g));
+                    applied[k] = k;
+                }
+                // L11 = chol(top w x w block) only; the rows below are solved as ONE GEMM with the explicit
+                // inverse V = L11^-T (w <= nb columns: 7 launches for the inverse) instead of riding through the
+                // 64-column leaf steps of the recursion (potrf_base + trsm_base + K <= 256 updates on all rows,
+                // ~2 ms per panel at ~8 TFLOP/s: it made every rank's panel work additive to its trailing updates)
+                Mat Pm, V, Vs;
+                Pm.p = Fp; Pm.ld = ld;
+                PGP_TRY(potrf_lower(ctx, Pm, w, 0, d->d_info + k));
+                V.p = d->d_V; V.ld = nb;
+                Vs.p = d->d_Vs; Vs.ld = nb;
+                PGP_CUDA(ctx, cudaMemsetAsync(d->d_V, 0, sizeof(double) * nb * nb, P));
+                PGP_TRY(inv_upper(ctx, V, Pm, w, Vs));
+                if (k >= 2) PGP_CUDA(ctx, cudaStreamWaitEvent(P, ev_unpacked(k - 2), 0));      // staging slot free again
+                GemmArgs x;                                  // X = B V  ->  rows w.. of the staging buffer
+                x.A = Fp + w * ld; x.lda = ld;
+                x.B = d->d_V; x.ldb = nb; x.transB = 1; x.kcol = 1;
+                x.C = buf + w * nb; x.ldc = nb;
+                x.M = rows - w; x.N = w; x.K = w;
+                x.alpha = 1.0; x.beta = 0.0;
+                x.splitk = 1;
+                PGP_TRY(launch_gemm(ctx, x));
+            }
+            PGP_CUDA(ctx, cudaMemcpy2DAsync(buf, nb * 8, Fp, ld * 8, w * 8, w, cudaMemcpyDeviceToDevice, P));   // L11
+            PGP_CUDA(ctx, cudaEventRecord(ev_packed(k), P));
+            PGP_CUDA(ctx, cudaStreamWaitEvent(C, ev_packed(k), 0));
+            // the owner's replica of the factor gets the solved rows off the chain
+            PGP_CUDA(ctx, cudaMemcpy2DAsync(Fp + w * ld, ld * 8, buf + w * nb, nb * 8, w * 8, rows - w, cudaMemcpyDeviceToDevice, P));
+            PGP_CUDA(ctx, cudaEventRecord(ev_fact(k), P));
+        } else {
+            // receiver: the slot was last used by panel k - 2 -- unpacked on the main stream, and read by this
+            // rank's own update of panel k - 1 if it owned that one
+            if (k >= 2) PGP_CUDA(ctx, cudaStreamWaitEvent(C, ev_unpacked(k - 2), 0));
+            if (k >= 1 && (int)((k - 1) % size) == rank) PGP_CUDA(ctx, cudaStreamWaitEvent(C, ev_fact(k - 1), 0));
+        }
+        PGP_NCCL(d, g_nccl.Broadcast(buf, buf, (size_t)rows * nb, ncclDouble, owner, d->comm, C));
         PGP_CUDA(ctx, cudaEventRecord(ev_bcast(k), C));
         return 0;
     };
@@ -355,7 +423,7 @@ extern "C" int pgp_dist_exact_update(pgp_dist* d, pgp_model* m, const double* hy
             PGP_CUDA(ctx, cudaStreamWaitEvent(S, ev_fact(k), 0));
         } else {
             PGP_CUDA(ctx, cudaStreamWaitEvent(S, ev_bcast(k), 0));
-            PGP_CUDA(ctx, cudaMemcpy2DAsync(m->d_F + j0 * ld + j0, ld * 8, d->stage[k & 1], w * 8, w * 8, rows,
+            PGP_CUDA(ctx, cudaMemcpy2DAsync(m->d_F + j0 * ld + j0, ld * 8, d->stage[k & 1], nb * 8, w * 8, rows,
                                             cudaMemcpyDeviceToDevice, S));
         }
         PGP_CUDA(ctx, cudaEventRecord(ev_unpacked(k), S));
@@ -367,8 +435,12 @@ extern "C" int pgp_dist_exact_update(pgp_dist* d, pgp_model* m, const double* hy
     for (int64_t k = 0; k < nblk; ++k) {
         PGP_TRY(consume(k));
         if (k + 1 < nblk) PGP_TRY(produce(k + 1));          // lookahead: the next panel is on its way ...
-        for (int64_t j = k + 2; j < nblk; ++j)              // ... while this step's trailing updates run
-            if ((int)(j % size) == rank) PGP_TRY(catch_up(j, k + 1));
+        // ... while this step's trailing updates run.  Panels further away than the next-but-one are brought
+        // up to date `group` panels at a time: one GEMM with K = group nb instead of `group` GEMMs with
+        // K = nb (a K = 512 update runs at ~25 TFLOP/s, K = 2048 at ~33: at 8 GPUs the ranks are GEMM-bound).
+        for (int64_t j = k + 2; j < nblk; ++j)
+            if ((int)(j % size) == rank && (j == k + 2 || k + 1 - applied[j] >= group))
+                PGP_TRY(catch_up(j, k + 1));
         PGP_CUDA(ctx, cudaEventRecord(ev_trail(k), S));
     }
 

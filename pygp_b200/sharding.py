@@ -141,12 +141,16 @@ def _batched(fn_name, gp, hypers, extra):
     info = np.zeros(B, dtype=np.int32)
     ip = info.ctypes.data_as(C.POINTER(C.c_int32))
     spec = gp._kernel._spec()
-    if fn_name == 'loglike':
+    if fn_name in ('loglike', 'loglike_grad'):
         lZ = np.empty(B)
+        dlZ = np.empty((B, H.shape[1])) if fn_name == 'loglike_grad' else None
         _lib.check(ctx, L.pgp_batched_loglike(ctx.handle, spec, _lib.ptr(Xd), _lib.ptr(yd), len(Xd),
-                                              _lib.ptr(H), B, _lib.ptr(lZ), ip))
+                                              _lib.ptr(H), B, _lib.ptr(lZ), None if dlZ is None else _lib.ptr(dlZ), ip))
         lZ[info != 0] = -np.inf       # not positive definite: zero likelihood
-        return lZ
+        if dlZ is None:
+            return lZ
+        dlZ[info != 0] = 0.0
+        return np.c_[lZ, dlZ]
     Xs = _lib.as_f64(extra, 2)
     mu, s2 = np.empty((B, len(Xs))), np.empty((B, len(Xs)))
     _lib.check(ctx, L.pgp_batched_predict(ctx.handle, spec, _lib.ptr(Xd), _lib.ptr(yd), len(Xd),
@@ -156,22 +160,26 @@ def _batched(fn_name, gp, hypers, extra):
     return mu, s2
 
 
-def sharded_batched_loglike(gp, hypers, group=None, local_fn=None):
+def sharded_batched_loglike(gp, hypers, group=None, local_fn=None, grad=False):
     """log marginal likelihood of `gp`'s data under each row of `hypers`
     ((B, nhyper), full GP vectors), the B problems split across the ranks.
-    `local_fn(hypers_slice) -> (b,)` replaces the device call (host-logic tests)."""
+    grad=True: returns (lZ (B,), dlZ (B, nhyper)) -- the objective of a multi-restart
+    `optimize` (learning/optimization.py:54-62) or of SMC particles in one device call per rank.
+    `local_fn(hypers_slice) -> (b,)` [(b, 1 + nhyper) with grad] replaces the device call
+    (host-logic tests)."""
     rank, size = world(group)
     hypers = np.array(hypers, ndmin=2, dtype=float)
     lo, hi = shard_range(len(hypers), rank, size)
-    fn = local_fn or (lambda h: _batched('loglike', gp, h, None))
-    err, mine = None, np.empty(0)
+    fn = local_fn or (lambda h: _batched('loglike_grad' if grad else 'loglike', gp, h, None))
+    err, mine = None, (np.empty((0, 1 + hypers.shape[1])) if grad else np.empty(0))
     try:
         if hi > lo:
             mine = fn(hypers[lo:hi])
     except Exception as e:                # noqa: BLE001
         err = e
     _raise_together(err, group)
-    return all_gather_rows(np.asarray(mine, dtype=float), len(hypers), group)
+    out = all_gather_rows(np.asarray(mine, dtype=float), len(hypers), group)
+    return (out[:, 0].copy(), out[:, 1:].copy()) if grad else out
 
 
 def sharded_mixture_posterior(gp, hypers, X, group=None, local_fn=None):

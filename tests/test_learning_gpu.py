@@ -122,17 +122,25 @@ def test_batched_loglike_vs_single(spec, n, d, B):
     H = h0 + np.random.RandomState(2).uniform(-0.5, 0.5, (B, len(h0)))
     lZ, info = np.empty(B), np.zeros(B, dtype=np.int32)
     ctx = _lib.context()
+    dlZ = np.empty((B, len(h0)))
     _lib.check(ctx, _lib.lib().pgp_batched_loglike(ctx.handle, k._spec(), _lib.ptr(X), _lib.ptr(y), n,
-                                                   _lib.ptr(H), B, _lib.ptr(lZ),
+                                                   _lib.ptr(H), B, _lib.ptr(lZ), _lib.ptr(dlZ),
                                                    info.ctypes.data_as(C.POINTER(C.c_int32))))
     assert not info.any()
+    lZ_only = np.empty(B)                          # dlZ = NULL: likelihood only, same values
+    _lib.check(ctx, _lib.lib().pgp_batched_loglike(ctx.handle, k._spec(), _lib.ptr(X), _lib.ptr(y), n,
+                                                   _lib.ptr(H), B, _lib.ptr(lZ_only), None,
+                                                   info.ctypes.data_as(C.POINTER(C.c_int32))))
+    nt.assert_array_equal(lZ_only, lZ)
     mu, s2 = np.empty((B, 40)), np.empty((B, 40))
     _lib.check(ctx, _lib.lib().pgp_batched_predict(ctx.handle, k._spec(), _lib.ptr(X), _lib.ptr(y), n,
                                                    _lib.ptr(H), B, _lib.ptr(Xs), 40, _lib.ptr(mu), _lib.ptr(s2),
                                                    info.ctypes.data_as(C.POINTER(C.c_int32))))
     for b in range(B):
         gp.set_hyper(H[b])
-        nt.assert_allclose(lZ[b], gp.loglikelihood(), rtol=1e-13)
+        l1, g1 = gp.loglikelihood(True)
+        nt.assert_allclose(lZ[b], l1, rtol=1e-13)
+        nt.assert_allclose(dlZ[b], g1, rtol=1e-10, atol=1e-10*np.abs(g1).max())      # batched gradient == pgp_exact_loglike
         m1, v1 = gp.posterior(Xs)
         nt.assert_allclose(mu[b], m1, rtol=1e-12, atol=1e-13)
         nt.assert_allclose(s2[b], v1, rtol=1e-12, atol=1e-14)
@@ -162,6 +170,13 @@ def test_sharding_single_rank_uses_device_path():
         o.set_hyper(h)
         ref.append((o.loglikelihood(),) + o.posterior(Xs))
     nt.assert_allclose(lZ, [r[0] for r in ref], rtol=LZ_RTOL)
+    lZg, dlZg = sharding.sharded_batched_loglike(gp, H, grad=True)     # batched gradient vs the oracle, one by one
+    nt.assert_array_equal(lZg, lZ)
+    for h, g in zip(H, dlZg):
+        o = OExactGP(0.1, make_kernel(spec), 0.0)
+        o.add_data(X, y)
+        o.set_hyper(h)
+        assert_grad_close(g, o.loglikelihood(True)[1])
     mu, s2 = sharding.sharded_mixture_posterior(gp, H, Xs)
     mu_ = np.array([r[1] for r in ref])
     s2_ = np.array([r[2] for r in ref])

@@ -25,6 +25,8 @@ def main():
     rank, world, local = int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), int(os.environ['LOCAL_RANK'])
     torch.cuda.set_device(local)
     os.environ['PYGP_B200_DEVICE'] = str(local)
+    if os.environ.get('PGP_DIST_PROF_DUMP'):
+        os.environ['PGP_PROF_DUMP'] = '%s.rank%d' % (os.environ['PGP_DIST_PROF_DUMP'], rank)
     dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     import pygp_b200 as pygp
     from pygp_b200 import sharding, distchol, _lib

@@ -72,7 +72,7 @@ def batched_probe(ctx, L, n, d, B):
 
     def run():
         _lib.check(ctx, L.pgp_batched_loglike(ctx.handle, spec, _lib.ptr(Xc), _lib.ptr(yc), n, _lib.ptr(hyps), B,
-                                              _lib.ptr(lZ), info.ctypes.data_as(_lib._ip)))
+                                              _lib.ptr(lZ), None, info.ctypes.data_as(_lib._ip)))
     run()
     t0 = time.perf_counter()
     run()
