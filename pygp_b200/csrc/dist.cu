@@ -84,6 +84,7 @@ struct pgp_dist {
     int rank = 0, size = 1;
     ncclComm_t comm = nullptr;
     cudaStream_t comm_stream = nullptr;
+    cudaStream_t copy_stream = nullptr;     // unpacking of received panels, off the main stream
     std::vector<cudaEvent_t> events;        // 3 per panel: packed, broadcast done, unpacked
     double* stage[2] = {nullptr, nullptr};  // contiguous send / receive buffers of one panel
     size_t stage_doubles = 0;
@@ -97,6 +98,7 @@ struct pgp_dist {
     double* d_part = nullptr;
     size_t part_doubles = 0;
     double* d_sums = nullptr;               // kMaxHyper + 4
+    int64_t group = 0;                      // trailing-update grouping (0: default)
 };
 
 #define PGP_NCCL(d, call)                                                                      \
@@ -146,8 +148,9 @@ extern "C" int pgp_dist_init(pgp_ctx* ctx, int n_ranks, int rank, const void* id
         if (!rc) {
             int lo = 0, hi = 0;
             cudaDeviceGetStreamPriorityRange(&lo, &hi);
-            if (cudaStreamCreateWithPriority(&d->comm_stream, cudaStreamNonBlocking, hi) != cudaSuccess)
-                rc = ctx->fail(PGP_E_CUDA, "cannot create the communication stream");
+            if (cudaStreamCreateWithPriority(&d->comm_stream, cudaStreamNonBlocking, hi) != cudaSuccess ||
+                cudaStreamCreateWithPriority(&d->copy_stream, cudaStreamNonBlocking, hi) != cudaSuccess)
+                rc = ctx->fail(PGP_E_CUDA, "cannot create the communication streams");
         }
     }
     if (!rc) rc = dev_alloc(ctx, &d->d_sums, (size_t)kMaxHyper + 4);
@@ -167,6 +170,7 @@ extern "C" void pgp_dist_destroy(pgp_dist* d) {
     if (d->comm_stream) cudaStreamSynchronize(d->comm_stream);
     if (d->comm) g_nccl.CommDestroy(d->comm);
     if (d->comm_stream) cudaStreamDestroy(d->comm_stream);
+    if (d->copy_stream) { cudaStreamSynchronize(d->copy_stream); cudaStreamDestroy(d->copy_stream); }
     for (cudaEvent_t e : d->events) cudaEventDestroy(e);
     dev_free(ctx, d->stage[0]);
     dev_free(ctx, d->stage[1]);
@@ -177,6 +181,14 @@ extern "C" void pgp_dist_destroy(pgp_dist* d) {
     dev_free(ctx, d->d_part);
     dev_free(ctx, d->d_sums);
     delete d;
+}
+
+// tuning knob of pgp_dist_exact_update: far block columns are updated every `group` steps with `group` panels
+// at a time (0 = default)
+extern "C" int pgp_dist_set_group(pgp_dist* d, int64_t group) {
+    if (!d || group < 0) return PGP_E_ARG;
+    d->group = group;
+    return 0;
 }
 
 extern "C" int pgp_dist_rank(const pgp_dist* d) { return d ? d->rank : -1; }
@@ -231,7 +243,7 @@ extern "C" int pgp_dist_exact_update(pgp_dist* d, pgp_model* m, const double* hy
     const double sn2 = std::exp(hyp[0] * 2), mean = hyp[1 + nk];
     PGP_TRY(compile_spec(&m->spec, hyp + 1, sn2, mean, &m->hspec, &ctx->err));
     m->factored = false;
-    cudaStream_t S = ctx->stream, C = d->comm_stream;
+    cudaStream_t S = ctx->stream, C = d->comm_stream, U = d->copy_stream;
     const int64_t n = m->n, ld = m->ld;
     const int rank = d->rank, size = d->size;
     Cols cols{n, nb, ceil_div(n, nb)};
@@ -268,7 +280,7 @@ extern "C" int pgp_dist_exact_update(pgp_dist* d, pgp_model* m, const double* hy
     auto ev_packed = [&](int64_t k) { return d->events[5 * k]; };        // panel k packed (panel stream)
     auto ev_bcast = [&](int64_t k) { return d->events[5 * k + 1]; };     // broadcast of panel k done (comm stream)
     auto ev_unpacked = [&](int64_t k) { return d->events[5 * k + 2]; };  // panel k in the replicated factor (main)
-    auto ev_trail = [&](int64_t k) { return d->events[5 * k + 3]; };     // trailing updates of step k enqueued (main)
+    auto ev_trail = [&](int64_t k) { return d->events[5 * k + 3]; };     // step k: panel k + 2 is up to date with panels <= k (main)
     auto ev_fact = [&](int64_t k) { return d->events[5 * k + 4]; };      // panel k factored (panel stream)
     cudaEvent_t ev_start = d->events[5 * nblk];
     // The panel chain (update of the next panel, its potrf, the pack) runs on a second, high-priority
@@ -310,8 +322,11 @@ extern "C" int pgp_dist_exact_update(pgp_dist* d, pgp_model* m, const double* hy
         PGP_TRY(launch_gram(ctx, g));
     }
     std::vector<int64_t> applied((size_t)nblk, 0);         // panels [0, applied[j]) are applied to owned panel j
-    static const int64_t group_env = [] { const char* e = getenv("PGP_DIST_GROUP"); return e ? atoll(e) : 0; }();
-    const int64_t group = group_env > 0 ? group_env : std::max<int64_t>(1, 2048 / nb);
+    // trailing-update grouping (see the main loop): d->group if set (pgp_dist_set_group), else PGP_DIST_GROUP, else a
+    // default by rank count
+    const char* ge = getenv("PGP_DIST_GROUP");
+    const int64_t group_env = ge ? atoll(ge) : 0;
+    const int64_t group = d->group > 0 ? d->group : group_env > 0 ? group_env : std::max<int64_t>(1, 1024 / nb);
 
     // owned panel j -= F[j0:, c_lo:c_hi) F[j0:j0+w, c_lo:c_hi)^T   (rows j0 .. n, the residual row included)
     auto catch_up = [&](int64_t j, int64_t upto) -> int {
@@ -416,17 +431,25 @@ extern "C" int pgp_dist_exact_update(pgp_dist* d, pgp_model* m, const double* hy
         PGP_CUDA(ctx, cudaEventRecord(ev_bcast(k), C));
         return 0;
     };
-    // everybody: panel k is in the replicated factor before the main stream reads it
+    // everybody: panel k is in the replicated factor before the main stream reads it.  Receivers unpack it on
+    // the copy stream: enqueued on the main stream the copy (and with it the release of the staging slot, and
+    // the whole chain) waited behind that stream's queued trailing updates -- tens of milliseconds once those
+    // are batched into one launch per step.
     auto consume = [&](int64_t k) -> int {
         const int64_t j0 = cols.j0(k), w = cols.w(k), rows = n - j0 + 1;
         if ((int)(k % size) == rank) {
             PGP_CUDA(ctx, cudaStreamWaitEvent(S, ev_fact(k), 0));
+            PGP_CUDA(ctx, cudaEventRecord(ev_unpacked(k), S));
         } else {
-            PGP_CUDA(ctx, cudaStreamWaitEvent(S, ev_bcast(k), 0));
+            PGP_CUDA(ctx, cudaStreamWaitEvent(U, ev_bcast(k), 0));
+            // the region of F it lands in was last touched by the main stream's updates of panel k (step k - 2)
+            if (k >= 2) PGP_CUDA(ctx, cudaStreamWaitEvent(U, ev_trail(k - 2), 0));
+            else PGP_CUDA(ctx, cudaStreamWaitEvent(U, ev_start, 0));
             PGP_CUDA(ctx, cudaMemcpy2DAsync(m->d_F + j0 * ld + j0, ld * 8, d->stage[k & 1], nb * 8, w * 8, rows,
-                                            cudaMemcpyDeviceToDevice, S));
+                                            cudaMemcpyDeviceToDevice, U));
+            PGP_CUDA(ctx, cudaEventRecord(ev_unpacked(k), U));
+            PGP_CUDA(ctx, cudaStreamWaitEvent(S, ev_unpacked(k), 0));
         }
-        PGP_CUDA(ctx, cudaEventRecord(ev_unpacked(k), S));
         return 0;
     };
 
@@ -435,13 +458,45 @@ extern "C" int pgp_dist_exact_update(pgp_dist* d, pgp_model* m, const double* hy
     for (int64_t k = 0; k < nblk; ++k) {
         PGP_TRY(consume(k));
         if (k + 1 < nblk) PGP_TRY(produce(k + 1));          // lookahead: the next panel is on its way ...
-        // ... while this step's trailing updates run.  Panels further away than the next-but-one are brought
-        // up to date `group` panels at a time: one GEMM with K = group nb instead of `group` GEMMs with
-        // K = nb (a K = 512 update runs at ~25 TFLOP/s, K = 2048 at ~33: at 8 GPUs the ranks are GEMM-bound).
-        for (int64_t j = k + 2; j < nblk; ++j)
-            if ((int)(j % size) == rank && (j == k + 2 || k + 1 - applied[j] >= group))
-                PGP_TRY(catch_up(j, k + 1));
-        PGP_CUDA(ctx, cudaEventRecord(ev_trail(k), S));
+        // ... while this step's trailing updates run.  The next-but-one panel is brought fully up to date (it
+        // is factored two steps from now); the panels further away are updated every `group` steps, `group`
+        // panels at a time and ALL OF THEM IN ONE LAUNCH (ragged batch: member q starts size nb rows further
+        // down): K = group nb instead of nb, and no per-panel wave tails or launch gaps -- a lone
+        // M x 512 x 512 update runs at ~25 TFLOP/s, M x 1024 x 2048 at ~33 (profiles/r02_gemm_update_shapes.txt),
+        // and with per-panel launches the ranks were GEMM-bound at ~24 TFLOP/s.
+        for (int64_t j = k + 2; j < std::min(k + 3, nblk); ++j)
+            if ((int)(j % size) == rank) PGP_TRY(catch_up(j, k + 1));
+        PGP_CUDA(ctx, cudaEventRecord(ev_trail(k), S));     // what the panel chain of step k + 2 waits for -- not the bulk below
+        if ((k + 1) % group == 0) {
+            const int64_t upto = k + 1, lo = upto - group;
+            int64_t jf = k + 3;
+            while (jf < nblk && (int)(jf % size) != rank) ++jf;
+            int64_t cnt = 0;
+            for (int64_t j = jf; j < nblk; j += size) {
+                if (applied[j] != lo) { cnt = -1; break; }          // (cannot happen: far panels move in lockstep)
+                if (cols.w(j) == nb) ++cnt;
+            }
+            if (cnt < 0) {
+                for (int64_t j = jf; j < nblk; j += size) PGP_TRY(catch_up(j, upto));
+            } else {
+                if (cnt > 0) {
+                    const int64_t j0 = cols.j0(jf), c_lo = cols.j0(lo), c_hi = cols.j0(upto - 1) + cols.w(upto - 1);
+                    GemmArgs g;
+                    g.A = m->d_F + j0 * ld + c_lo; g.lda = ld; g.strideA = (int64_t)size * nb * ld;
+                    g.B = g.A; g.ldb = ld; g.strideB = g.strideA;
+                    g.C = m->d_F + j0 * ld + j0; g.ldc = ld; g.strideC = (int64_t)size * nb * (ld + 1);
+                    g.M = n - j0 + 1; g.N = nb; g.K = c_hi - c_lo;
+                    g.alpha = -1.0; g.beta = 1.0;
+                    g.tri = 1;
+                    g.batch = (int)cnt;
+                    g.ragged_mstep = (int64_t)size * nb;
+                    PGP_TRY(launch_gemm_nt(ctx, g));
+                    for (int64_t q = 0; q < cnt; ++q) applied[jf + q * size] = upto;
+                }
+                const int64_t jl = jf + cnt * size;                 // a ragged last block column, if owned
+                if (jl < nblk && cols.w(jl) != nb) PGP_TRY(catch_up(jl, upto));
+            }
+        }
     }
 
     // lZ from the complete factor; info: first failing minor over all panels and ranks

@@ -100,6 +100,10 @@ __global__ void __launch_bounds__(WM * WN * 32, C::BM == 64 ? 2 : 1) gemm_kernel
     }
     const int64_t m0 = (int64_t)tile_m * BM;
     const int64_t n0 = (int64_t)tile_n * BN;
+    if (STAIR && a.ragged_mstep) {          // ragged batch: this member's row count
+        a.M -= (int64_t)blockIdx.z * a.ragged_mstep;
+        if (m0 >= a.M) return;
+    }
     if (a.tri && n0 > m0 + BM - 1 + a.tri_off) return;
     // staircase operands (gemm.cuh): first column at which this tile row's block exists, relative to the
     // operand's column 0 (32-bit arithmetic: the prologue must not cost the main loop registers)
@@ -390,7 +394,7 @@ namespace {
 template <int WM, int WN, class C, bool TA, bool TB>
 int launch_variant(pgp_ctx* ctx, const GemmArgs& a, int64_t tm, int64_t tn) {
     dim3 grid((unsigned)(tm * tn), (unsigned)std::max(a.splitk, 1), a.batch);
-    if (a.stair) {
+    if (a.stair || a.ragged_mstep) {
         if (TA) return ctx->fail(PGP_E_ARG, "gemm: staircase operands need A stored (M, K)");
         auto kern = gemm_kernel<WM, WN, C, false, TB, true>;
         PGP_TRY(ensure_dyn_smem(ctx, kern, C::SMEM));
@@ -439,7 +443,7 @@ int launch_gemm(pgp_ctx* ctx, const GemmArgs& a_in) {
     // (FITC: p x p results contracted over n >> p): partials go to a workspace
     // and are summed in a fixed order
     a.splitk = 1;
-    if (a_in.splitk != 1 && !a.krow && !a.kcol && !a.stair && a.batch == 1) {
+    if (a_in.splitk != 1 && !a.krow && !a.kcol && !a.stair && !a.ragged_mstep && a.batch == 1) {
         int64_t tiles = count_tiles(BM);
         int64_t want = a_in.splitk > 1 ? a_in.splitk : (2 * ctx->sm_count) / std::max<int64_t>(tiles, 1);
         int64_t max_by_k = a.K / 2048;  // keep >= 2048 contraction steps per slice
@@ -485,8 +489,14 @@ int launch_gemm(pgp_ctx* ctx, const GemmArgs& a_in) {
         }
         flops += 2.0 * rows * cols * klen;
     }
+    double batch_flops = flops * a.batch;
+    if (a.ragged_mstep) {       // member b has M - b mstep rows (rectangular count; tri only trims the top block)
+        batch_flops = 0.0;
+        for (int b = 0; b < a.batch; ++b)
+            batch_flops += 2.0 * (double)std::max<int64_t>(a.M - b * a.ragged_mstep, 0) * (double)a.N * (double)a.K;
+    }
     {
-        Launch L(ctx, PC_GEMM, flops * a.batch);
+        Launch L(ctx, PC_GEMM, batch_flops);
         L.shape(a.M, a.N, a.K, a.tri | (a.krow << 1) | (a.transA << 2) | (a.transB << 3) | (a.kcol << 4) | (a.batch << 8));
         int rc;
         if (small) {

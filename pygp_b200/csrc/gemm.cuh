@@ -38,6 +38,9 @@ struct GemmArgs {
     int64_t stair_front = 0, stair_nb = 1, stair_first = 0, stair_step = 0, stair_off = 0;
     int batch = 1;
     int64_t strideA = 0, strideB = 0, strideC = 0;
+    // ragged batch: member b has M - b * ragged_mstep rows (the block columns of one trailing update of the
+    // distributed factorisation: equal width, each starting ragged_mstep rows further down)
+    int64_t ragged_mstep = 0;
     // general forms (launch_gemm): transA -> A is stored (K x M) row-major,
     // transB -> B is stored (K x N) row-major, i.e.
     //   NT (0,0): C = A B^T     NN (0,1): C = A B     TN (1,1): C = A^T B

@@ -48,6 +48,27 @@ def main():
         mk = lambda: pygp.inference.ExactGP(pygp.likelihoods.Gaussian(0.1), pygp.kernels.SE(1.0, [0.5*np.sqrt(d)]*d), 0.0)
     y = np.sin(3*X.sum(1)) + 0.1*rng.randn(n)
     Xs = np.random.RandomState(1).rand(4096, d)*(64 if kern == 'c5' else 1)
+    if os.environ.get('PGP_DIST_SWEEP'):
+        # timing sweep only: "nb:group,nb:group,..." -- distributed evaluation per setting, no one-GPU reference
+        g2 = mk()
+        g2.add_data(X, y)
+        comm = distchol.communicator()
+        for item in os.environ['PGP_DIST_SWEEP'].split(','):
+            nb_s, grp = (int(v) for v in item.split(':'))
+            os.environ['PGP_DIST_GROUP_NOW'] = str(grp)
+            for rep in range(2):
+                dist.barrier()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                distchol.distributed_update(g2, nb=nb_s, group_size=grp)
+                ctx.sync()
+                t_u = comm.allreduce([time.perf_counter() - t0], 'max')[0]
+                t0 = time.perf_counter()
+                lZs, dlZs = distchol.distributed_loglikelihood(g2, True, nb=nb_s)
+                t_g = comm.allreduce([time.perf_counter() - t0], 'max')[0]
+            say(check='dist_sweep', kernel=kern, n=n, world=world, nb=nb_s, group=grp, update_s=t_u, grad_s=t_g, lZ=lZs)
+        dist.destroy_process_group()
+        return
     gp = mk()
     gp.add_data(X, y)                      # single-GPU factorisation on every rank (reference)
     ctx.sync()
