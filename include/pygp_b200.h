@@ -273,7 +273,7 @@ int pgp_dev_potrf(pgp_ctx* ctx, double* d_F, int64_t n, int64_t ld, int64_t extr
 
 /* the short FP64 elementary functions of the covariance epilogues (csrc/fastmath.cuh),
  * elementwise on host arrays, for their accuracy sweep against libm
- * (tests/test_fastmath_gpu.py).  which: 0 exp, 1 sqrt, 2 exp clamped at -708. */
+ * (tests/test_fastmath_gpu.py).  which: 0 exp, 1 sqrt, 2 exp clamped at -708, 3 log (x >= 1), 4 |sin|. */
 int pgp_dev_fastmath(pgp_ctx* ctx, int which, const double* x, int64_t n, double* out);
 
 #ifdef __cplusplus

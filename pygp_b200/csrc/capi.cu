@@ -1382,7 +1382,7 @@ extern "C" int pgp_dev_potrf(pgp_ctx* ctx, double* d_F, int64_t n, int64_t ld, i
 
 extern "C" int pgp_dev_fastmath(pgp_ctx* ctx, int which, const double* x, int64_t n, double* out) {
     if (!ctx) return PGP_E_ARG;
-    if (!x || !out || n < 0 || which < 0 || which > 2) return ctx->fail(PGP_E_ARG, "bad argument");
+    if (!x || !out || n < 0 || which < 0 || which > 4) return ctx->fail(PGP_E_ARG, "bad argument");
     if (n == 0) return 0;
     PGP_TRY(set_device(ctx));
     DevBuf dx, dout;

@@ -42,12 +42,14 @@ struct Tile {
     __device__ int col(int b) const { return 2 * tx + 32 * (b >> 1) + (b & 1); }
 };
 
-// ---- shared memory: [exp table 512 B][mbarrier 16 B][DevSpecHdr][Zs1][Zs2][extra] -----------
+// ---- shared memory: [exp table 512 B][log table 2 KB][mbarrier 16 B][DevSpecHdr][Zs1][Zs2][extra] -----------
 constexpr size_t kHdrBytes = ((sizeof(DevSpecHdr) + 15) / 16) * 16;
-constexpr size_t kSmemFixed = fm::kExpTabDoubles * sizeof(double) + 16 + kHdrBytes;
+constexpr size_t kTabBytes = (fm::kExpTabDoubles + fm::kLogTabDoubles) * sizeof(double);
+constexpr size_t kSmemFixed = kTabBytes + 16 + kHdrBytes;
 
 struct Smem {
     double* tab;
+    double* ltab;
     uint64_t* bar;
     DevSpecHdr* S;
     double* Zs1;
@@ -55,8 +57,9 @@ struct Smem {
     double* extra;
     __device__ Smem(unsigned char* raw, int npd) {
         tab = reinterpret_cast<double*>(raw);
-        bar = reinterpret_cast<uint64_t*>(raw + fm::kExpTabDoubles * sizeof(double));
-        S = reinterpret_cast<DevSpecHdr*>(raw + fm::kExpTabDoubles * sizeof(double) + 16);
+        ltab = tab + fm::kExpTabDoubles;
+        bar = reinterpret_cast<uint64_t*>(raw + kTabBytes);
+        S = reinterpret_cast<DevSpecHdr*>(raw + kTabBytes + 16);
         Zs1 = reinterpret_cast<double*>(raw + kSmemFixed);
         Zs2 = Zs1 + npd * kTile;
         extra = Zs2 + npd * kTile;
@@ -128,7 +131,7 @@ __device__ __forceinline__ void stage_wait(const Smem& sm, bool bulk, uint32_t& 
 // Once per kernel: mbarrier, first tile's copies, then -- while they fly -- the exp table and (composite
 // kernels only: the tree interpreter indexes it at random) the spec header.  Single-leaf kernels read the
 // two scalars they need straight from the global spec instead of copying 800 bytes per CTA.
-template <bool HDR>
+template <bool HDR, bool LOGTAB = false>
 __device__ __forceinline__ void smem_init_and_issue(const Smem& sm, const DevSpec* spec, const double* Z1, const double* Z2,
                                                     int64_t zd1, int64_t zd2, int64_t i0, int64_t j0, int npd, bool bulk) {
     if (bulk && threadIdx.x == 0) mbar_init(sm.bar, 1);      // init + fence by the thread that arms it
@@ -140,7 +143,8 @@ __device__ __forceinline__ void smem_init_and_issue(const Smem& sm, const DevSpe
         for (int i = threadIdx.x; i < nwords; i += kThreads) d[i] = s[i];
     }
     fm::load_exp_tab(sm.tab, threadIdx.x, kThreads);
-    __syncthreads();                                          // table / header / mbarrier init visible to all
+    if (LOGTAB) fm::load_log_tab(sm.ltab, threadIdx.x, kThreads);
+    __syncthreads();                                          // tables / header / mbarrier init visible to all
 }
 
 // bulk copies need 16-byte aligned sources: base pointers and every (leaf, dim) row
@@ -156,15 +160,35 @@ __device__ __forceinline__ void tri_decode(int64_t idx, int* ti, int* tj) {
 }
 
 // ---- one leaf at one entry ------------------------------------------------------------------------
-constexpr bool is_fast_type(int t) { return t == PGP_SE || (t >= PGP_MATERN1 && t <= PGP_MATERN5); }
+// value kernels with a fastmath.cuh epilogue (every leaf type); gradients: SE / Matern only
+constexpr bool is_fast_type(int t) { return t >= PGP_SE && t <= PGP_RQ; }
+constexpr bool is_fast_grad_type(int t) { return t == PGP_SE || (t >= PGP_MATERN1 && t <= PGP_MATERN5); }
 
-// covariance only, SE / Matern through fastmath.cuh.  `bad` is raised when the fast exp left the
-// normal range; the caller then redoes its micro-tile with the library (slow_redo).
+// covariance only, through fastmath.cuh.  D is the squared distance -- except for the Periodic leaf
+// (ndim == 1), which takes |x1 - x2| itself: that IS the reference's sqrt(sqdist) to the bit
+// (periodic.py:54), where any sqrt of ours could be an ulp off, an ulp that pi / p amplifies.
+// `bad` is raised when an argument left the fast functions' range; the caller then redoes its micro-tile
+// with the library (slow_redo).
 template <int PTYPE>
-__device__ __forceinline__ double fast_value(double two_logsf, double D, const double* tab, int& bad) {
-    if (PTYPE == PGP_SE) return fm::exp_tab(fma(D, -0.5, two_logsf), tab, bad);
+__device__ __forceinline__ double fast_value(const DevPart& p, double D, const double* tab, const double* ltab, int& bad) {
+    if (PTYPE == PGP_SE) return fm::exp_tab(fma(D, -0.5, p.two_logsf), tab, bad);
+    if (PTYPE == PGP_RQ) {
+        // rq.py:56-63: sf2 (1 + D / (2 alpha))^-alpha = exp(2 log sf - alpha log E)
+        const double E = fma(D, p.q1, 1.0);
+        const double lg = fm::log_ge1_tab(E, ltab, bad);
+        return fm::exp_tab(fma(-p.p0, lg, p.two_logsf), tab, bad);
+    }
+    if (PTYPE == PGP_PERIODIC) {
+        // periodic.py:53-59: sf2 exp(-2 (sin(r pi / p) / ell)^2); the quotient (r pi) / p is rounded as the
+        // division is (one Newton correction of a (1 / p)), the sine's sign is irrelevant
+        const double a = D * kPi;
+        const double q0 = a * p.q1;
+        const double Dp = fma(fma(-q0, p.p1, a), p.q1, q0);
+        const double R = fm::sin_unsigned_cw(Dp, bad) * p.q0;
+        return fm::exp_tab(fma(-2.0 * R, R, p.two_logsf), tab, bad);
+    }
     const double r = fm::sqrt_pos(D);
-    const double S = fm::exp_tab(two_logsf - r, tab, bad);
+    const double S = fm::exp_tab(p.two_logsf - r, tab, bad);
     if (PTYPE == PGP_MATERN1) return S;
     if (PTYPE == PGP_MATERN3) return fma(S, r, S);
     return S * fma(r, fma(r, fm::kFmC[5], 1.0), 1.0);
@@ -303,6 +327,20 @@ __device__ __forceinline__ double composite_gradxy(const DevSpecHdr& S, const De
     return node[S.n_nodes - 1].xy;
 }
 
+// |x1 - x2| of a thread's 4 x 4 micro-tile for a one-dimensional leaf (the Periodic kernel's distance)
+__device__ __forceinline__ void micro_absdiff(const double* Zs1, const double* Zs2, const Tile& t, double (&D)[4][4]) {
+    double zi[4], zj[4];
+#pragma unroll
+    for (int x = 0; x < 4; ++x) zi[x] = Zs1[t.row(x)];
+    const double2 q0 = *reinterpret_cast<const double2*>(&Zs2[2 * t.tx]);
+    const double2 q1 = *reinterpret_cast<const double2*>(&Zs2[2 * t.tx + 32]);
+    zj[0] = q0.x; zj[1] = q0.y; zj[2] = q1.x; zj[3] = q1.y;
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y) D[x][y] = fabs(zi[x] - zj[y]);
+}
+
 // squared distances of a thread's 4 x 4 micro-tile for one leaf (rows of Zs: [dim][64])
 __device__ __forceinline__ void micro_dist(const double* Zs1, const double* Zs2, int ndim, const Tile& t,
                                            double (&D)[4][4]) {
@@ -332,24 +370,20 @@ __device__ __forceinline__ void micro_dist(const double* Zs1, const double* Zs2,
 // One leaf for the thread's whole micro-tile: 16 distances, then ONE warp-uniform switch on the
 // leaf type around a 16-entry epilogue loop -- instead of the per-entry tree interpreter, whose
 // local arrays and rolled loops ran the SE + Periodic Gram build at 1.0 TB/s (round 1).
-__device__ __noinline__ double lib_value(const DevPart& part, double D) {
-    PartVal v;
-    part_eval<false>(part, D, v);
-    return v.K;
-}
-
 __device__ __forceinline__ void leaf_vec(const DevPart& part, const double* Zs1, const double* Zs2, int ndim,
-                                         const Tile& t, const double* tab, double (&K)[4][4], int& bad) {
-    micro_dist(Zs1, Zs2, ndim, t, K);
-#define PGP_LEAF_LOOP(EXPR)                              \
+                                         const Tile& t, const double* tab, const double* ltab, double (&K)[4][4], int& bad) {
+    if (part.type == PGP_PERIODIC) micro_absdiff(Zs1, Zs2, t, K);
+    else micro_dist(Zs1, Zs2, ndim, t, K);
+#define PGP_LEAF_LOOP(T)                                 \
     _Pragma("unroll") for (int x = 0; x < 4; ++x)        \
-        _Pragma("unroll") for (int y = 0; y < 4; ++y) { const double D = K[x][y]; K[x][y] = (EXPR); }
+        _Pragma("unroll") for (int y = 0; y < 4; ++y) K[x][y] = fast_value<T>(part, K[x][y], tab, ltab, bad);
     switch (part.type) {
-        case PGP_SE: PGP_LEAF_LOOP(fast_value<PGP_SE>(part.two_logsf, D, tab, bad)) break;
-        case PGP_MATERN1: PGP_LEAF_LOOP(fast_value<PGP_MATERN1>(part.two_logsf, D, tab, bad)) break;
-        case PGP_MATERN3: PGP_LEAF_LOOP(fast_value<PGP_MATERN3>(part.two_logsf, D, tab, bad)) break;
-        case PGP_MATERN5: PGP_LEAF_LOOP(fast_value<PGP_MATERN5>(part.two_logsf, D, tab, bad)) break;
-        default: PGP_LEAF_LOOP(lib_value(part, D)) break;     // Periodic / RQ: library sincos / pow
+        case PGP_SE: PGP_LEAF_LOOP(PGP_SE) break;
+        case PGP_MATERN1: PGP_LEAF_LOOP(PGP_MATERN1) break;
+        case PGP_MATERN3: PGP_LEAF_LOOP(PGP_MATERN3) break;
+        case PGP_MATERN5: PGP_LEAF_LOOP(PGP_MATERN5) break;
+        case PGP_PERIODIC: PGP_LEAF_LOOP(PGP_PERIODIC) break;
+        default: PGP_LEAF_LOOP(PGP_RQ) break;
     }
 #undef PGP_LEAF_LOOP
 }
@@ -364,11 +398,12 @@ __device__ __forceinline__ void vec_fold(double (&acc)[4][4], const double (&v)[
 
 // value of a depth <= 2 tree on the micro-tile, folding children in the order tree_forward does
 __device__ __forceinline__ void composite_vec(const DevSpecHdr& S, const double* Zs1, const double* Zs2, int ndim,
-                                              const Tile& t, const double* tab, double (&res)[4][4], int& bad) {
+                                              const Tile& t, const double* tab, const double* ltab, double (&res)[4][4],
+                                              int& bad) {
     const int root = S.n_nodes - 1;
     if (S.node_kind[root] == NK_LEAF) {
         const int p = S.node_leaf[root];
-        leaf_vec(S.parts[p], Zs1 + p * ndim * kTile, Zs2 + p * ndim * kTile, ndim, t, tab, res, bad);
+        leaf_vec(S.parts[p], Zs1 + p * ndim * kTile, Zs2 + p * ndim * kTile, ndim, t, tab, ltab, res, bad);
         return;
     }
     const int rkind = S.node_kind[root];
@@ -378,7 +413,7 @@ __device__ __forceinline__ void composite_vec(const DevSpecHdr& S, const double*
         const int cn = rc[c];
         if (S.node_kind[cn] == NK_LEAF) {
             const int p = S.node_leaf[cn];
-            leaf_vec(S.parts[p], Zs1 + p * ndim * kTile, Zs2 + p * ndim * kTile, ndim, t, tab, v, bad);
+            leaf_vec(S.parts[p], Zs1 + p * ndim * kTile, Zs2 + p * ndim * kTile, ndim, t, tab, ltab, v, bad);
             vec_fold(res, v, rkind, c == 0);
         } else {
             double sub[4][4];
@@ -386,7 +421,7 @@ __device__ __forceinline__ void composite_vec(const DevSpecHdr& S, const double*
             const int* gc = S.child + S.node_child0[cn];
             for (int g = 0; g < S.node_nchild[cn]; ++g) {
                 const int p = S.node_leaf[gc[g]];
-                leaf_vec(S.parts[p], Zs1 + p * ndim * kTile, Zs2 + p * ndim * kTile, ndim, t, tab, v, bad);
+                leaf_vec(S.parts[p], Zs1 + p * ndim * kTile, Zs2 + p * ndim * kTile, ndim, t, tab, ltab, v, bad);
                 vec_fold(sub, v, ckind, g == 0);
             }
             vec_fold(res, sub, rkind, c == 0);
@@ -489,7 +524,7 @@ __device__ __noinline__ void slow_redo(const DevSpecHdr* S, const double* Zs1, c
 }
 
 template <int PTYPE, int MODE>
-__global__ void __launch_bounds__(kThreads, (MODE == 0 && is_fast_type(PTYPE)) ? 4 : (MODE == 0 && PTYPE < 0) ? 2 : 1) gram_kernel(GramKArgs a) {
+__global__ void __launch_bounds__(kThreads, (MODE == 0 && is_fast_grad_type(PTYPE)) ? 4 : (MODE == 0 && (PTYPE == PGP_RQ || PTYPE == PGP_PERIODIC)) ? 3 : (MODE == 0 && PTYPE < 0) ? 2 : 1) gram_kernel(GramKArgs a) {
     constexpr bool GRAD1 = MODE == 1;
     constexpr bool GRADX = MODE == 2;
     constexpr bool GRADXY = MODE == 3;      // composite path only (PTYPE < 0)
@@ -507,7 +542,7 @@ __global__ void __launch_bounds__(kThreads, (MODE == 0 && is_fast_type(PTYPE)) ?
 
     // composites keep the header in shared memory; a single leaf reads its scalars from the global spec
     const DevSpecHdr* S = PTYPE < 0 ? sm.S : &a.spec[b].h;
-    smem_init_and_issue<(PTYPE < 0)>(sm, a.spec + b, a.Z1 + (int64_t)b * npd * a.zd1, a.Z2 + (int64_t)b * npd * a.zd2,
+    smem_init_and_issue<(PTYPE < 0), (MODE == 0 && (PTYPE < 0 || PTYPE == PGP_RQ))>(sm, a.spec + b, a.Z1 + (int64_t)b * npd * a.zd1, a.Z2 + (int64_t)b * npd * a.zd2,
                                    a.zd1, a.zd2, i0, j0, npd, a.bulk);
     uint32_t phase = 0;
 
@@ -516,7 +551,6 @@ __global__ void __launch_bounds__(kThreads, (MODE == 0 && is_fast_type(PTYPE)) ?
     int gpart = 0, gkind = 0, gdim = 0;
     if (GRAD1) classify_hyper(*S, a.hidx, &gpart, &gkind, &gdim);
     const double noise = a.add_noise ? S->sn2 : 0.0;
-    const double two_logsf = S->parts[0].two_logsf;
     stage_wait(sm, a.bulk, phase);
     const bool diag_noise = a.add_noise && i0 == j0;     // tile-uniform: off the diagonal tiles nothing is added
     const int xdim = a.xdim;
@@ -528,7 +562,8 @@ __global__ void __launch_bounds__(kThreads, (MODE == 0 && is_fast_type(PTYPE)) ?
 
     if (PTYPE >= 0) {
         double D[4][4];
-        micro_dist(sm.Zs1, sm.Zs2, ndim, t, D);
+        if (FAST && PTYPE == PGP_PERIODIC) micro_absdiff(sm.Zs1, sm.Zs2, t, D);
+        else micro_dist(sm.Zs1, sm.Zs2, ndim, t, D);
         const DevPart part = S->parts[0];
 #pragma unroll
         for (int x = 0; x < 4; ++x) {
@@ -536,7 +571,7 @@ __global__ void __launch_bounds__(kThreads, (MODE == 0 && is_fast_type(PTYPE)) ?
 #pragma unroll
             for (int y = 0; y < 4; ++y) {
                 if (FAST) {
-                    v[y] = fast_value<PTYPE>(two_logsf, D[x][y], sm.tab, bad);
+                    v[y] = fast_value<PTYPE>(part, D[x][y], sm.tab, sm.ltab, bad);
                 } else {
                     PartVal pv;
                     leaf_eval<PTYPE, GRAD1 || GRADX>(part, D[x][y], pv, sm.tab);
@@ -571,7 +606,7 @@ __global__ void __launch_bounds__(kThreads, (MODE == 0 && is_fast_type(PTYPE)) ?
         if (MODE == 0 && S->depth2) {
             // vectorised composite: whole micro-tile per leaf, children folded in tree order
             double res[4][4];
-            composite_vec(*S, sm.Zs1, sm.Zs2, ndim, t, sm.tab, res, bad);
+            composite_vec(*S, sm.Zs1, sm.Zs2, ndim, t, sm.tab, sm.ltab, res, bad);
 #pragma unroll
             for (int x = 0; x < 4; ++x) {
                 if (diag_noise) add_noise_row(res[x], t, x, noise);
@@ -651,6 +686,13 @@ __global__ void __launch_bounds__(kThreads, (MODE == 0 && is_fast_type(PTYPE)) ?
         }
     }
 }
+
+// (A persistent variant of the fast value kernels -- each CTA walking tiles and issuing the bulk copies of its
+// next tile right after the distance loop, so that the copy latency hides behind the epilogue -- was measured
+// and dropped: Matern-5/2 d = 16 3.11 ms against 2.57 ms for one tile per CTA, SE d = 1 1.66 against 1.39
+// (profiles/r02d_gram_persistent_experiment.txt).  The barrier it needs between the distance loop and the
+// epilogue puts the eight warps of a CTA in lockstep; with one tile per CTA the four resident CTAs drift apart
+// and overlap their phases, which is worth more than the hidden copy latency.)
 
 template <int PTYPE, int MODE>
 static int launch_gram_t(pgp_ctx* ctx, const GramKArgs& a, size_t smem) {
@@ -1193,14 +1235,18 @@ int launch_trace_dist(pgp_ctx* ctx, const TraceDistArgs& a) {
 // ---------------------------------------------------------------------------
 __global__ void fastmath_kernel(int which, const double* x, int64_t n, double* out) {
     __shared__ double tab[fm::kExpTabDoubles];
+    __shared__ __align__(16) double ltab[fm::kLogTabDoubles];
     fm::load_exp_tab(tab, threadIdx.x, blockDim.x);
+    fm::load_log_tab(ltab, threadIdx.x, blockDim.x);
     __syncthreads();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         int bad = 0;
         double r;
         if (which == 0) { r = fm::exp_tab(x[i], tab, bad); if (bad) r = exp(x[i]); }
         else if (which == 1) r = fm::sqrt_pos(x[i]);
-        else r = fm::exp_tab_clamped(x[i], tab);
+        else if (which == 2) r = fm::exp_tab_clamped(x[i], tab);
+        else if (which == 3) { r = fm::log_ge1_tab(x[i], ltab, bad); if (bad) r = log(x[i]); }
+        else { r = fabs(fm::sin_unsigned_cw(x[i], bad)); if (bad) r = fabs(sin(x[i])); }
         out[i] = r;
     }
 }

@@ -31,6 +31,8 @@ struct DevPart {
     double sf2;        // exp(2 log sf)      (Periodic, RQ, dget)
     double p0;         // Periodic: ell      RQ: alpha
     double p1;         // Periodic: p
+    double q0;         // Periodic: 1 / ell  (fast value path)
+    double q1;         // Periodic: 1 / p    RQ: 1 / (2 alpha)
 };
 
 // Header (copied to shared memory by the tile kernels) + per-part divisors.
@@ -118,8 +120,11 @@ inline int compile_spec(const pgp_kernel_spec* s, const double* hyp, double sn2,
         if (sp.type == PGP_PERIODIC) {
             d.p0 = std::exp(hp[1]);
             d.p1 = std::exp(hp[2]);
+            d.q0 = 1.0 / d.p0;
+            d.q1 = 1.0 / d.p1;
         } else if (sp.type == PGP_RQ) {
             d.p0 = std::exp(hp[1 + nell]);
+            d.q1 = 0.5 / d.p0;
         }
     }
     if (hsum != s->nhyper) { *err = "sum of leaf nhyper != kernel nhyper"; return PGP_E_ARG; }

@@ -56,3 +56,24 @@ def test_sqrt_pos():
     assert _run(1, np.array([1e-300]))[0] < 1e-140
     assert _run(1, np.array([0.0]))[0] == 0.0          # exact zero at coincident points (Matern r = 0 guards)
     assert np.isnan(_run(1, np.array([np.nan])))[0]
+
+
+def test_log_ge1_tab():
+    """log for x >= 1 with ABSOLUTE accuracy (what exp(-alpha log E) of the RQ kernel needs, rq.py:56-63)."""
+    rng = np.random.RandomState(2)
+    x = np.r_[1 + rng.uniform(0, 1e-6, 100000), rng.uniform(1, 4, 300000), 10.0**rng.uniform(0, 300, 300000),
+              [1.0, 2.0, np.e, 1 + 2.0**-52, 1e308]]
+    got, want = _run(3, x), np.log(x)
+    assert np.abs(got - want).max() <= 4e-16*np.maximum(1.0, np.abs(want)).max()
+    assert (np.abs(got - want) <= 3e-16*np.maximum(1.0, np.abs(want))).all()
+    assert _run(3, np.array([1.0]))[0] == 0.0
+    assert np.isnan(_run(3, np.array([np.nan])))[0] and np.isinf(_run(3, np.array([np.inf])))[0]
+
+
+def test_sin_unsigned_cw():
+    """|sin x| by Cody-Waite reduction in pi/2 (the Periodic kernel squares it, periodic.py:53-59)."""
+    rng = np.random.RandomState(3)
+    x = np.r_[rng.uniform(0, 10, 300000), rng.uniform(0, 1e4, 300000), rng.uniform(0, 1.5e6, 100000),
+              [0.0, np.pi/2, np.pi, 1e-300, 3e6, 1e12]]
+    got, want = _run(4, x), np.abs(np.sin(x))
+    assert np.abs(got - want).max() <= 3e-16
