@@ -170,13 +170,13 @@ struct PoolBuf {
     ~PoolBuf() {
         if (p) {
             cudaStreamSynchronize(ctx->stream);
-            pool_free(ctx, p, count);
+            dev_free_null(ctx, p);
         }
     }
     int get(pgp_ctx* c, size_t n) {
         ctx = c;
         count = std::max<size_t>(n, 1);
-        return pool_alloc(c, &p, count);
+        return dev_alloc(c, &p, count);
     }
 };
 
@@ -438,13 +438,13 @@ namespace {
 void model_free_work(pgp_model* m) {
     pgp_ctx* ctx = m->ctx;
     cudaStreamSynchronize(ctx->stream);  // pooled buffers may be handed out again at once
-    pool_free(ctx, m->d_Z, (size_t)m->spec.n_parts * m->n * m->ndim);
-    pool_free(ctx, m->d_F, (size_t)(m->n + 1) * m->ld);
-    pool_free(ctx, m->d_G, (size_t)m->n * m->ld);
-    pool_free(ctx, m->d_H, (size_t)m->n * m->ld);
+    dev_free_null(ctx, m->d_Z);
+    dev_free_null(ctx, m->d_F);
+    dev_free_null(ctx, m->d_G);
+    dev_free_null(ctx, m->d_H);
     dev_free(ctx, m->d_alpha); m->d_alpha = nullptr;
     dev_free(ctx, m->d_partials); m->d_partials = nullptr;
-    pool_free(ctx, m->d_Bc, (size_t)m->bc_rows * m->ld);
+    dev_free_null(ctx, m->d_Bc);
     m->bc_rows = 0;
     m->factored = false;
 }
@@ -453,8 +453,8 @@ int model_alloc_work(pgp_model* m) {
     pgp_ctx* ctx = m->ctx;
     m->cap = m->n;                       // exact fit; pgp_exact_append_inc adds slack when it has to grow
     m->ld = lead_dim(m->cap);
-    PGP_TRY(pool_alloc(ctx, &m->d_Z, z_doubles(m->spec.n_parts, m->ndim, m->xcap)));
-    PGP_TRY(pool_alloc(ctx, &m->d_F, (size_t)(m->cap + 1) * m->ld));
+    PGP_TRY(dev_alloc(ctx, &m->d_Z, z_doubles(m->spec.n_parts, m->ndim, m->xcap)));
+    PGP_TRY(dev_alloc(ctx, &m->d_F, (size_t)(m->cap + 1) * m->ld));
     PGP_TRY(dev_alloc(ctx, &m->d_alpha, (size_t)m->xcap));
     return 0;
 }
@@ -558,7 +558,7 @@ extern "C" int pgp_exact_append_inc(pgp_model* m, const double* X, const double*
     PoolBuf T;                                   // (n_new + 1, ldt) scratch block
     const int64_t ldt = lead_dim(n_new);
     PGP_TRY(T.get(ctx, (size_t)(n_new + 1) * ldt));
-    if (!inplace) PGP_TRY(pool_alloc(ctx, &nF, (size_t)(cap + 1) * ld));
+    if (!inplace) PGP_TRY(dev_alloc(ctx, &nF, (size_t)(cap + 1) * ld));
     // a failure must leave the model consistent (unfactored, buffers sized for m->n rows): the host
     // falls back to a full pgp_exact_update
     auto bail = [&](int code) {
@@ -594,7 +594,7 @@ extern "C" int pgp_exact_append_inc(pgp_model* m, const double* X, const double*
     if ((rc = model_upload(m, X, y, n_old, n_new))) return bail(rc);           // X, y grow (m->n = n now)
     if (m->xcap != xcap_old) {                                                  // Z, alpha follow the row capacity
         double *nZ = nullptr, *nAlpha = nullptr;
-        rc = pool_alloc(ctx, &nZ, z_doubles(np, d, m->xcap));
+        rc = dev_alloc(ctx, &nZ, z_doubles(np, d, m->xcap));
         if (!rc) rc = dev_alloc(ctx, &nAlpha, (size_t)m->xcap);
         if (rc) {
             dev_free(ctx, nZ);
@@ -842,11 +842,11 @@ extern "C" int pgp_exact_loglike(pgp_model* m, int want_grad, double* lZ, double
     const int64_t n = m->n, ld = m->ld;
     const int nk = m->spec.nhyper;
     if (!m->d_G) {
-        PGP_TRY(pool_alloc(ctx, &m->d_G, (size_t)n * ld));
+        PGP_TRY(dev_alloc(ctx, &m->d_G, (size_t)n * ld));
         // blocks of G below the diagonal are never written: zero them once
         PGP_CUDA(ctx, cudaMemsetAsync(m->d_G, 0, sizeof(double) * n * ld, ctx->stream));
     }
-    if (!m->d_H) PGP_TRY(pool_alloc(ctx, &m->d_H, (size_t)n * ld));
+    if (!m->d_H) PGP_TRY(dev_alloc(ctx, &m->d_H, (size_t)n * ld));
     if (!m->d_partials) PGP_TRY(dev_alloc(ctx, &m->d_partials, (size_t)trace_cta_count(n) * (kMaxHyper + 1)));
     Mat F, G, H;
     F.p = m->d_F; F.ld = ld;
@@ -895,9 +895,9 @@ int predict_chunked(pgp_model* m, const double* Xs, bool xs_on_device, int64_t m
     const int64_t need_rows = chunk * rpp;
     if (m->bc_rows < need_rows) {
         PGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        pool_free(ctx, m->d_Bc, (size_t)m->bc_rows * ld);
+        dev_free_null(ctx, m->d_Bc);
         m->bc_rows = 0;
-        PGP_TRY(pool_alloc(ctx, &m->d_Bc, (size_t)need_rows * ld));
+        PGP_TRY(dev_alloc(ctx, &m->d_Bc, (size_t)need_rows * ld));
         m->bc_rows = need_rows;
     }
     DevBuf xs, zs, o;

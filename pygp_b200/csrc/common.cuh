@@ -186,14 +186,9 @@ inline int dev_alloc(pgp_ctx* ctx, T** p, size_t count) {
     return dev_alloc_bytes(ctx, reinterpret_cast<void**>(p), count * sizeof(T));
 }
 
-// historical names of the large-buffer path (same cache)
+// free and forget: most owners keep the pointer in a struct field that is tested later
 template <class T>
-inline int pool_alloc(pgp_ctx* ctx, T** p, size_t count) {
-    return dev_alloc(ctx, p, count);
-}
-
-template <class T>
-inline void pool_free(pgp_ctx* ctx, T*& p, size_t /*count*/) {
+inline void dev_free_null(pgp_ctx* ctx, T*& p) {
     dev_free(ctx, p);
     p = nullptr;
 }

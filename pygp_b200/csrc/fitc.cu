@@ -444,12 +444,12 @@ void fitc_free(pgp_fitc* f) {
     pgp_ctx* ctx = f->ctx;
     cudaStreamSynchronize(ctx->stream);
     const size_t np_ = (size_t)f->n * f->ldp;
-    pool_free(ctx, f->d_Vs, np_);
-    pool_free(ctx, f->d_Bt, np_);
-    pool_free(ctx, f->d_Wt, np_);
-    pool_free(ctx, f->d_T, np_);
-    pool_free(ctx, f->d_Kc, (size_t)f->kc_rows * f->ldp);
-    pool_free(ctx, f->d_pred, (size_t)2 * f->pc_rows * f->ldp);
+    dev_free_null(ctx, f->d_Vs);
+    dev_free_null(ctx, f->d_Bt);
+    dev_free_null(ctx, f->d_Wt);
+    dev_free_null(ctx, f->d_T);
+    dev_free_null(ctx, f->d_Kc);
+    dev_free_null(ctx, f->d_pred);
     double** small[] = {&f->d_X, &f->d_y, &f->d_U, &f->d_ZX, &f->d_ZU, &f->d_L, &f->d_A, &f->d_R, &f->d_ell,
                         &f->d_rs, &f->d_c, &f->d_alpha, &f->d_q, &f->d_cw, &f->d_bb, &f->d_a, &f->d_b, &f->d_t,
                         &f->d_w, &f->d_P, &f->d_Cuu, &f->d_VW, &f->d_part, &f->d_res};
@@ -498,8 +498,8 @@ extern "C" int pgp_fitc_create(pgp_ctx* ctx, const pgp_kernel_spec* spec, const 
     A(&f->d_res, (size_t)2 * kMaxHyper + kScal);
     if (!rc) rc = dev_alloc(ctx, &f->d_spec, 2);
     if (!rc) rc = dev_alloc(ctx, &f->d_info, 4);
-    if (!rc) rc = pool_alloc(ctx, &f->d_Vs, (size_t)n * ldp);
-    if (!rc) rc = pool_alloc(ctx, &f->d_Kc, (size_t)f->kc_rows * ldp);
+    if (!rc) rc = dev_alloc(ctx, &f->d_Vs, (size_t)n * ldp);
+    if (!rc) rc = dev_alloc(ctx, &f->d_Kc, (size_t)f->kc_rows * ldp);
     if (rc) {
         pgp_fitc_destroy(f);
         return rc;
@@ -667,9 +667,9 @@ extern "C" int pgp_fitc_loglike(pgp_fitc* f, int want_grad, double* lZ, double* 
     const int64_t n = f->n, p = f->p, ldp = f->ldp;
     cudaStream_t s = ctx->stream;
     const size_t np_ = (size_t)n * ldp;
-    if (!f->d_Bt) PGP_TRY(pool_alloc(ctx, &f->d_Bt, np_));
-    if (!f->d_Wt) PGP_TRY(pool_alloc(ctx, &f->d_Wt, np_));
-    if (!f->d_T) PGP_TRY(pool_alloc(ctx, &f->d_T, np_));
+    if (!f->d_Bt) PGP_TRY(dev_alloc(ctx, &f->d_Bt, np_));
+    if (!f->d_Wt) PGP_TRY(dev_alloc(ctx, &f->d_Wt, np_));
+    if (!f->d_T) PGP_TRY(dev_alloc(ctx, &f->d_T, np_));
     if (!f->d_q) PGP_TRY(dev_alloc(ctx, &f->d_q, (size_t)n));
     if (!f->d_cw) PGP_TRY(dev_alloc(ctx, &f->d_cw, (size_t)n));
     if (!f->d_bb) PGP_TRY(dev_alloc(ctx, &f->d_bb, (size_t)n));
@@ -779,9 +779,9 @@ static int fitc_predict_impl(pgp_fitc* f, const double* Xs, int64_t ms, double* 
     if (want_grad) chunk = std::max<int64_t>(1, std::min(chunk, std::max<int64_t>(64, chunk / rpp)));
     if (f->pc_rows < chunk * rpp) {
         PGP_CUDA(ctx, cudaStreamSynchronize(s));
-        pool_free(ctx, f->d_pred, (size_t)2 * f->pc_rows * ldp);
+        dev_free_null(ctx, f->d_pred);
         f->pc_rows = 0;
-        PGP_TRY(pool_alloc(ctx, &f->d_pred, (size_t)2 * chunk * rpp * ldp));
+        PGP_TRY(dev_alloc(ctx, &f->d_pred, (size_t)2 * chunk * rpp * ldp));
         f->pc_rows = chunk * rpp;
     }
     double *dxs = nullptr, *dzs = nullptr, *dout = nullptr;
@@ -871,9 +871,9 @@ extern "C" int pgp_fitc_full_posterior(pgp_fitc* f, const double* Xs, int64_t ms
     cudaStream_t s = ctx->stream;
     if ((double)ms * ldp * 16 > 8.0 * (1ull << 30)) return ctx->fail(PGP_E_ARG, "full posterior: too many test points for one chunk");
     double *LK = nullptr, *RK = nullptr, *S = nullptr, *dxs = nullptr, *dzs = nullptr, *dout = nullptr;
-    int rc = pool_alloc(ctx, &LK, (size_t)ms * ldp);
-    if (!rc) rc = pool_alloc(ctx, &RK, (size_t)ms * ldp);
-    if (!rc) rc = pool_alloc(ctx, &S, (size_t)ms * lds);
+    int rc = dev_alloc(ctx, &LK, (size_t)ms * ldp);
+    if (!rc) rc = dev_alloc(ctx, &RK, (size_t)ms * ldp);
+    if (!rc) rc = dev_alloc(ctx, &S, (size_t)ms * lds);
     if (!rc) rc = dev_alloc(ctx, &dxs, (size_t)ms * d);
     if (!rc) rc = dev_alloc(ctx, &dzs, z_doubles(np, d, ms));
     if (!rc) rc = dev_alloc(ctx, &dout, (size_t)2 * ms);
@@ -916,9 +916,9 @@ extern "C" int pgp_fitc_full_posterior(pgp_fitc* f, const double* Xs, int64_t ms
     };
     if (!rc) rc = body();
     cudaStreamSynchronize(s);
-    pool_free(ctx, LK, (size_t)ms * ldp);
-    pool_free(ctx, RK, (size_t)ms * ldp);
-    pool_free(ctx, S, (size_t)ms * lds);
+    dev_free_null(ctx, LK);
+    dev_free_null(ctx, RK);
+    dev_free_null(ctx, S);
     dev_free(ctx, dxs);
     dev_free(ctx, dzs);
     dev_free(ctx, dout);

@@ -556,6 +556,11 @@ __global__ void __launch_bounds__(kThreads, (MODE == 0 && is_fast_grad_type(PTYP
     const int xdim = a.xdim;
     const bool vec_ok = a.ostride == 1 && ((a.ldo & 1) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
     const bool mirror = a.symmetric && ti != tj;
+    // interior tile with aligned unit-stride rows: every store is a 128-bit store at base + constant, no bound
+    // checks and no 64-bit index arithmetic per row (CTA-uniform branch; all but the last tile row / column)
+    const bool interior = MODE < 2 && vec_ok && i0 + kTile <= a.n1 && j0 + kTile <= a.n2;
+    double* const tile_base = out + (i0 + t.ty) * a.ldo + j0 + 2 * t.tx;     // entry (ty, 2 tx) of the tile
+    const int64_t row_step = 16 * a.ldo;                                      // micro-tile rows are 16 apart
     double* T = sm.extra;                   // [64][kTile + 1] transpose scratch of the mirrored tile
     constexpr int TP = kTile + 1;
     int bad = 0;
@@ -593,7 +598,13 @@ __global__ void __launch_bounds__(kThreads, (MODE == 0 && is_fast_grad_type(PTYP
                 }
             }
             if (diag_noise) add_noise_row(v, t, x, noise);
-            store_row<MODE < 2>(out, a.ldo, a.ostride, a.n1, a.n2, vec_ok, i0 + t.row(x), j0 + 2 * t.tx, v);
+            if (interior) {
+                double* rowp = tile_base + x * row_step;
+                *reinterpret_cast<double2*>(rowp) = make_double2(v[0], v[1]);
+                *reinterpret_cast<double2*>(rowp + 32) = make_double2(v[2], v[3]);
+            } else {
+                store_row<MODE < 2>(out, a.ldo, a.ostride, a.n1, a.n2, vec_ok, i0 + t.row(x), j0 + 2 * t.tx, v);
+            }
             if (mirror) {
 #pragma unroll
                 for (int y = 0; y < 4; ++y) T[t.row(x) * TP + t.col(y)] = v[y];
@@ -664,7 +675,17 @@ __global__ void __launch_bounds__(kThreads, (MODE == 0 && is_fast_grad_type(PTYP
     // transpose of this one -- k and every dk/dhyper are symmetric in (x1, x2) --
     // so it is written from a shared-memory transpose instead of being
     // recomputed: half the FP64 work per byte written.
-    if (mirror) {
+    if (mirror && interior) {
+        __syncthreads();
+        double* mbase = out + (j0 + t.ty) * a.ldo + i0 + 2 * t.tx;          // entry (ty, 2 tx) of the mirrored tile
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+            double* rowp = mbase + x * row_step;
+            const int r = t.row(x), c = 2 * t.tx;
+            *reinterpret_cast<double2*>(rowp) = make_double2(T[c * TP + r], T[(c + 1) * TP + r]);
+            *reinterpret_cast<double2*>(rowp + 32) = make_double2(T[(c + 32) * TP + r], T[(c + 33) * TP + r]);
+        }
+    } else if (mirror) {
         __syncthreads();
 #pragma unroll
         for (int x = 0; x < 4; ++x) {

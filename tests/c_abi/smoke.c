@@ -51,6 +51,33 @@ int main(void) {
     for (int i = 0; i < M; ++i) printf(" %.17g", mu[i]);
     for (int i = 0; i < M; ++i) printf(" %.17g", s2[i]);
     printf("\n");
+    /* the batched entry point: two hyper vectors in one call, values and gradients (optimization.py:54-62 over
+     * restarts); the first one is `hyp`, so it must reproduce the single-model result */
+    {
+        double hyps[2 * (1 + 1 + D + 1)], blZ[2], bdlZ[2 * 8];
+        int32_t binfo[2];
+        for (int i = 0; i < nh; ++i) { hyps[i] = hyp[i]; hyps[nh + i] = hyp[i] + 0.05; }
+        if ((rc = pgp_batched_loglike(ctx, &spec, X, y, N, hyps, 2, blZ, bdlZ, binfo))) {
+            fprintf(stderr, "batched: %s\n", pgp_last_error(ctx));
+            return 8;
+        }
+        if (binfo[0] || binfo[1] || fabs(blZ[0] - lZ) > 1e-10 * fabs(lZ)) { fprintf(stderr, "batched lZ mismatch\n"); return 9; }
+        for (int i = 0; i < nh; ++i)
+            if (fabs(bdlZ[i] - dlZ[i]) > 1e-8 * (1.0 + fabs(dlZ[i]))) { fprintf(stderr, "batched dlZ mismatch\n"); return 10; }
+    }
+    /* the distributed entry points on a communicator of ONE rank (no NCCL needed): block-column factorisation and
+     * block-column gradient must reproduce pgp_exact_update / pgp_exact_loglike */
+    {
+        pgp_dist* comm = NULL;
+        double lZd, dlZd[8];
+        if ((rc = pgp_dist_init(ctx, 1, 0, NULL, &comm))) { fprintf(stderr, "dist init: %s\n", pgp_last_error(ctx)); return 11; }
+        if ((rc = pgp_dist_exact_update(comm, m, hyp, 64))) { fprintf(stderr, "dist update: %d %s\n", rc, pgp_last_error(ctx)); return 12; }
+        if ((rc = pgp_dist_exact_loglike(comm, m, 64, 1, &lZd, dlZd))) { fprintf(stderr, "dist loglike: %s\n", pgp_last_error(ctx)); return 13; }
+        if (fabs(lZd - lZ) > 1e-10 * fabs(lZ)) { fprintf(stderr, "dist lZ mismatch %.17g %.17g\n", lZd, lZ); return 14; }
+        for (int i = 0; i < nh; ++i)
+            if (fabs(dlZd[i] - dlZ[i]) > 1e-8 * (1.0 + fabs(dlZ[i]))) { fprintf(stderr, "dist dlZ mismatch\n"); return 15; }
+        pgp_dist_destroy(comm);
+    }
     /* error convention: a non positive-definite matrix comes back as LAPACK info > 0 */
     double bad[1 + 1 + D + 1] = {log(1e-12), log(1.0), log(50.0), log(50.0), log(50.0), 0.0};
     rc = pgp_exact_update(m, bad);
