@@ -355,6 +355,11 @@ struct StreamSwap {                     // run the enclosed launches on another 
     ~StreamSwap() { ctx->stream = saved; }
 };
 
+// (Tried in round 2 and dropped: factoring only the panel's w x w diagonal block with the recursion and solving
+// the rows below as ONE GEMM with its explicit inverse -- the scheme dist.cu uses for its broadcast panels.  On one
+// GPU it is slower: potrf N = 2048 / 4096 / 8192 / 16384: 1.73 / 3.90 / 11.75 / 56.1 ms against 1.42 / 3.16 / 10.26 /
+// 54.8 ms with the rows riding through the leaf steps (profiles/r02g_chol_panel_inverse_experiment.txt): the inverse,
+// the out-of-place GEMM and the copy back cost more than the leaf kernels they remove.)
 int chol_lookahead(pgp_ctx* ctx, const Mat& F, int64_t n, int64_t mrows, int* d_info) {
     if (!ctx->stream2) {
         // highest priority: the panel's short kernels must get the next free SM even
