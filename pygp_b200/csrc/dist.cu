@@ -85,6 +85,7 @@ struct pgp_dist {
     ncclComm_t comm = nullptr;
     cudaStream_t comm_stream = nullptr;
     cudaStream_t copy_stream = nullptr;     // unpacking of received panels, off the main stream
+    cudaStream_t bulk_stream = nullptr;     // the owner's update of the rows below a panel's diagonal block
     std::vector<cudaEvent_t> events;        // 3 per panel: packed, broadcast done, unpacked
     double* stage[2] = {nullptr, nullptr};  // contiguous send / receive buffers of one panel
     size_t stage_doubles = 0;
@@ -149,7 +150,8 @@ extern "C" int pgp_dist_init(pgp_ctx* ctx, int n_ranks, int rank, const void* id
             int lo = 0, hi = 0;
             cudaDeviceGetStreamPriorityRange(&lo, &hi);
             if (cudaStreamCreateWithPriority(&d->comm_stream, cudaStreamNonBlocking, hi) != cudaSuccess ||
-                cudaStreamCreateWithPriority(&d->copy_stream, cudaStreamNonBlocking, hi) != cudaSuccess)
+                cudaStreamCreateWithPriority(&d->copy_stream, cudaStreamNonBlocking, hi) != cudaSuccess ||
+                cudaStreamCreateWithPriority(&d->bulk_stream, cudaStreamNonBlocking, hi) != cudaSuccess)
                 rc = ctx->fail(PGP_E_CUDA, "cannot create the communication streams");
         }
     }
@@ -171,6 +173,7 @@ extern "C" void pgp_dist_destroy(pgp_dist* d) {
     if (d->comm) g_nccl.CommDestroy(d->comm);
     if (d->comm_stream) cudaStreamDestroy(d->comm_stream);
     if (d->copy_stream) { cudaStreamSynchronize(d->copy_stream); cudaStreamDestroy(d->copy_stream); }
+    if (d->bulk_stream) { cudaStreamSynchronize(d->bulk_stream); cudaStreamDestroy(d->bulk_stream); }
     for (cudaEvent_t e : d->events) cudaEventDestroy(e);
     dev_free(ctx, d->stage[0]);
     dev_free(ctx, d->stage[1]);
@@ -243,7 +246,7 @@ extern "C" int pgp_dist_exact_update(pgp_dist* d, pgp_model* m, const double* hy
     const double sn2 = std::exp(hyp[0] * 2), mean = hyp[1 + nk];
     PGP_TRY(compile_spec(&m->spec, hyp + 1, sn2, mean, &m->hspec, &ctx->err));
     m->factored = false;
-    cudaStream_t S = ctx->stream, C = d->comm_stream, U = d->copy_stream;
+    cudaStream_t S = ctx->stream, C = d->comm_stream, U = d->copy_stream, Q = d->bulk_stream;
     const int64_t n = m->n, ld = m->ld;
     const int rank = d->rank, size = d->size;
     Cols cols{n, nb, ceil_div(n, nb)};
@@ -276,13 +279,14 @@ extern "C" int pgp_dist_exact_update(pgp_dist* d, pgp_model* m, const double* hy
         PGP_TRY(dev_alloc(ctx, &d->d_Vs, (size_t)nb * nb));
         d->v_nb = nb;
     }
-    PGP_TRY(ensure_events(d, (size_t)5 * nblk + 2));
-    auto ev_packed = [&](int64_t k) { return d->events[5 * k]; };        // panel k packed (panel stream)
-    auto ev_bcast = [&](int64_t k) { return d->events[5 * k + 1]; };     // broadcast of panel k done (comm stream)
-    auto ev_unpacked = [&](int64_t k) { return d->events[5 * k + 2]; };  // panel k in the replicated factor (main)
-    auto ev_trail = [&](int64_t k) { return d->events[5 * k + 3]; };     // step k: panel k + 2 is up to date with panels <= k (main)
-    auto ev_fact = [&](int64_t k) { return d->events[5 * k + 4]; };      // panel k factored (panel stream)
-    cudaEvent_t ev_start = d->events[5 * nblk];
+    PGP_TRY(ensure_events(d, (size_t)6 * nblk + 2));
+    auto ev_packed = [&](int64_t k) { return d->events[6 * k]; };        // panel k packed (panel stream)
+    auto ev_bcast = [&](int64_t k) { return d->events[6 * k + 1]; };     // broadcast of panel k done (comm stream)
+    auto ev_unpacked = [&](int64_t k) { return d->events[6 * k + 2]; };  // panel k in the replicated factor (main)
+    auto ev_trail = [&](int64_t k) { return d->events[6 * k + 3]; };     // step k: panel k + 2 is up to date with panels <= k (main)
+    auto ev_fact = [&](int64_t k) { return d->events[6 * k + 4]; };      // panel k factored (panel stream)
+    auto ev_bulk = [&](int64_t k) { return d->events[6 * k + 5]; };      // rows below the diagonal block of panel k updated (bulk stream)
+    cudaEvent_t ev_start = d->events[6 * nblk];
     // The panel chain (update of the next panel, its potrf, the pack) runs on a second, high-priority
     // stream P so that on the owner it overlaps the trailing updates of the same step (the single-GPU
     // lookahead of chol.cu, here across the panel broadcast as well).
@@ -381,17 +385,32 @@ extern "C" int pgp_dist_exact_update(pgp_dist* d, pgp_model* m, const double* hy
                 Swap sw(ctx, P);
                 if (k >= 1) {
                     // panel k -= P_{k-1}[rows >= j0] P_{k-1}[block k]^T, P_{k-1} read straight from the staging buffer it
-                    // was received into (dense, pitch nb): no wait for its unpacking into F
+                    // was received into (dense, pitch nb): no wait for its unpacking into F.  Only the diagonal
+                    // block is updated on the panel stream; the rows below go to the bulk stream, so that the
+                    // potrf of the block and its inverse (~0.45 ms of small dependent kernels) run beside that GEMM
+                    // instead of after it.
                     PGP_CUDA(ctx, cudaStreamWaitEvent(P, ev_bcast(k - 1), 0));
                     const double* prev = d->stage[(k - 1) & 1] + (j0 - cols.j0(k - 1)) * nb;
                     GemmArgs g;
                     g.A = prev; g.lda = nb;
                     g.B = prev; g.ldb = nb;
                     g.C = Fp; g.ldc = ld;
-                    g.M = rows; g.N = w; g.K = cols.w(k - 1);
+                    g.M = w; g.N = w; g.K = cols.w(k - 1);
                     g.alpha = -1.0; g.beta = 1.0;
                     g.tri = 1;
                     PGP_TRY(launch_gemm_nt(ctx, g));
+                    if (rows > w) {
+                        PGP_CUDA(ctx, cudaStreamWaitEvent(Q, k >= 2 ? ev_trail(k - 2) : ev_start, 0));
+                        PGP_CUDA(ctx, cudaStreamWaitEvent(Q, ev_bcast(k - 1), 0));
+                        Swap sq(ctx, Q);
+                        GemmArgs gb = g;
+                        gb.A = prev + w * nb;
+                        gb.C = Fp + w * ld;
+                        gb.M = rows - w;
+                        gb.tri = 0;
+                        PGP_TRY(launch_gemm_nt(ctx, gb));
+                        PGP_CUDA(ctx, cudaEventRecord(ev_bulk(k), Q));
+                    }
                     applied[k] = k;
                 }
                 // L11 = chol(top w x w block) only; the rows below are solved as ONE GEMM with the explicit
@@ -406,6 +425,7 @@ extern "C" int pgp_dist_exact_update(pgp_dist* d, pgp_model* m, const double* hy
                 PGP_CUDA(ctx, cudaMemsetAsync(d->d_V, 0, sizeof(double) * nb * nb, P));
                 PGP_TRY(inv_upper(ctx, V, Pm, w, Vs));
                 if (k >= 2) PGP_CUDA(ctx, cudaStreamWaitEvent(P, ev_unpacked(k - 2), 0));      // staging slot free again
+                if (k >= 1 && rows > w) PGP_CUDA(ctx, cudaStreamWaitEvent(P, ev_bulk(k), 0));  // rows below are up to date
                 GemmArgs x;                                  // X = B V  ->  rows w.. of the staging buffer
                 x.A = Fp + w * ld; x.lda = ld;
                 x.B = d->d_V; x.ldb = nb; x.transB = 1; x.kcol = 1;
