@@ -242,6 +242,15 @@ __device__ __forceinline__ void eval_parts(const DevSpecHdr& S, const double* z1
     }
 }
 
+// value of a composite at one entry through the tree interpreter (deep trees, and the cold redo of the
+// vectorised path): not inlined, so that its local arrays do not set the register budget of the value kernel
+__device__ __noinline__ double composite_value_interp(const DevSpecHdr& S, const double* z1, const double* z2) {
+    PartVal pv[kMaxParts];
+    double val[kMaxNodes];
+    eval_parts<false>(S, z1, z2, pv);
+    return tree_forward(S, pv, val);
+}
+
 // value of d k / d hyper[slot] for a composite at one entry
 __device__ __forceinline__ double composite_grad1(const DevSpecHdr& S, const double* z1, const double* z2,
                                                   int part, int kind, int dim) {
@@ -367,16 +376,33 @@ __device__ __forceinline__ void micro_dist(const double* Zs1, const double* Zs2,
 }
 
 // ---- vectorised composite value (trees of depth <= 2) ------------------------------------------
-// One leaf for the thread's whole micro-tile: 16 distances, then ONE warp-uniform switch on the
-// leaf type around a 16-entry epilogue loop -- instead of the per-entry tree interpreter, whose
-// local arrays and rolled loops ran the SE + Periodic Gram build at 1.0 TB/s (round 1).
-__device__ __forceinline__ void leaf_vec(const DevPart& part, const double* Zs1, const double* Zs2, int ndim,
-                                         const Tile& t, const double* tab, const double* ltab, double (&K)[4][4], int& bad) {
-    if (part.type == PGP_PERIODIC) micro_absdiff(Zs1, Zs2, t, K);
-    else micro_dist(Zs1, Zs2, ndim, t, K);
-#define PGP_LEAF_LOOP(T)                                 \
-    _Pragma("unroll") for (int x = 0; x < 4; ++x)        \
-        _Pragma("unroll") for (int y = 0; y < 4; ++y) K[x][y] = fast_value<T>(part, K[x][y], tab, ltab, bad);
+// One leaf for one micro-tile ROW of the thread (4 entries): 4 distances, then ONE warp-uniform switch on the
+// leaf type around a 4-entry epilogue -- instead of the per-entry tree interpreter, whose local arrays and
+// rolled loops ran the SE + Periodic Gram build at 1.0 TB/s (round 1).  Row-wise (not the whole 4 x 4 micro-tile
+// per leaf, the first round-2 version: 128 registers, 2 CTAs per SM, 0.35 of HBM) so that the running values of
+// the root and of one inner node fit the register budget of three to four resident CTAs.
+__device__ __forceinline__ void leaf_row(const DevPart& part, const double* Zs1, const double* Zs2, int ndim,
+                                         const Tile& t, int row, const double* tab, const double* ltab, double (&K)[4],
+                                         int& bad) {
+    {
+        double D[4] = {0.0, 0.0, 0.0, 0.0};
+        const bool absdiff = part.type == PGP_PERIODIC;            // ndim == 1: |x1 - x2| itself (fast_value)
+        for (int k = 0; k < ndim; ++k) {
+            const double zi = Zs1[k * kTile + row];
+            const double2 q0 = *reinterpret_cast<const double2*>(&Zs2[k * kTile + 2 * t.tx]);
+            const double2 q1 = *reinterpret_cast<const double2*>(&Zs2[k * kTile + 2 * t.tx + 32]);
+            const double zj[4] = {q0.x, q0.y, q1.x, q1.y};
+#pragma unroll
+            for (int y = 0; y < 4; ++y) {
+                const double df = zi - zj[y];
+                D[y] = absdiff ? fabs(df) : fma(df, df, D[y]);
+            }
+        }
+#pragma unroll
+        for (int y = 0; y < 4; ++y) K[y] = D[y];
+    }
+#define PGP_LEAF_LOOP(T) \
+    _Pragma("unroll") for (int y = 0; y < 4; ++y) K[y] = fast_value<T>(part, K[y], tab, ltab, bad);
     switch (part.type) {
         case PGP_SE: PGP_LEAF_LOOP(PGP_SE) break;
         case PGP_MATERN1: PGP_LEAF_LOOP(PGP_MATERN1) break;
@@ -388,43 +414,40 @@ __device__ __forceinline__ void leaf_vec(const DevPart& part, const double* Zs1,
 #undef PGP_LEAF_LOOP
 }
 
-__device__ __forceinline__ void vec_fold(double (&acc)[4][4], const double (&v)[4][4], int kind, bool first) {
+__device__ __forceinline__ void row_fold(double (&acc)[4], const double (&v)[4], int kind, bool first) {
 #pragma unroll
-    for (int x = 0; x < 4; ++x)
-#pragma unroll
-        for (int y = 0; y < 4; ++y)
-            acc[x][y] = first ? v[x][y] : (kind == NK_SUM ? acc[x][y] + v[x][y] : acc[x][y] * v[x][y]);
+    for (int y = 0; y < 4; ++y) acc[y] = first ? v[y] : (kind == NK_SUM ? acc[y] + v[y] : acc[y] * v[y]);
 }
 
-// value of a depth <= 2 tree on the micro-tile, folding children in the order tree_forward does
-__device__ __forceinline__ void composite_vec(const DevSpecHdr& S, const double* Zs1, const double* Zs2, int ndim,
-                                              const Tile& t, const double* tab, const double* ltab, double (&res)[4][4],
-                                              int& bad) {
+// value of a depth <= 2 tree on one micro-tile row, folding children in the order tree_forward does
+__device__ __forceinline__ void composite_row(const DevSpecHdr& S, const double* Zs1, const double* Zs2, int ndim,
+                                              const Tile& t, int row, const double* tab, const double* ltab,
+                                              double (&res)[4], int& bad) {
     const int root = S.n_nodes - 1;
     if (S.node_kind[root] == NK_LEAF) {
         const int p = S.node_leaf[root];
-        leaf_vec(S.parts[p], Zs1 + p * ndim * kTile, Zs2 + p * ndim * kTile, ndim, t, tab, ltab, res, bad);
+        leaf_row(S.parts[p], Zs1 + p * ndim * kTile, Zs2 + p * ndim * kTile, ndim, t, row, tab, ltab, res, bad);
         return;
     }
     const int rkind = S.node_kind[root];
     const int* rc = S.child + S.node_child0[root];
-    double v[4][4];
+    double v[4];
     for (int c = 0; c < S.node_nchild[root]; ++c) {
         const int cn = rc[c];
         if (S.node_kind[cn] == NK_LEAF) {
             const int p = S.node_leaf[cn];
-            leaf_vec(S.parts[p], Zs1 + p * ndim * kTile, Zs2 + p * ndim * kTile, ndim, t, tab, ltab, v, bad);
-            vec_fold(res, v, rkind, c == 0);
+            leaf_row(S.parts[p], Zs1 + p * ndim * kTile, Zs2 + p * ndim * kTile, ndim, t, row, tab, ltab, v, bad);
+            row_fold(res, v, rkind, c == 0);
         } else {
-            double sub[4][4];
+            double sub[4];
             const int ckind = S.node_kind[cn];
             const int* gc = S.child + S.node_child0[cn];
             for (int g = 0; g < S.node_nchild[cn]; ++g) {
                 const int p = S.node_leaf[gc[g]];
-                leaf_vec(S.parts[p], Zs1 + p * ndim * kTile, Zs2 + p * ndim * kTile, ndim, t, tab, ltab, v, bad);
-                vec_fold(sub, v, ckind, g == 0);
+                leaf_row(S.parts[p], Zs1 + p * ndim * kTile, Zs2 + p * ndim * kTile, ndim, t, row, tab, ltab, v, bad);
+                row_fold(sub, v, ckind, g == 0);
             }
-            vec_fold(res, sub, rkind, c == 0);
+            row_fold(res, sub, rkind, c == 0);
         }
     }
 }
@@ -524,7 +547,7 @@ __device__ __noinline__ void slow_redo(const DevSpecHdr* S, const double* Zs1, c
 }
 
 template <int PTYPE, int MODE>
-__global__ void __launch_bounds__(kThreads, (MODE == 0 && is_fast_grad_type(PTYPE)) ? 4 : (MODE == 0 && (PTYPE == PGP_RQ || PTYPE == PGP_PERIODIC)) ? 3 : (MODE == 0 && PTYPE < 0) ? 2 : 1) gram_kernel(GramKArgs a) {
+__global__ void __launch_bounds__(kThreads, (MODE == 0 && is_fast_grad_type(PTYPE)) ? 4 : (MODE == 0 && (PTYPE == PGP_RQ || PTYPE == PGP_PERIODIC || PTYPE < 0)) ? 3 : 1) gram_kernel(GramKArgs a) {
     constexpr bool GRAD1 = MODE == 1;
     constexpr bool GRADX = MODE == 2;
     constexpr bool GRADXY = MODE == 3;      // composite path only (PTYPE < 0)
@@ -615,16 +638,16 @@ __global__ void __launch_bounds__(kThreads, (MODE == 0 && is_fast_grad_type(PTYP
     } else {
         bool interp = true;
         if (MODE == 0 && S->depth2) {
-            // vectorised composite: whole micro-tile per leaf, children folded in tree order
-            double res[4][4];
-            composite_vec(*S, sm.Zs1, sm.Zs2, ndim, t, sm.tab, sm.ltab, res, bad);
-#pragma unroll
+            // vectorised composite: one micro-tile row per leaf at a time, children folded in tree order
+#pragma unroll 1
             for (int x = 0; x < 4; ++x) {
-                if (diag_noise) add_noise_row(res[x], t, x, noise);
-                store_row<true>(out, a.ldo, 1, a.n1, a.n2, vec_ok, i0 + t.row(x), j0 + 2 * t.tx, res[x]);
+                double res[4];
+                composite_row(*S, sm.Zs1, sm.Zs2, ndim, t, t.row(x), sm.tab, sm.ltab, res, bad);
+                if (diag_noise) add_noise_row(res, t, x, noise);
+                store_row<true>(out, a.ldo, 1, a.n1, a.n2, vec_ok, i0 + t.row(x), j0 + 2 * t.tx, res);
                 if (mirror) {
 #pragma unroll
-                    for (int y = 0; y < 4; ++y) T[t.row(x) * TP + t.col(y)] = res[x][y];
+                    for (int y = 0; y < 4; ++y) T[t.row(x) * TP + t.col(y)] = res[y];
                 }
             }
             interp = bad != 0;      // a leaf left the fast exp's range: redo this thread's entries below
@@ -654,10 +677,7 @@ __global__ void __launch_bounds__(kThreads, (MODE == 0 && is_fast_grad_type(PTYP
                 } else if (GRAD1) {
                     r = composite_grad1(*S, z1, z2, gpart, gkind, gdim);
                 } else {
-                    PartVal pv[kMaxParts];
-                    double val[kMaxNodes];
-                    eval_parts<false>(*S, z1, z2, pv);
-                    r = tree_forward(*S, pv, val);
+                    r = composite_value_interp(*S, z1, z2);
                 }
                 // dynamic y: keep v[] in registers with a static store
                 if (y == 0) v[0] = r; else if (y == 1) v[1] = r; else if (y == 2) v[2] = r; else v[3] = r;
