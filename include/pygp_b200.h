@@ -191,6 +191,8 @@ int  pgp_dist_rank(const pgp_dist* d);
 int  pgp_dist_size(const pgp_dist* d);
 /* tuning: far block columns of the distributed factorisation are updated `group` panels at a time (0 = default) */
 int  pgp_dist_set_group(pgp_dist* d, int64_t group);
+/* tuning: a panel is updated, solved and broadcast in up to `chunks` row chunks, pipelined (0 = default) */
+int  pgp_dist_set_chunks(pgp_dist* d, int chunks);
 /* all-reduce of a short host vector (n <= 100) over the ranks; op: 0 sum, 1 max, 2 min */
 int  pgp_dist_allreduce(pgp_dist* d, double* x, int64_t n, int op);
 /* ExactGP._update (exact.py:50-55) on every rank's replica of the same model (same data, same

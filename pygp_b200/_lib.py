@@ -88,6 +88,7 @@ SIGNATURES = {
     'pgp_dist_rank': (C.c_int, [_vp]),
     'pgp_dist_size': (C.c_int, [_vp]),
     'pgp_dist_set_group': (C.c_int, [_vp, _i64]),
+    'pgp_dist_set_chunks': (C.c_int, [_vp, C.c_int]),
     'pgp_dist_allreduce': (C.c_int, [_vp, _dp, _i64, C.c_int]),
     'pgp_dist_exact_update': (C.c_int, [_vp, _vp, _dp, _i64]),
     'pgp_dist_exact_loglike': (C.c_int, [_vp, _vp, _i64, C.c_int, _dp, _dp]),

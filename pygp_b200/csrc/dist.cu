@@ -100,6 +100,7 @@ struct pgp_dist {
     size_t part_doubles = 0;
     double* d_sums = nullptr;               // kMaxHyper + 4
     int64_t group = 0;                      // trailing-update grouping (0: default)
+    int chunks = 0;                         // row chunks a panel travels in (0: default)
 };
 
 #define PGP_NCCL(d, call)                                                                      \
@@ -194,6 +195,13 @@ extern "C" int pgp_dist_set_group(pgp_dist* d, int64_t group) {
     return 0;
 }
 
+// tuning knob of pgp_dist_exact_update: a panel is updated, solved and broadcast in up to `chunks` row chunks (0 = default)
+extern "C" int pgp_dist_set_chunks(pgp_dist* d, int chunks) {
+    if (!d || chunks < 0) return PGP_E_ARG;
+    d->chunks = chunks;
+    return 0;
+}
+
 extern "C" int pgp_dist_rank(const pgp_dist* d) { return d ? d->rank : -1; }
 extern "C" int pgp_dist_size(const pgp_dist* d) { return d ? d->size : 0; }
 
@@ -279,14 +287,33 @@ extern "C" int pgp_dist_exact_update(pgp_dist* d, pgp_model* m, const double* hy
         PGP_TRY(dev_alloc(ctx, &d->d_Vs, (size_t)nb * nb));
         d->v_nb = nb;
     }
-    PGP_TRY(ensure_events(d, (size_t)6 * nblk + 2));
-    auto ev_packed = [&](int64_t k) { return d->events[6 * k]; };        // panel k packed (panel stream)
-    auto ev_bcast = [&](int64_t k) { return d->events[6 * k + 1]; };     // broadcast of panel k done (comm stream)
-    auto ev_unpacked = [&](int64_t k) { return d->events[6 * k + 2]; };  // panel k in the replicated factor (main)
-    auto ev_trail = [&](int64_t k) { return d->events[6 * k + 3]; };     // step k: panel k + 2 is up to date with panels <= k (main)
-    auto ev_fact = [&](int64_t k) { return d->events[6 * k + 4]; };      // panel k factored (panel stream)
-    auto ev_bulk = [&](int64_t k) { return d->events[6 * k + 5]; };      // rows below the diagonal block of panel k updated (bulk stream)
-    cudaEvent_t ev_start = d->events[6 * nblk];
+    // A panel travels in up to kMaxChunks row chunks (see `produce`); events per panel: packed / broadcast /
+    // rows-updated per chunk, then unpacked, trail, fact
+    constexpr int kMaxChunks = 8;
+    static const int chunks_env = [] { const char* e = getenv("PGP_DIST_CHUNKS"); return e ? atoi(e) : 0; }();
+    const int max_chunks = std::max(1, std::min(kMaxChunks, d->chunks > 0 ? d->chunks : chunks_env > 0 ? chunks_env : 4));
+    constexpr int kEvPer = 3 * kMaxChunks + 3;
+    PGP_TRY(ensure_events(d, (size_t)kEvPer * nblk + 2));
+    auto ev_packed = [&](int64_t k, int c) { return d->events[kEvPer * k + c]; };                   // chunk c of panel k solved (panel stream)
+    auto ev_bcast = [&](int64_t k, int c) { return d->events[kEvPer * k + kMaxChunks + c]; };       // ... broadcast (comm stream)
+    auto ev_bulk = [&](int64_t k, int c) { return d->events[kEvPer * k + 2 * kMaxChunks + c]; };    // ... its rows updated (bulk stream)
+    auto ev_unpacked = [&](int64_t k) { return d->events[kEvPer * k + 3 * kMaxChunks]; };           // panel k in the replicated factor
+    auto ev_trail = [&](int64_t k) { return d->events[kEvPer * k + 3 * kMaxChunks + 1]; };          // step k: panel k + 2 is up to date with panels <= k (main)
+    auto ev_fact = [&](int64_t k) { return d->events[kEvPer * k + 3 * kMaxChunks + 2]; };           // panel k factored and in the owner's F (panel stream)
+    cudaEvent_t ev_start = d->events[kEvPer * nblk];
+    // chunking of panel k: rows [0, rows) in nchunks(k) pieces of chunk_rows(k) rows; the first piece holds the
+    // diagonal block and the rows the next panel's update multiplies with (rows [nb, 2 nb)), so it is >= 2 nb
+    auto nchunks = [&](int64_t k) -> int {
+        const int64_t rows = n - cols.j0(k) + 1;
+        return (int)std::max<int64_t>(1, std::min<int64_t>(max_chunks, rows / (4 * nb)));
+    };
+    auto chunk_rows = [&](int64_t k) -> int64_t {
+        const int64_t rows = n - cols.j0(k) + 1;
+        return std::max<int64_t>(2 * nb, round_up(ceil_div(rows, (int64_t)nchunks(k)), 64));
+    };
+    auto chunk_lo = [&](int64_t k, int c) -> int64_t { return std::min<int64_t>(n - cols.j0(k) + 1, c * chunk_rows(k)); };
+    // chunk of panel k that holds its local row r
+    auto chunk_of = [&](int64_t k, int64_t r) -> int { return (int)std::min<int64_t>(nchunks(k) - 1, r / chunk_rows(k)); };
     // The panel chain (update of the next panel, its potrf, the pack) runs on a second, high-priority
     // stream P so that on the owner it overlaps the trailing updates of the same step (the single-GPU
     // lookahead of chol.cu, here across the panel broadcast as well).
@@ -377,46 +404,36 @@ extern "C" int pgp_dist_exact_update(pgp_dist* d, pgp_model* m, const double* hy
             PGP_CUDA(ctx, cudaEventRecord(ev_fact(k), P));
             return 0;
         }
+        // More than one rank.  The chain broadcast(k - 1) -> update(k) -> potrf -> solve -> broadcast(k) is a strict
+        // dependency, so it is PIPELINED IN ROW CHUNKS instead: the owner updates, solves and broadcasts its panel
+        // chunk by chunk, each chunk as soon as the chunk(s) of panel k - 1 it multiplies with have arrived, and the
+        // potrf + inverse of the diagonal block (first chunk only) run beside the update of the rows below.  Per
+        // panel the chain is then one chunk's broadcast + update + solve plus the ~0.45 ms potrf / inverse.
         double* buf = d->stage[k & 1];
+        const int nc = nchunks(k);
         if (owner == rank) {
             double* Fp = m->d_F + j0 * ld + j0;             // the panel in this rank's replica of the factor
-            PGP_CUDA(ctx, cudaStreamWaitEvent(P, k >= 2 ? ev_trail(k - 2) : ev_start, 0));   // main stream's updates of panel k
-            {
+            const double* prev = k >= 1 ? d->stage[(k - 1) & 1] + (j0 - cols.j0(k - 1)) * nb : nullptr;   // row 0 of panel k inside panel k - 1
+            const int64_t roff = k >= 1 ? j0 - cols.j0(k - 1) : 0;
+            cudaEvent_t ev_mine = k >= 2 ? ev_trail(k - 2) : ev_start;      // main stream's updates of panel k are done
+            PGP_CUDA(ctx, cudaStreamWaitEvent(P, ev_mine, 0));
+            PGP_CUDA(ctx, cudaStreamWaitEvent(Q, ev_mine, 0));
+            GemmArgs g;                                     // panel k -= P_{k-1}[rows] P_{k-1}[block k]^T, from the staging buffer
+            if (k >= 1) {
+                g.A = prev; g.lda = nb;
+                g.B = prev; g.ldb = nb;
+                g.C = Fp; g.ldc = ld;
+                g.N = w; g.K = cols.w(k - 1);
+                g.alpha = -1.0; g.beta = 1.0;
+            }
+            {   // diagonal block on the panel stream: update, potrf, inverse
                 Swap sw(ctx, P);
                 if (k >= 1) {
-                    // panel k -= P_{k-1}[rows >= j0] P_{k-1}[block k]^T, P_{k-1} read straight from the staging buffer it
-                    // was received into (dense, pitch nb): no wait for its unpacking into F.  Only the diagonal
-                    // block is updated on the panel stream; the rows below go to the bulk stream, so that the
-                    // potrf of the block and its inverse (~0.45 ms of small dependent kernels) run beside that GEMM
-                    // instead of after it.
-                    PGP_CUDA(ctx, cudaStreamWaitEvent(P, ev_bcast(k - 1), 0));
-                    const double* prev = d->stage[(k - 1) & 1] + (j0 - cols.j0(k - 1)) * nb;
-                    GemmArgs g;
-                    g.A = prev; g.lda = nb;
-                    g.B = prev; g.ldb = nb;
-                    g.C = Fp; g.ldc = ld;
-                    g.M = w; g.N = w; g.K = cols.w(k - 1);
-                    g.alpha = -1.0; g.beta = 1.0;
-                    g.tri = 1;
-                    PGP_TRY(launch_gemm_nt(ctx, g));
-                    if (rows > w) {
-                        PGP_CUDA(ctx, cudaStreamWaitEvent(Q, k >= 2 ? ev_trail(k - 2) : ev_start, 0));
-                        PGP_CUDA(ctx, cudaStreamWaitEvent(Q, ev_bcast(k - 1), 0));
-                        Swap sq(ctx, Q);
-                        GemmArgs gb = g;
-                        gb.A = prev + w * nb;
-                        gb.C = Fp + w * ld;
-                        gb.M = rows - w;
-                        gb.tri = 0;
-                        PGP_TRY(launch_gemm_nt(ctx, gb));
-                        PGP_CUDA(ctx, cudaEventRecord(ev_bulk(k), Q));
-                    }
-                    applied[k] = k;
+                    PGP_CUDA(ctx, cudaStreamWaitEvent(P, ev_bcast(k - 1, chunk_of(k - 1, roff + w - 1)), 0));
+                    GemmArgs gt = g;
+                    gt.M = w; gt.tri = 1;
+                    PGP_TRY(launch_gemm_nt(ctx, gt));
                 }
-                // L11 = chol(top w x w block) only; the rows below are solved as ONE GEMM with the explicit
-                // inverse V = L11^-T (w <= nb columns: 7 launches for the inverse) instead of riding through the
-                // 64-column leaf steps of the recursion (potrf_base + trsm_base + K <= 256 updates on all rows,
-                // ~2 ms per panel at ~8 TFLOP/s: it made every rank's panel work additive to its trailing updates)
                 Mat Pm, V, Vs;
                 Pm.p = Fp; Pm.ld = ld;
                 PGP_TRY(potrf_lower(ctx, Pm, w, 0, d->d_info + k));
@@ -425,48 +442,73 @@ extern "C" int pgp_dist_exact_update(pgp_dist* d, pgp_model* m, const double* hy
                 PGP_CUDA(ctx, cudaMemsetAsync(d->d_V, 0, sizeof(double) * nb * nb, P));
                 PGP_TRY(inv_upper(ctx, V, Pm, w, Vs));
                 if (k >= 2) PGP_CUDA(ctx, cudaStreamWaitEvent(P, ev_unpacked(k - 2), 0));      // staging slot free again
-                if (k >= 1 && rows > w) PGP_CUDA(ctx, cudaStreamWaitEvent(P, ev_bulk(k), 0));  // rows below are up to date
-                GemmArgs x;                                  // X = B V  ->  rows w.. of the staging buffer
-                x.A = Fp + w * ld; x.lda = ld;
-                x.B = d->d_V; x.ldb = nb; x.transB = 1; x.kcol = 1;
-                x.C = buf + w * nb; x.ldc = nb;
-                x.M = rows - w; x.N = w; x.K = w;
-                x.alpha = 1.0; x.beta = 0.0;
-                x.splitk = 1;
-                PGP_TRY(launch_gemm(ctx, x));
+                PGP_CUDA(ctx, cudaMemcpy2DAsync(buf, nb * 8, Fp, ld * 8, w * 8, w, cudaMemcpyDeviceToDevice, P));   // L11
             }
-            PGP_CUDA(ctx, cudaMemcpy2DAsync(buf, nb * 8, Fp, ld * 8, w * 8, w, cudaMemcpyDeviceToDevice, P));   // L11
-            PGP_CUDA(ctx, cudaEventRecord(ev_packed(k), P));
-            PGP_CUDA(ctx, cudaStreamWaitEvent(C, ev_packed(k), 0));
+            for (int c = 0; c < nc; ++c) {
+                const int64_t r_lo = std::max<int64_t>(chunk_lo(k, c), w), r_hi = chunk_lo(k, c + 1);   // rows below the block
+                if (k >= 1 && r_hi > r_lo) {   // their update on the bulk stream, once the rows of panel k - 1 they need are here
+                    PGP_CUDA(ctx, cudaStreamWaitEvent(Q, ev_bcast(k - 1, chunk_of(k - 1, roff + r_hi - 1)), 0));
+                    Swap sq(ctx, Q);
+                    GemmArgs gb = g;
+                    gb.A = prev + r_lo * nb;
+                    gb.C = Fp + r_lo * ld;
+                    gb.M = r_hi - r_lo;
+                    PGP_TRY(launch_gemm_nt(ctx, gb));
+                    PGP_CUDA(ctx, cudaEventRecord(ev_bulk(k, c), Q));
+                }
+                if (r_hi > r_lo) {             // solve them: X = B V, written densely into the staging buffer
+                    if (k >= 1) PGP_CUDA(ctx, cudaStreamWaitEvent(P, ev_bulk(k, c), 0));
+                    Swap sw(ctx, P);
+                    GemmArgs x;
+                    x.A = Fp + r_lo * ld; x.lda = ld;
+                    x.B = d->d_V; x.ldb = nb; x.transB = 1; x.kcol = 1;
+                    x.C = buf + r_lo * nb; x.ldc = nb;
+                    x.M = r_hi - r_lo; x.N = w; x.K = w;
+                    x.alpha = 1.0; x.beta = 0.0;
+                    x.splitk = 1;
+                    PGP_TRY(launch_gemm(ctx, x));
+                }
+                PGP_CUDA(ctx, cudaEventRecord(ev_packed(k, c), P));
+                PGP_CUDA(ctx, cudaStreamWaitEvent(C, ev_packed(k, c), 0));
+                const int64_t b_lo = chunk_lo(k, c), b_hi = chunk_lo(k, c + 1);
+                PGP_NCCL(d, g_nccl.Broadcast(buf + b_lo * nb, buf + b_lo * nb, (size_t)(b_hi - b_lo) * nb, ncclDouble, owner, d->comm, C));
+                PGP_CUDA(ctx, cudaEventRecord(ev_bcast(k, c), C));
+            }
+            if (k >= 1) applied[k] = k;
             // the owner's replica of the factor gets the solved rows off the chain
-            PGP_CUDA(ctx, cudaMemcpy2DAsync(Fp + w * ld, ld * 8, buf + w * nb, nb * 8, w * 8, rows - w, cudaMemcpyDeviceToDevice, P));
+            if (rows > w)
+                PGP_CUDA(ctx, cudaMemcpy2DAsync(Fp + w * ld, ld * 8, buf + w * nb, nb * 8, w * 8, rows - w, cudaMemcpyDeviceToDevice, P));
             PGP_CUDA(ctx, cudaEventRecord(ev_fact(k), P));
         } else {
-            // receiver: the slot was last used by panel k - 2 -- unpacked on the main stream, and read by this
-            // rank's own update of panel k - 1 if it owned that one
+            // receiver: the slot was last used by panel k - 2 -- unpacked on the copy stream, and read by this rank's
+            // own update of panel k - 1 if it owned that one
             if (k >= 2) PGP_CUDA(ctx, cudaStreamWaitEvent(C, ev_unpacked(k - 2), 0));
             if (k >= 1 && (int)((k - 1) % size) == rank) PGP_CUDA(ctx, cudaStreamWaitEvent(C, ev_fact(k - 1), 0));
+            for (int c = 0; c < nc; ++c) {
+                const int64_t b_lo = chunk_lo(k, c), b_hi = chunk_lo(k, c + 1);
+                PGP_NCCL(d, g_nccl.Broadcast(buf + b_lo * nb, buf + b_lo * nb, (size_t)(b_hi - b_lo) * nb, ncclDouble, owner, d->comm, C));
+                PGP_CUDA(ctx, cudaEventRecord(ev_bcast(k, c), C));
+            }
         }
-        PGP_NCCL(d, g_nccl.Broadcast(buf, buf, (size_t)rows * nb, ncclDouble, owner, d->comm, C));
-        PGP_CUDA(ctx, cudaEventRecord(ev_bcast(k), C));
         return 0;
     };
     // everybody: panel k is in the replicated factor before the main stream reads it.  Receivers unpack it on
-    // the copy stream: enqueued on the main stream the copy (and with it the release of the staging slot, and
-    // the whole chain) waited behind that stream's queued trailing updates -- tens of milliseconds once those
-    // are batched into one launch per step.
+    // the copy stream (chunk by chunk as it arrives): enqueued on the main stream the copy (and with it the release
+    // of the staging slot, and the whole chain) waited behind that stream's queued trailing updates -- tens of
+    // milliseconds once those are batched into one launch per step.
     auto consume = [&](int64_t k) -> int {
-        const int64_t j0 = cols.j0(k), w = cols.w(k), rows = n - j0 + 1;
-        if ((int)(k % size) == rank) {
+        const int64_t j0 = cols.j0(k), w = cols.w(k);
+        if (size == 1 || (int)(k % size) == rank) {
             PGP_CUDA(ctx, cudaStreamWaitEvent(S, ev_fact(k), 0));
             PGP_CUDA(ctx, cudaEventRecord(ev_unpacked(k), S));
         } else {
-            PGP_CUDA(ctx, cudaStreamWaitEvent(U, ev_bcast(k), 0));
-            // the region of F it lands in was last touched by the main stream's updates of panel k (step k - 2)
-            if (k >= 2) PGP_CUDA(ctx, cudaStreamWaitEvent(U, ev_trail(k - 2), 0));
-            else PGP_CUDA(ctx, cudaStreamWaitEvent(U, ev_start, 0));
-            PGP_CUDA(ctx, cudaMemcpy2DAsync(m->d_F + j0 * ld + j0, ld * 8, d->stage[k & 1], nb * 8, w * 8, rows,
-                                            cudaMemcpyDeviceToDevice, U));
+            const int nc = nchunks(k);
+            for (int c = 0; c < nc; ++c) {
+                const int64_t b_lo = chunk_lo(k, c), b_hi = chunk_lo(k, c + 1);
+                PGP_CUDA(ctx, cudaStreamWaitEvent(U, ev_bcast(k, c), 0));
+                PGP_CUDA(ctx, cudaMemcpy2DAsync(m->d_F + (j0 + b_lo) * ld + j0, ld * 8, d->stage[k & 1] + b_lo * nb, nb * 8, w * 8,
+                                                b_hi - b_lo, cudaMemcpyDeviceToDevice, U));
+            }
             PGP_CUDA(ctx, cudaEventRecord(ev_unpacked(k), U));
             PGP_CUDA(ctx, cudaStreamWaitEvent(S, ev_unpacked(k), 0));
         }

@@ -213,7 +213,7 @@ def communicator(group=None):
     return _comms[key]
 
 
-def distributed_update(gp, nb=512, group=None, group_size=0):
+def distributed_update(gp, nb=512, group=None, group_size=0, chunks=0):
     """`ExactGP._update` with the factorisation spread over the ranks of `group`.
     Every rank must hold the same model (data and hypers) and call this together.
     Afterwards the model on every rank is factored exactly as after `pgp_exact_update`;
@@ -224,6 +224,7 @@ def distributed_update(gp, nb=512, group=None, group_size=0):
     comm = communicator(group)
     hyp = _lib.as_f64(gp.get_hyper())
     _lib.check(comm.ctx, _lib.lib().pgp_dist_set_group(comm.handle, int(group_size)))   # 0: the library's default
+    _lib.check(comm.ctx, _lib.lib().pgp_dist_set_chunks(comm.handle, int(chunks)))
     _lib.check(comm.ctx, _lib.lib().pgp_dist_exact_update(comm.handle, gp._dev.handle, _lib.ptr(hyp), int(nb)))
     return gp
 

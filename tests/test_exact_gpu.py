@@ -201,6 +201,27 @@ def test_distributed_update_single_rank(N, nb):
     nt.assert_allclose(s2, s20, rtol=1e-9, atol=1e-12)
 
 
+def test_distributed_update_not_positive_definite():
+    """A matrix that is not positive definite comes back from the distributed path as the same LinAlgError
+    the one-GPU path raises (scipy.linalg.cholesky at exact.py:54), with the failing minor reported."""
+    import pygp_b200 as pygp
+    from pygp_b200.distchol import distributed_update
+    X, y, _ = synthetic_problem(300, 2, 0)
+    X[200] = X[10]                                   # duplicated input + (almost) no noise: singular K
+    gp = pygp.inference.ExactGP(pygp.likelihoods.Gaussian(0.1), pygp.kernels.SE(1.0, [0.5, 0.5]), 0.0)
+    gp.add_data(X, y)
+    gp._likelihood.set_hyper(np.array([np.log(1e-12)]))
+    with pytest.raises(np.linalg.LinAlgError):
+        distributed_update(gp, nb=64)
+    with pytest.raises(np.linalg.LinAlgError):
+        gp.set_hyper(gp.get_hyper())
+    gp._likelihood.set_hyper(np.array([np.log(0.1)]))   # and the model recovers on both paths
+    distributed_update(gp, nb=64)
+    lZ = gp.loglikelihood()
+    gp.set_hyper(gp.get_hyper())
+    nt.assert_allclose(gp.loglikelihood(), lZ, rtol=1e-12)
+
+
 def test_full_size_properties_n32768():
     """BASELINE configs[2] at full size (Matern-5/2 ARD d=16, N=32768), where the
     oracle cannot run (> 72 GiB): size-independent properties of the same

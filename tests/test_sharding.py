@@ -90,6 +90,20 @@ def _worker(rank, size, port, q):
         got = sharding.sharded_batched_loglike(gp, H[:1], local_fn=lz)
         nt.assert_array_equal(got, lz(H[:1]))
 
+        # values and gradients in one sharded call (multi-restart objective, optimization.py:54-62)
+        def lzg(hs):
+            out = []
+            for h in hs:
+                g = copy.deepcopy(gp)
+                g.set_hyper(h)
+                l, d = g.loglikelihood(True)
+                out.append(np.r_[l, d])
+            return np.array(out).reshape(len(hs), 1 + gp.nhyper)
+        l2, d2 = sharding.sharded_batched_loglike(gp, H, local_fn=lzg, grad=True)
+        ref = lzg(H)
+        nt.assert_array_equal(l2, ref[:, 0])
+        nt.assert_array_equal(d2, ref[:, 1:])
+
         # a failure on ONE rank (non-PD hyper slice) must surface on EVERY rank before the
         # all-reduces, as the same exception class, instead of leaving the others waiting
         def pred_bad(hs, x):

@@ -54,19 +54,20 @@ def main():
         g2.add_data(X, y)
         comm = distchol.communicator()
         for item in os.environ['PGP_DIST_SWEEP'].split(','):
-            nb_s, grp = (int(v) for v in item.split(':'))
+            vals = [int(v) for v in item.split(':')]
+            nb_s, grp, chk = vals[0], vals[1], (vals[2] if len(vals) > 2 else 0)
             os.environ['PGP_DIST_GROUP_NOW'] = str(grp)
             for rep in range(2):
                 dist.barrier()
                 torch.cuda.synchronize()
                 t0 = time.perf_counter()
-                distchol.distributed_update(g2, nb=nb_s, group_size=grp)
+                distchol.distributed_update(g2, nb=nb_s, group_size=grp, chunks=chk)
                 ctx.sync()
                 t_u = comm.allreduce([time.perf_counter() - t0], 'max')[0]
                 t0 = time.perf_counter()
                 lZs, dlZs = distchol.distributed_loglikelihood(g2, True, nb=nb_s)
                 t_g = comm.allreduce([time.perf_counter() - t0], 'max')[0]
-            say(check='dist_sweep', kernel=kern, n=n, world=world, nb=nb_s, group=grp, update_s=t_u, grad_s=t_g, lZ=lZs)
+            say(check='dist_sweep', kernel=kern, n=n, world=world, nb=nb_s, group=grp, chunks=chk, update_s=t_u, grad_s=t_g, lZ=lZs)
         dist.destroy_process_group()
         return
     gp = mk()
