@@ -13,8 +13,9 @@
 //                           the rank that owns J.  Per rank: 2 N^3 / (3 G) flops and an (N / G, N)
 //                           buffer instead of two (N, N) ones.
 //
-// The whole schedule is enqueued from C++ on two streams (compute + communication) with events; the
-// host never waits inside the loop (round 1 paced it from Python: one ctypes call and one
+// The whole schedule is enqueued from C++ on five streams (main: trailing updates; panel: diagonal block and
+// solves; bulk: update of the rows below a diagonal block; communication: NCCL; copy: unpacking) with events;
+// the host never waits inside the loop (round 1 paced it from Python: one ctypes call and one
 // torch.distributed.broadcast per panel).  pygp_b200/distchol.py keeps the schedule's numpy model for
 // the CPU (gloo) tests and is no longer on the product path.
 //
@@ -86,7 +87,7 @@ struct pgp_dist {
     cudaStream_t comm_stream = nullptr;
     cudaStream_t copy_stream = nullptr;     // unpacking of received panels, off the main stream
     cudaStream_t bulk_stream = nullptr;     // the owner's update of the rows below a panel's diagonal block
-    std::vector<cudaEvent_t> events;        // 3 per panel: packed, broadcast done, unpacked
+    std::vector<cudaEvent_t> events;        // per panel: packed / broadcast / rows-updated per chunk, unpacked, trail, fact
     double* stage[2] = {nullptr, nullptr};  // contiguous send / receive buffers of one panel
     size_t stage_doubles = 0;
     int* d_info = nullptr;                  // per-panel potrf info
