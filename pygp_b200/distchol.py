@@ -44,7 +44,7 @@ import numpy as np
 
 from . import sharding
 
-__all__ = ['block_columns', 'distributed_factor', 'gradient_partition_model', 'Communicator',
+__all__ = ['block_columns', 'distributed_factor', 'gradient_partition_model', 'staircase_solve_model', 'Communicator',
            'communicator', 'distributed_update', 'distributed_loglikelihood']
 
 
@@ -160,6 +160,81 @@ def gradient_partition_model(L, a, dK, sn2, nb, rank, size):
         for h, dk in enumerate(dK):
             S[1 + h] += np.sum(wgt*Q*dk[j0:, j0:j0 + w])
     return S
+
+
+def staircase_solve_model(L, nb, rank, size, a=None, leaf=64):
+    """numpy MODEL of the two staircase right-solves of `pgp_dist_exact_loglike` (csrc/chol.cu:
+    trsm_rec_stair / trsm_nt_rec_stair with csrc/chol.cuh: Stair), same recursion, same row counts.
+
+    The rows of B are (optionally) one dense front row `a` followed by this rank's rows of the identity:
+    block q belongs to global block column J = rank + q size and starts at column J nb.  Returns
+    (B, flops): after  B <- B L^-T  on the identity rows and  B <- B L^-1  on all rows, row r of block J
+    holds K~^-1[i, c(r)] at the columns i >= J nb, and the front row holds alpha^T = a^T L^-1.
+    `flops` counts the multiply-adds x 2 the recursion performs with every GEMM restricted to the rows
+    (and, for the first solve, the contraction range) the staircase allows."""
+    import scipy.linalg as sla
+    n = len(L)
+    blocks = [j for j in range(-(-n // nb)) if j % size == rank]
+    starts = [j*nb for j in blocks for _ in range(min(nb, n - j*nb))]
+    front = 0 if a is None else 1
+    B = np.zeros((front + len(starts), n))
+    if front:
+        B[0] = a
+    for r, j in enumerate([j*nb + i for j in blocks for i in range(min(nb, n - j*nb))]):
+        B[front + r, j] = 1.0
+    flops = [0.0]
+
+    def rows(c_end, fr, total):
+        nblk = -(-c_end // nb) if c_end > 0 else 0
+        mine = -(-(nblk - rank) // size) if nblk > rank else 0
+        return min(fr + mine*nb, total)
+
+    def split(m):
+        h = -(-(m // 2) // leaf)*leaf
+        h = leaf if h <= 0 else h
+        return m - leaf if h >= m else h
+
+    def lt(Bv, fr, j0, m):                      # Bv[:, j0:j0+m] <- Bv[:, j0:j0+m] L[j0.., j0..]^-T with earlier columns eliminated
+        total = len(Bv)
+        if m <= leaf:
+            r = rows(j0 + m, fr, total)
+            if r:
+                T = L[j0:j0 + m, j0:j0 + m]
+                Bv[:r, j0:j0 + m] = sla.solve_triangular(T, Bv[:r, j0:j0 + m].T, lower=True).T
+            return
+        m1 = split(m)
+        c0 = j0 + m1
+        lt(Bv, fr, j0, m1)
+        r = rows(c0, fr, total)
+        if r:
+            Bv[:r, c0:j0 + m] -= Bv[:r, j0:c0] @ L[c0:j0 + m, j0:c0].T
+            # contraction of row block q starts at its first column (GemmArgs::stair bit 1)
+            st = np.array([0]*fr + starts)[:r]
+            flops[0] += 2.0*np.sum(np.maximum(c0 - np.maximum(st, j0), 0))*(m - m1)
+        lt(Bv, fr, c0, m - m1)
+
+    def ln(Bv, fr, j0, m):                      # Bv[:, j0:j0+m] <- (. L^-1)[:, j0:j0+m], later columns first
+        total = len(Bv)
+        if m <= leaf:
+            r = rows(j0 + m, fr, total)
+            if r:
+                T = L[j0:j0 + m, j0:j0 + m]
+                Bv[:r, j0:j0 + m] = sla.solve_triangular(T, Bv[:r, j0:j0 + m].T, lower=True, trans=1).T
+            return
+        m1 = split(m)
+        c0 = j0 + m1
+        ln(Bv, fr, c0, m - m1)
+        r = rows(c0, fr, total)
+        if r:
+            Bv[:r, j0:c0] -= Bv[:r, c0:j0 + m] @ L[c0:j0 + m, j0:c0]
+            st = np.array([0]*fr + starts)[:r]
+            # output columns left of a row block's first column are skipped in 64-wide tiles (stair bit 2)
+            flops[0] += 2.0*np.sum(np.maximum(c0 - np.maximum(st, j0), 0))*(m - m1)
+        ln(Bv, fr, j0, m1)
+
+    lt(B[front:], 0, 0, n)
+    ln(B, front, 0, n)
+    return B, flops[0]
 
 
 class Communicator(object):

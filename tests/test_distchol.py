@@ -103,6 +103,35 @@ def test_gradient_partition_model(n, nb, size):
     nt.assert_allclose(S, want, rtol=1e-9, atol=1e-9*np.abs(want).max())
 
 
+@pytest.mark.parametrize('n,nb,size', [(300, 64, 1), (300, 64, 2), (500, 128, 3), (130, 64, 4), (257, 64, 2), (640, 128, 8)])
+def test_staircase_solve_model(n, nb, size):
+    """The staircase recursions of the distributed gradient (row counts per column range, contraction starts) give,
+    on every rank, the owned columns of K~^-1 at and below their diagonal and alpha -- including ranks that own
+    nothing (130 / 64 on 4 ranks) and ragged last blocks -- with n^3 / (3 size) flops per solve up to block effects."""
+    from pygp_b200.distchol import staircase_solve_model, block_columns
+    K, r = _problem(n, seed=3*n)
+    L = np.linalg.cholesky(K)
+    a = sla.solve_triangular(L, r, lower=True)
+    iK = np.linalg.inv(K)
+    alpha = iK @ r
+    total = 0.0
+    for rank in range(size):
+        B, fl = staircase_solve_model(L, nb, rank, size, a)
+        total += fl
+        nt.assert_allclose(B[0], alpha, rtol=1e-9, atol=1e-9*np.abs(alpha).max())
+        row = 1
+        for j, (j0, w) in enumerate(block_columns(n, nb)):
+            if j % size != rank:
+                continue
+            for i in range(w):
+                c = j0 + i
+                nt.assert_allclose(B[row, c:], iK[c:, c], rtol=1e-8, atol=1e-9*np.abs(iK).max())
+                row += 1
+        assert row == len(B)
+    # flops of the GEMM part over all ranks: two solves of ~n^3/3 each, never the rows x n^2 of a dense solve
+    assert total <= 2*(n**3/3.0)*1.0 + 4.0*n*n*nb
+
+
 def _free_port():
     s = socket.socket()
     s.bind(('127.0.0.1', 0))
