@@ -442,7 +442,12 @@ extern "C" int pgp_dist_exact_update(pgp_dist* d, pgp_model* m, const double* hy
                 Vs.p = d->d_Vs; Vs.ld = nb;
                 PGP_CUDA(ctx, cudaMemsetAsync(d->d_V, 0, sizeof(double) * nb * nb, P));
                 PGP_TRY(inv_upper(ctx, V, Pm, w, Vs));
-                if (k >= 2) PGP_CUDA(ctx, cudaStreamWaitEvent(P, ev_unpacked(k - 2), 0));      // staging slot free again
+                if (k >= 2) {
+                    // staging slot free again: panel k - 2 unpacked here (receiver) / its broadcast finished
+                    // reading the buffer (sender: the same rank owns k - 2 when there are two ranks)
+                    PGP_CUDA(ctx, cudaStreamWaitEvent(P, ev_unpacked(k - 2), 0));
+                    PGP_CUDA(ctx, cudaStreamWaitEvent(P, ev_bcast(k - 2, nchunks(k - 2) - 1), 0));
+                }
                 PGP_CUDA(ctx, cudaMemcpy2DAsync(buf, nb * 8, Fp, ld * 8, w * 8, w, cudaMemcpyDeviceToDevice, P));   // L11
             }
             for (int c = 0; c < nc; ++c) {
