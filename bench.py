@@ -525,7 +525,9 @@ def run_ours(args):
                    'what': 'SE + Periodic d=1, N=%d: ExactGP._update + loglikelihood(True); 1 GPU = pgp_exact_update / '
                            '_loglike, %d rank(s) = pgp_dist_exact_update / _loglike (block columns of %d, NCCL panel '
                            'broadcast, block-column gradient + one all-reduce)' % (n5, world, nb5)})
-        assert c5['lZ_rel_diff_vs_1gpu'] <= 1e-10 and c5['dlZ_rel_diff_vs_1gpu'] <= 1e-8, c5
+        # parity of the distributed evaluation with the one-GPU one, at the north-star tolerances: reported, not
+        # asserted (a benchmark line with `parity_ok: false` is worth more than no line; tests/test_multigpu.py asserts it)
+        c5['parity_ok'] = bool(c5['lZ_rel_diff_vs_1gpu'] <= 1e-10 and c5['dlZ_rel_diff_vs_1gpu'] <= 1e-8)
         extra['dist_chol_n65536'] = c5
         del g5
 
