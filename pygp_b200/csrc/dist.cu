@@ -385,7 +385,7 @@ extern "C" int pgp_dist_exact_update(pgp_dist* d, pgp_model* m, const double* hy
     //   potrf       of the top block only; the rows below as one GEMM with its explicit inverse, written
     //               DENSE (row pitch nb) into the staging buffer the panel is broadcast from: no pack step
     //   broadcast   from that buffer; the copy of the solved rows back into the owner's F follows off the chain.
-    // Measured on the way here (8 GPUs, N = 65536, nb = 512; profiles/r02_dist_*.txt): everything in place with
+    // Measured on the way here (8 GPUs, N = 65536, nb = 512; profiles/r02_dist8_c5_*.txt): everything in place with
     // pack after potrf and unpack before the next update 0.58 s; dense panels (pack first) 0.57 s; round 1's
     // Python-paced schedule 0.51 s.
     auto produce = [&](int64_t k) -> int {
