@@ -261,7 +261,7 @@ extern "C" int pgp_dist_exact_update(pgp_dist* d, pgp_model* m, const double* hy
     Cols cols{n, nb, ceil_div(n, nb)};
     const int64_t nblk = cols.nblk;
 
-    // workspaces: one info slot per panel, two panel staging buffers, 3 events per panel
+    // workspaces: one info slot per panel, two panel staging buffers, the inverse of a diagonal block + scratch
     if (d->info_cap < nblk) {
         PGP_CUDA(ctx, cudaStreamSynchronize(S));
         dev_free(ctx, d->d_info);
