@@ -201,6 +201,31 @@ def test_distributed_update_single_rank(N, nb):
     nt.assert_allclose(s2, s20, rtol=1e-9, atol=1e-12)
 
 
+def test_distributed_option_through_the_public_api():
+    """`ExactGP.distributed` (opt-in, here forced on a single rank): add_data / set_hyper / loglikelihood(True) /
+    posterior go through the block-column path and agree with the default path."""
+    import pygp_b200 as pygp
+    X, y, Xs = synthetic_problem(450, 3, 20)
+    spec = ('se', 1.0, [0.6, 0.7, 0.8])
+    mk = lambda: pygp.inference.ExactGP(pygp.likelihoods.Gaussian(0.1), product_kernel(spec), 0.0)
+    ref, gp = mk(), mk()
+    gp.distributed = {'nb': 128, 'min_n': 100, 'force': True}
+    ref.add_data(X, y)
+    gp.add_data(X, y)
+    h = ref.get_hyper() + 0.04
+    ref.set_hyper(h)
+    gp.set_hyper(h)
+    lZ0, dlZ0 = ref.loglikelihood(True)
+    lZ, dlZ = gp.loglikelihood(True)
+    nt.assert_allclose(lZ, lZ0, rtol=1e-11)
+    assert_grad_close(dlZ, dlZ0, rtol=1e-9)
+    nt.assert_allclose(gp.loglikelihood(), lZ0, rtol=1e-11)
+    mu, s2 = gp.posterior(Xs)
+    mu0, s20 = ref.posterior(Xs)
+    nt.assert_allclose(mu, mu0, rtol=1e-10, atol=1e-11)
+    nt.assert_allclose(s2, s20, rtol=1e-9, atol=1e-12)
+
+
 def test_distributed_update_not_positive_definite():
     """A matrix that is not positive definite comes back from the distributed path as the same LinAlgError
     the one-GPU path raises (scipy.linalg.cholesky at exact.py:54), with the failing minor reported."""
